@@ -1,0 +1,159 @@
+/* libv2f_b200 - C ABI of the B200 (sm_100a) hot path of the Visuelle 2.0 multimodal forecasters.
+ *
+ * Plain C: raw device pointers, sizes, a cudaStream_t passed as void*.  No torch types.
+ * Every function returns 0 (V2F_OK) or a negative error code; nothing allocates, creates
+ * streams or keeps global state.  All tensors are caller-allocated, contiguous row-major fp32
+ * (int64 for indices) unless stated, and 16-byte aligned.
+ *
+ * The reference (jeonghoya/visuelle2-multimodal-fusion) is pure Python: it has no FFI layer,
+ * its "plugin interface" for this path is the nn.Module surface of models/*.py.  Each entry
+ * point below therefore cites the reference lines whose arithmetic it replaces; the Python
+ * binding (ctypes) a maintainer adds is shown in INTEGRATION.md.
+ */
+#ifndef V2F_H_
+#define V2F_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define V2F_OK 0
+#define V2F_ERR_BAD_ARG (-1)
+#define V2F_ERR_ALIGN (-2)
+#define V2F_ERR_LAUNCH (-3)
+#define V2F_ERR_UNSUPPORTED (-4)
+
+/* ABI version; bumped whenever a struct layout or signature changes. */
+int v2f_version(void);
+/* Number of kernels launched by this library since load (bench.py's gpu_launches). */
+long long v2f_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Dense projections: C[b] = op(A[b]) op(B[b]) (+bias[n]) (+beta*C[b]), optional ReLU (act=1).
+ * ta=0: A stored [M,K]; ta=1: A stored [K,M].  tb=0: B stored [K,N]; tb=1: B stored [N,K].
+ * Replaces nn.Linear / autograd mm in e.g. models/CrossAttnRNN210.py:72 (ImageEncoder.fc),
+ * :84-85 (encoder_linear / decoder_linear), :196 (trend_linear), :208 (multimodal_embedder).
+ * fp32 CUDA-core kernel (exact mode, 1e-5 contract).                                        */
+int v2f_gemm_f32(int ta, int tb, int M, int N, int K, const float* A, int lda, long long strideA,
+                 const float* B, int ldb, long long strideB, float* C, int ldc, long long strideC,
+                 int batch, const float* bias, float beta, int act, void* stream);
+/* out[n] = sum_m X[m,n] (+beta*out[n]) : bias gradients. */
+int v2f_colsum_f32(int M, int N, const float* X, int ldx, float* out, float beta, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused recurrent-attention decoder (the hot loop):
+ *   CrossAttnRNN210.forward loop   models/CrossAttnRNN210.py:191-225   (variant 0)
+ *   CrossAttnRNN21 single fusion   models/CrossAttnRNN21.py:183-206    (variant 1)
+ *   CrossAttnRNNDemand loop        models/CrossAttnRNNDemand.py:285-347 (variant 2)
+ * with AdditiveAttention (CrossAttnRNN210.py:83-89 / CrossAttnRNNDemand.py:134-149), the
+ * nn.GRU decoder cell (CrossAttnRNN210.py:135-140,210-211), decoder_fc and the teacher-forcing
+ * select (:212-225).  Step-invariant projections are hoisted by the caller:
+ *   Himg = We_img V, Htr = We_tr Vtr, Ptr[j] = W_tl[:, jE:(j+1)E] Vtr[j], HMst = We_mm Mst.
+ * Row n belongs to item b = n / W.  E == A (attention_dim) is required, as in the reference.   */
+typedef struct v2f_decode_params {
+  int N, B, W, E, H, Li, Lt, T;
+  int variant;      /* 0: 210, 1: 21 (T must be 1, no GRU), 2: Demand */
+  int mod_mask;     /* bit0 date (always), bit1 image, bit2 attributes, bit3 trends */
+  unsigned tf_mask; /* bit t: decoder input of step t+1 is y[:,t] instead of yhat_t */
+  int reserved;
+  /* step-invariant tiles, per item */
+  const float *Himg, *Vimg; /* [B,Li,E] energies source / context source (Demand: Vimg == Himg) */
+  const float *Htr, *Ptr;   /* [B,Lt,E] */
+  const float *Mst, *HMst;  /* [B,2,E]: (date, attributes) and their We_mm projections */
+  const float *h0, *x0, *y; /* [N,H], [N], [N,T] (y may be NULL) */
+  /* weights, packed by the caller */
+  const float *Wcat, *bcat;        /* [3E+G,H],[3E+G]: rows = Wd_img,Wd_tr,Wd_mm,(W_hh); G=3H or 0 */
+  const float *w_att, *beta_att;   /* [3,E],[3]: attn_linear of img, trend, multimodal */
+  const float *b_tl;               /* [E] trend_linear.bias */
+  const float *We_mm;              /* [E,E] multimodal_attention.encoder_linear */
+  const float *W_me, *b_me;        /* [E,E],[E] multimodal_embedder */
+  const float *W_ihc, *w_x, *b_ih; /* [3H,E],[3H],[3H]: decoder GRU weight_ih split ctx | scalar */
+  const float *w_fc, *b_fc;        /* [H] (variant 1: [E]), [1] */
+  /* forward outputs and saved activations */
+  float *yhat;                             /* [N,T] */
+  float *h_all;                            /* [T+1,N,H] */
+  float *S_all;                            /* [T,N,3E+G] */
+  float *alpha_img, *alpha_tr, *alpha_mm;  /* [T,N,Li],[T,N,Lt],[T,N,4] */
+  float *C, *HC;                           /* [T,N,2,E] contexts (img,trend) and We_mm C */
+  float *U, *CTX;                          /* [T,N,E] */
+  float *GI;                               /* [N,3H] scratch */
+  float *RZN;                              /* [T,N,3H] */
+  float *xin;                              /* [T+1,N] decoder scalar inputs */
+  /* backward: inputs, scratch (zero-initialised where noted), outputs */
+  const float *dY;                         /* [N,T] dL/dyhat */
+  float *dh;                               /* [N,H] in: dL/dh_T (zeros); out: dL/dh_0 */
+  float *DScat;                            /* [T,N,3E+G] */
+  float *DGI;                              /* [T,N,3H] */
+  float *DCTX;                             /* [T,N,E] */
+  float *dU;                               /* [N,E] scratch */
+  float *DHC, *DC;                         /* [T,N,2,E] */
+  float *DE_img, *DE_tr;                   /* [T,N,Li],[T,N,Lt] */
+  float *DYH;                              /* [T,N] */
+  float *dxn;                              /* [N] scratch */
+  float *dw_acc;                           /* [N,3,E] zero-init */
+  float *dMst_acc, *dHMst_acc;             /* [N,2,E] zero-init */
+  float *dHimg, *dVimg, *dHtr, *dPtr;      /* tile gradients, written once */
+  float *dMst, *dHMst;                     /* [B,2,E] */
+  float *dWcat, *dbcat, *dw_att, *db_tl, *dWe_mm, *dW_me, *db_me, *dW_ihc, *dw_x, *db_ih,
+      *dw_fc, *db_fc;
+} v2f_decode_params;
+
+int v2f_decode_fwd(const v2f_decode_params* p, void* stream);
+int v2f_decode_bwd(const v2f_decode_params* p, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Single-layer batch-first GRU over a sequence (nn.GRU, gate order r,z,n):
+ *   TSEmbedder  models/CrossAttnRNN210.py:13-24  (52 steps, input 3)
+ *   sales_encoder_gru :123,182 / SalesEncoder models/GTM_Visuelle2.py:99-107 (2 steps, input 1)
+ * x [N,L,I]; h0 [N,H] or NULL (zeros); out [N,L,H]; saved RZN [L,N,3H], GHN [L,N,H];
+ * GI [N,L,3H] scratch.                                                                      */
+int v2f_gru_seq_fwd(int N, int L, int I, int H, const float* x, const float* h0,
+                    const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
+                    float* out, float* GI, float* GH, float* RZN, float* GHN, void* stream);
+/* dOut [N,L,H] (may be NULL), dhL [N,H] (may be NULL).  Scratch: dh [N,H], DGI [N,L,3H],
+ * DGH [L,N,3H], Hprev [L,N,H].  Outputs (any may be NULL): dx [N,L,I], dh0 [N,H], dw_ih, dw_hh,
+ * db_ih, db_hh.                                                                              */
+int v2f_gru_seq_bwd(int N, int L, int I, int H, const float* x, const float* h0,
+                    const float* w_ih, const float* w_hh, const float* out, const float* RZN,
+                    const float* GHN, const float* dOut, const float* dhL, float* dh, float* DGI,
+                    float* DGH, float* Hprev, float* dx, float* dh0, float* dw_ih, float* dw_hh,
+                    float* db_ih, float* db_hh, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Scaled-dot-product attention core for short sequences (Lq,Lk <= 64), one CTA per
+ * (batch, head): nn.MultiheadAttention ts_self_attention models/CrossAttnRNN210.py:126,176-179;
+ * nn.TransformerEncoder/DecoderLayer attention in models/GTM_Visuelle2.py:52-53,200-202.
+ * q/k/v/o are addressed as base + b*bstride + l*ld + head*hd.  mask: additive [Lq,Lk] or NULL.
+ * drop: [B,heads,Lq,Lk] multiplicative keep-mask already scaled by 1/(1-p), or NULL.
+ * P (saved softmax, before dropout): [B,heads,Lq,Lk].                                         */
+int v2f_sdpa_fwd(int B, int heads, int Lq, int Lk, int hd, const float* q, int ldq, long long bsq,
+                 const float* k, int ldk, long long bsk, const float* v, int ldv, long long bsv,
+                 float* o, int ldo, long long bso, const float* mask, const float* drop, float* P,
+                 float scale, void* stream);
+int v2f_sdpa_bwd(int B, int heads, int Lq, int Lk, int hd, const float* q, int ldq, long long bsq,
+                 const float* k, int ldk, long long bsk, const float* v, int ldv, long long bsv,
+                 const float* dO, int ldo, long long bso, const float* drop, const float* P,
+                 float* dq, int lddq, long long bsdq, float* dk, int lddk, long long bsdk, float* dv,
+                 int lddv, long long bsdv, float scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Static embedders: TemporalFeatureEncoder + AttributeEncoder, models/CrossAttnRNN210.py:26-56
+ * (Demand copy: CrossAttnRNNDemand.py:47-68 routes all four features through day_embedding:
+ * pass the day weights four times).  out [B,2,E] = (date, attributes).
+ * Wt,bt [4,E]; tables: 4 embedding tables [rows_k,E]; idx [4,B] int64; drop [B,8,E] keep-mask
+ * (already scaled) or NULL.                                                                  */
+int v2f_embed_fwd(int B, int E, const float* temporal, const float* Wt, const float* bt,
+                  const float* const* tables, const long long* idx, const float* drop, float* out,
+                  void* stream);
+int v2f_embed_bwd(int B, int E, const float* temporal, const long long* idx, const float* drop,
+                  const float* dout, const int* table_rows, float* dWt, float* dbt,
+                  float* const* dtables, void* stream);
+
+/* out = x * m : application of a dropout keep-mask (already scaled by 1/(1-p)); nn.Dropout in
+ * TSEmbedder / ImageEncoder, models/CrossAttnRNN210.py:21-24,67-72.                           */
+int v2f_mul_f32(long long n, const float* x, const float* m, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* V2F_H_ */

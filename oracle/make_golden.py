@@ -56,7 +56,7 @@ def case_rnn210(name, B, E, H, T, hw, tf, seed):
     loss = F.mse_loss(y.reshape(out.shape), out)
     loss.backward()
     grads, gfeat = _grads(m, feat)
-    return dict(model="CrossAttnRNN210", cfg=dict(E=E, A=E, H=H, T=T, B=B, tf=tf), state=_head_state(m),
+    return dict(model="CrossAttnRNN210", cfg=dict(E=E, A=E, H=H, T=T, B=B, tf=tf, seed=seed), state=_head_state(m),
                 inputs=dict(X=X, y=y, cat=cat, col=col, fab=fab, store=store, temporal=temporal,
                             gtrends=gt, feat=feat.detach()),
                 tf_mask=tf_mask, out=out.detach(), loss=loss.detach(), grads=grads, grad_feat=gfeat)
@@ -75,7 +75,7 @@ def case_rnn21(name, B, E, H, hw, seed):
     loss = F.mse_loss(y, out)
     loss.backward()
     grads, gfeat = _grads(m, feat)
-    return dict(model="CrossAttnRNN21", cfg=dict(E=E, A=E, H=H, T=1, B=B), state=_head_state(m),
+    return dict(model="CrossAttnRNN21", cfg=dict(E=E, A=E, H=H, T=1, B=B, seed=seed), state=_head_state(m),
                 inputs=dict(X=X, y=y, cat=cat, col=col, fab=fab, store=store, temporal=temporal,
                             gtrends=gt, feat=feat.detach()),
                 tf_mask=None, out=out.detach(), loss=loss.detach(), grads=grads, grad_feat=gfeat)
@@ -98,7 +98,7 @@ def case_demand(name, B, E, H, T, hw, tf, seed):
     loss = F.mse_loss(ts, out.squeeze())
     loss.backward()
     grads, gfeat = _grads(m, feat)
-    return dict(model="CrossAttnRNNDemand", cfg=dict(E=E, A=E, H=H, T=T, B=B, tf=tf), state=_head_state(m),
+    return dict(model="CrossAttnRNNDemand", cfg=dict(E=E, A=E, H=H, T=T, B=B, tf=tf, seed=seed), state=_head_state(m),
                 inputs=dict(ts=ts, cat=cat, col=col, fab=fab, store=store, temporal=temporal,
                             gtrends=gt, feat=feat.detach()),
                 tf_mask=tf_mask, out=out.detach(), img_alphas=torch.stack([a.detach() for a in img_a]),

@@ -55,3 +55,89 @@ def oracle_run(blob, requires_grad=True):
     else:
         raise KeyError(model)
     return out, loss, extras, P, feat
+
+
+# ------------------------------------------------------------------ product side (CUDA only)
+def product_model(blob, device="cuda"):
+    """The drop-in module for a golden blob, backbone replaced by identity, weights loaded."""
+    import torch.nn as nn
+    import visuelle2_multimodal_fusion_b200.synth as synth
+    from visuelle2_multimodal_fusion_b200.models import CrossAttnRNN21, CrossAttnRNN210, CrossAttnRNNDemand
+    import visuelle2_multimodal_fusion_b200.models.modules as mods
+    cfg, name = blob["cfg"], blob["model"]
+    cat_d, col_d, fab_d = synth.label_dicts()
+    orig = mods.resnet101_trunk
+    mods.resnet101_trunk = lambda: nn.Identity()       # goldens feed feature maps, not images
+    try:
+        if name == "CrossAttnRNN210":
+            m = CrossAttnRNN210.CrossAttnRNN(cfg["E"], cfg["E"], cfg["H"], cat_d, col_d, fab_d, synth.STORE_N, 3,
+                                             out_len=cfg["T"], use_teacher_forcing=cfg["tf"])
+        elif name == "CrossAttnRNN21":
+            m = CrossAttnRNN21.CrossAttnRNN(cfg["E"], cfg["E"], cfg["H"], cat_d, col_d, fab_d, synth.STORE_N, 3)
+        elif name == "CrossAttnRNNDemand":
+            m = CrossAttnRNNDemand.CrossAttnRNN(cfg["E"], cfg["E"], 3, cfg["H"], cat_d, col_d, fab_d,
+                                                synth.STORE_N, True, True, True, True, out_len=cfg["T"],
+                                                use_teacher_forcing=cfg["tf"])
+        else:
+            raise KeyError(name)
+    finally:
+        mods.resnet101_trunk = orig
+    missing, unexpected = m.load_state_dict(blob["state"], strict=False)
+    assert not unexpected, unexpected
+    assert all(k.startswith("image_encoder.cnn") for k in missing), missing
+    return m.to(device).eval()
+
+
+def product_run(m, blob, device="cuda"):
+    """forward + training loss + backward of the drop-in module on a blob's inputs."""
+    import torch.nn.functional as F
+    inp = {k: v.to(device) for k, v in blob["inputs"].items()}
+    feat = inp["feat"].clone().requires_grad_(True)
+    torch.manual_seed(blob["cfg"]["seed"] + 1)       # host teacher-forcing draws, as in make_golden
+    name = blob["model"]
+    extras = {}
+    if name == "CrossAttnRNNDemand":
+        out, ia, ma = m(inp["ts"], inp["cat"], inp["col"], inp["fab"], inp["store"], inp["temporal"],
+                        inp["gtrends"], feat)
+        extras = dict(img_alphas=torch.stack(ia), mm_alphas=torch.stack(ma))
+        loss = F.mse_loss(inp["ts"], out.squeeze())
+    else:
+        out, _ = m(inp["X"], inp["y"], inp["cat"], inp["col"], inp["fab"], inp["store"], inp["temporal"],
+                   inp["gtrends"], feat)
+        y = inp["y"]
+        loss = F.mse_loss(y.reshape(out.shape) if name == "CrossAttnRNN210" else y, out)
+    loss.backward()
+    grads = {k: p.grad for k, p in m.named_parameters()}
+    return out, loss, extras, grads, feat.grad
+
+
+def compare_blob(blob, tol, report=None):
+    """Compare the CUDA product against a golden blob; returns list of (what, rel_err, ok)."""
+    m = product_model(blob)
+    out, loss, extras, grads, gfeat = product_run(m, blob)
+    rows = []
+
+    def cmp(what, a, b):
+        a = a.detach().double().cpu()
+        b = b.detach().double().cpu()
+        diff = float((a - b).abs().max())
+        scale = float(b.abs().max())
+        ok = (a.shape == b.shape) and diff <= tol * scale + 1e-7
+        rows.append((what, diff / max(scale, 1e-30), scale, ok))
+
+    cmp("out", out, blob["out"])
+    cmp("loss", loss, blob["loss"])
+    for k, v in extras.items():
+        cmp(k, v, blob[k])
+    cmp("grad_feat", gfeat, blob["grad_feat"])
+    for k, g in blob["grads"].items():
+        if k.startswith("image_encoder.cnn"):
+            continue
+        mine = grads.get(k)
+        if g is None:
+            rows.append(("grad:" + k + " (none)", 0.0, 0.0, mine is None or float(mine.abs().max()) == 0.0))
+        elif mine is None:
+            rows.append(("grad:" + k + " MISSING", float("inf"), 0.0, False))
+        else:
+            cmp("grad:" + k, mine, g)
+    return rows

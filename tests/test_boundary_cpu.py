@@ -1,0 +1,92 @@
+"""CPU: the C-ABI library loads and exports every symbol include/v2f.h declares; the drop-in modules
+keep the reference's state_dict keys / shapes; the product refuses to compute without CUDA."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from helpers import load_golden
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "v2f.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(v2f_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from visuelle2_multimodal_fusion_b200 import build
+    lib = ctypes.CDLL(build.build())
+    names = _declared_symbols()
+    assert len(names) >= 12
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/v2f.h but not exported"
+    assert lib.v2f_version() == 1
+
+
+def test_decode_params_struct_matches_header():
+    """Field order of the ctypes mirror == field order of the C struct."""
+    from visuelle2_multimodal_fusion_b200._lib import DecodeParams
+    src = open(os.path.join(ROOT, "include", "v2f.h")).read()
+    body = src[src.index("typedef struct v2f_decode_params {"):src.index("} v2f_decode_params;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S).split("{", 1)[1]
+    fields = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        decl = re.sub(r"^(const\s+)?(unsigned|int|float)\s*", "", decl)
+        fields += [f.strip().lstrip("*").strip() for f in decl.split(",")]
+    assert fields == [f[0] for f in DecodeParams._fields_]
+
+
+@pytest.mark.parametrize("name", ["rnn210_small", "rnn21_small", "demand_small"])
+def test_state_dict_keys_match_reference(name):
+    from helpers import product_model
+    blob = load_golden(name)
+    m = product_model(blob, device="cpu")
+    mine = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    ref = {k: tuple(v.shape) for k, v in blob["state"].items()}
+    assert mine == ref
+
+
+def test_no_cpu_fallback():
+    from helpers import product_model, product_run
+    blob = load_golden("rnn210_notf")
+    m = product_model(blob, device="cpu")
+    with pytest.raises(RuntimeError, match="CUDA only"):
+        product_run(m, blob, device="cpu")
+
+
+def test_same_seed_same_init_as_reference():
+    """Construction order mirrors the reference => identical default initialisation under a seed."""
+    from oracle import refshim
+    if not refshim.reference_available():
+        pytest.skip("reference tree not mounted")
+    import torch.nn as nn
+    import visuelle2_multimodal_fusion_b200.synth as synth
+    import visuelle2_multimodal_fusion_b200.models.modules as mods
+    from visuelle2_multimodal_fusion_b200.models import CrossAttnRNN210
+    cat_d, col_d, fab_d = synth.label_dicts()
+    ref_mod = refshim.load_reference_module("CrossAttnRNN210")
+    import torchvision.models as tvm
+    orig_tv = tvm.resnet101
+    tvm.resnet101 = lambda *a, **k: nn.Sequential(nn.Identity(), nn.Identity(), nn.Identity())
+    orig = mods.resnet101_trunk
+    mods.resnet101_trunk = lambda: nn.Identity()
+    try:
+        torch.manual_seed(21)
+        r = ref_mod.CrossAttnRNN(32, 32, 48, cat_d, col_d, fab_d, synth.STORE_N, 3)
+        torch.manual_seed(21)
+        m = CrossAttnRNN210.CrossAttnRNN(32, 32, 48, cat_d, col_d, fab_d, synth.STORE_N, 3)
+    finally:
+        tvm.resnet101 = orig_tv
+        mods.resnet101_trunk = orig
+    rs, ms = r.state_dict(), m.state_dict()
+    assert set(rs) == set(ms)
+    for k in rs:
+        assert torch.equal(rs[k], ms[k]), k

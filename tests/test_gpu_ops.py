@@ -1,0 +1,140 @@
+"""GPU unit parity of the C-ABI primitives against plain torch / the oracle's explicit math."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def _rel(a, b):
+    return float((a.double().cpu() - b.double().cpu()).abs().max() / max(float(b.abs().max()), 1e-30))
+
+
+@pytest.mark.parametrize("ta,tb", [(0, 0), (0, 1), (1, 0), (1, 1)])
+@pytest.mark.parametrize("M,N,K", [(128, 512, 512), (37, 19, 53), (1, 7, 3), (200, 1, 1280), (64, 64, 16)])
+def test_gemm(ta, tb, M, N, K):
+    from visuelle2_multimodal_fusion_b200 import functional as Fv
+    g = torch.Generator().manual_seed(M * 131 + N * 7 + K)
+    A = torch.randn((K, M) if ta else (M, K), generator=g).cuda()
+    B = torch.randn((N, K) if tb else (K, N), generator=g).cuda()
+    bias = torch.randn(N, generator=g).cuda()
+    C0 = torch.randn(M, N, generator=g).cuda()
+    C = C0.clone()
+    Fv.gemm(ta, tb, M, N, K, A, A.shape[1], B, B.shape[1], C, N, bias=bias, beta=1.0)
+    ref = (A.t() if ta else A).double() @ (B.t() if tb else B).double() + bias.double() + C0.double()
+    assert _rel(C, ref) < TOL
+
+
+def test_gemm_batched_strided():
+    from visuelle2_multimodal_fusion_b200 import functional as Fv
+    g = torch.Generator().manual_seed(0)
+    B_, L, E, Eo = 5, 7, 32, 24
+    V = torch.randn(B_, L, E, generator=g).cuda().requires_grad_(True)
+    W = torch.randn(Eo, L * E, generator=g).cuda().requires_grad_(True)
+    P = Fv.trend_proj(V, W)
+    ref = torch.einsum("ble,ole->blo", V.double(), W.double().view(Eo, L, E))
+    assert _rel(P, ref) < TOL
+    # the identity the re-association rests on: trend_linear(vec(alpha_j V_j)) = sum_j alpha_j P_j
+    alpha = torch.rand(B_, L, generator=g).cuda()
+    lhs = (alpha.unsqueeze(2) * V).reshape(B_, -1) @ W.t()
+    rhs = (alpha.unsqueeze(2) * P).sum(1)
+    assert _rel(rhs, lhs) < TOL
+    dP = torch.randn(B_, L, Eo, generator=g).cuda()
+    P.backward(dP)
+    Vd, Wd = V.detach().double().requires_grad_(True), W.detach().double().requires_grad_(True)
+    torch.einsum("ble,ole->blo", Vd, Wd.view(Eo, L, E)).backward(dP.double())
+    assert _rel(V.grad, Vd.grad) < TOL and _rel(W.grad, Wd.grad) < TOL
+
+
+@pytest.mark.parametrize("N,L,I,H", [(5, 7, 3, 48), (128, 52, 3, 512), (9, 2, 1, 64)])
+def test_gru_seq(N, L, I, H):
+    from oracle import rnn as orc
+    from visuelle2_multimodal_fusion_b200 import functional as Fv
+    g = torch.Generator().manual_seed(N + L)
+    k = 1 / math.sqrt(H)
+    P = {"weight_ih_l0": (torch.rand(3 * H, I, generator=g) * 2 - 1) * k,
+         "weight_hh_l0": (torch.rand(3 * H, H, generator=g) * 2 - 1) * k,
+         "bias_ih_l0": (torch.rand(3 * H, generator=g) * 2 - 1) * k,
+         "bias_hh_l0": (torch.rand(3 * H, generator=g) * 2 - 1) * k}
+    x = torch.rand(N, L, I, generator=g)
+    h0 = torch.randn(N, H, generator=g) * 0.1
+    dOut = torch.randn(N, L, H, generator=g)
+    Pc = {k_: v.clone().requires_grad_(True) for k_, v in P.items()}
+    xc, hc = x.clone().requires_grad_(True), h0.clone().requires_grad_(True)
+    out_ref, _ = orc.gru_seq(xc, hc, Pc, "")
+    out_ref.backward(dOut)
+    Pg = {k_: v.cuda().requires_grad_(True) for k_, v in P.items()}
+    xg, hg = x.cuda().requires_grad_(True), h0.cuda().requires_grad_(True)
+    out = Fv.gru_seq(xg, hg, Pg["weight_ih_l0"], Pg["weight_hh_l0"], Pg["bias_ih_l0"], Pg["bias_hh_l0"])
+    out.backward(dOut.cuda())
+    assert _rel(out, out_ref) < TOL
+    assert _rel(xg.grad, xc.grad) < TOL and _rel(hg.grad, hc.grad) < TOL
+    for k_ in P:
+        assert _rel(Pg[k_].grad, Pc[k_].grad) < TOL, k_
+
+
+@pytest.mark.parametrize("B,L,E,heads,masked", [(3, 52, 32, 4, False), (4, 52, 512, 4, False), (2, 52, 64, 4, True)])
+def test_mha_self(B, L, E, heads, masked):
+    from oracle import rnn as orc
+    from visuelle2_multimodal_fusion_b200 import functional as Fv
+    g = torch.Generator().manual_seed(B + E)
+    k = 1 / math.sqrt(E)
+    P = {"in_proj_weight": torch.randn(3 * E, E, generator=g) * k, "in_proj_bias": torch.randn(3 * E, generator=g) * 0.1,
+         "out_proj.weight": torch.randn(E, E, generator=g) * k, "out_proj.bias": torch.randn(E, generator=g) * 0.1}
+    x = torch.randn(B, L, E, generator=g)
+    mask = None
+    if masked:
+        mask = torch.full((L, L), float("-inf"))
+        for i in range(0, L, 4):
+            mask[i:i + 4, i:i + 4] = 0.0
+    dO = torch.randn(B, L, E, generator=g)
+    Pc = {k_: v.clone().requires_grad_(True) for k_, v in P.items()}
+    xc = x.clone().requires_grad_(True)
+    ref = orc.mha_self(xc.permute(1, 0, 2), Pc, "", heads, 0.0, False, attn_mask=mask).permute(1, 0, 2)
+    ref.backward(dO)
+    Pg = {k_: v.cuda().requires_grad_(True) for k_, v in P.items()}
+    xg = x.cuda().requires_grad_(True)
+    out = Fv.mha_self(xg, Pg["in_proj_weight"], Pg["in_proj_bias"], Pg["out_proj.weight"], Pg["out_proj.bias"],
+                      heads, 0.0, False, mask=mask.cuda() if masked else None)
+    out.backward(dO.cuda())
+    assert _rel(out, ref) < TOL
+    assert _rel(xg.grad, xc.grad) < TOL
+    for k_ in P:
+        assert _rel(Pg[k_].grad, Pc[k_].grad) < TOL, k_
+
+
+def test_embed_with_mask_and_linear_relu():
+    from visuelle2_multimodal_fusion_b200 import functional as Fv
+    g = torch.Generator().manual_seed(1)
+    B, E = 9, 32
+    rows = [5, 3, 7, 11]
+    tables = [torch.randn(r, E, generator=g).cuda().requires_grad_(True) for r in rows]
+    idx = torch.stack([torch.randint(0, r, (B,), generator=g) for r in rows]).cuda()
+    temporal = torch.rand(B, 4, generator=g).cuda()
+    Wt = torch.randn(4, E, generator=g).cuda().requires_grad_(True)
+    bt = torch.randn(4, E, generator=g).cuda().requires_grad_(True)
+    drop = ((torch.rand(B, 8, E, generator=g) > 0.3).float() / 0.7).cuda()
+    out = Fv.embed(temporal, Wt, bt, tables, idx, drop)
+    d = sum(drop[:, k] * (temporal[:, k:k + 1] * Wt[k] + bt[k]) for k in range(4))
+    a = sum(drop[:, 4 + k] * tables[k][idx[k]] for k in range(4))
+    ref = torch.stack([d, a], 1)
+    assert _rel(out, ref) < TOL
+    dout = torch.randn(B, 2, E, generator=g).cuda()
+    gr = torch.autograd.grad(ref, [Wt, bt] + tables, dout, retain_graph=True)
+    gm = torch.autograd.grad(out, [Wt, bt] + tables, dout)
+    for x, y in zip(gm, gr):
+        assert _rel(x, y) < TOL
+    # linear + relu epilogue
+    x = torch.randn(17, 40, generator=g).cuda().requires_grad_(True)
+    W = torch.randn(24, 40, generator=g).cuda().requires_grad_(True)
+    b = torch.randn(24, generator=g).cuda().requires_grad_(True)
+    y = Fv.linear(x, W, b, act=1)
+    yr = torch.relu(x @ W.t() + b)
+    dy = torch.randn_like(y)
+    gm = torch.autograd.grad(y, [x, W, b], dy)
+    gr = torch.autograd.grad(yr, [x, W, b], dy)
+    assert _rel(y, yr) < TOL
+    for p, q in zip(gm, gr):
+        assert _rel(p, q) < TOL

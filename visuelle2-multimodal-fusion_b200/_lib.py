@@ -1,0 +1,103 @@
+"""ctypes binding of libv2f_b200.so (the C ABI declared in include/v2f.h).
+
+There is no CPU or eager fallback: if the shared library is missing, or a tensor is not a
+contiguous CUDA tensor of the expected dtype, the call raises.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libv2f_b200.so")
+ABI_VERSION = 1
+
+_lib = None
+
+c_int, c_ll, c_float, c_vp = ctypes.c_int, ctypes.c_longlong, ctypes.c_float, ctypes.c_void_p
+
+_ERRORS = {-1: "bad argument", -2: "pointer not 16-byte aligned", -3: "kernel launch failed",
+           -4: "unsupported size"}
+
+
+class DecodeParams(ctypes.Structure):
+    """Mirror of ``struct v2f_decode_params`` (include/v2f.h), field for field."""
+    _INTS = ["N", "B", "W", "E", "H", "Li", "Lt", "T", "variant", "mod_mask"]
+    _PTRS = ["Himg", "Vimg", "Htr", "Ptr", "Mst", "HMst", "h0", "x0", "y",
+             "Wcat", "bcat", "w_att", "beta_att", "b_tl", "We_mm", "W_me", "b_me", "W_ihc", "w_x",
+             "b_ih", "w_fc", "b_fc",
+             "yhat", "h_all", "S_all", "alpha_img", "alpha_tr", "alpha_mm", "C", "HC", "U", "CTX",
+             "GI", "RZN", "xin",
+             "dY", "dh", "DScat", "DGI", "DCTX", "dU", "DHC", "DC", "DE_img", "DE_tr", "DYH", "dxn",
+             "dw_acc", "dMst_acc", "dHMst_acc", "dHimg", "dVimg", "dHtr", "dPtr", "dMst", "dHMst",
+             "dWcat", "dbcat", "dw_att", "db_tl", "dWe_mm", "dW_me", "db_me", "dW_ihc", "dw_x",
+             "db_ih", "dw_fc", "db_fc"]
+    _fields_ = ([(n, c_int) for n in _INTS] + [("tf_mask", ctypes.c_uint), ("reserved", c_int)] +
+                [(n, c_vp) for n in _PTRS])
+
+
+def _declare(lib):
+    lib.v2f_version.restype = c_int
+    lib.v2f_launch_count.restype = c_ll
+    lib.v2f_gemm_f32.argtypes = [c_int, c_int, c_int, c_int, c_int, c_vp, c_int, c_ll, c_vp, c_int, c_ll,
+                                 c_vp, c_int, c_ll, c_int, c_vp, c_float, c_int, c_vp]
+    lib.v2f_colsum_f32.argtypes = [c_int, c_int, c_vp, c_int, c_vp, c_float, c_vp]
+    lib.v2f_mul_f32.argtypes = [c_ll, c_vp, c_vp, c_vp, c_vp]
+    lib.v2f_decode_fwd.argtypes = [ctypes.POINTER(DecodeParams), c_vp]
+    lib.v2f_decode_bwd.argtypes = [ctypes.POINTER(DecodeParams), c_vp]
+    lib.v2f_gru_seq_fwd.argtypes = [c_int] * 4 + [c_vp] * 11 + [c_vp]
+    lib.v2f_gru_seq_bwd.argtypes = [c_int] * 4 + [c_vp] * 19 + [c_vp]
+    sd = [c_int] * 5 + [c_vp, c_int, c_ll] * 3
+    lib.v2f_sdpa_fwd.argtypes = sd + [c_vp, c_int, c_ll, c_vp, c_vp, c_vp, c_float, c_vp]
+    lib.v2f_sdpa_bwd.argtypes = sd + [c_vp, c_int, c_ll, c_vp, c_vp] + [c_vp, c_int, c_ll] * 3 + [c_float, c_vp]
+    lib.v2f_embed_fwd.argtypes = [c_int, c_int, c_vp, c_vp, c_vp, ctypes.POINTER(c_vp), c_vp, c_vp, c_vp, c_vp]
+    lib.v2f_embed_bwd.argtypes = [c_int, c_int, c_vp, c_vp, c_vp, c_vp, ctypes.POINTER(c_int), c_vp, c_vp,
+                                  ctypes.POINTER(c_vp), c_vp]
+    for name in ("v2f_gemm_f32", "v2f_colsum_f32", "v2f_mul_f32", "v2f_decode_fwd", "v2f_decode_bwd",
+                 "v2f_gru_seq_fwd", "v2f_gru_seq_bwd", "v2f_sdpa_fwd", "v2f_sdpa_bwd", "v2f_embed_fwd",
+                 "v2f_embed_bwd"):
+        getattr(lib, name).restype = c_int
+
+
+def lib():
+    """The loaded library.  Raises (loudly) if it has not been built: there is no fallback."""
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python __graft_entry__.py` "
+                "(nvcc, sm_100a).  This package has no CPU / eager fallback.")
+        handle = ctypes.CDLL(LIB_PATH)
+        _declare(handle)
+        if handle.v2f_version() != ABI_VERSION:
+            raise RuntimeError("libv2f_b200.so ABI version mismatch; rebuild")
+        _lib = handle
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        raise RuntimeError(f"{what} failed: {_ERRORS.get(rc, rc)}")
+
+
+def ptr(t, dtype=torch.float32, allow_none=False):
+    """Device pointer of a contiguous CUDA tensor (or NULL)."""
+    if t is None:
+        if allow_none:
+            return None
+        raise ValueError("tensor required")
+    if not t.is_cuda:
+        raise RuntimeError("visuelle2-multimodal-fusion_b200 runs on CUDA only (got a CPU tensor)")
+    if t.dtype != dtype:
+        raise TypeError(f"expected {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError("tensor must be contiguous")
+    return t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def launch_count():
+    return int(lib().v2f_launch_count())

@@ -1,0 +1,92 @@
+"""Drop-in for the reference's ``models/CrossAttnRNN210.py`` (SO-fore2-10, the metric model).
+
+Same constructor, parameter names / state_dict keys, forward signature and Lightning hooks as
+``/root/reference/models/CrossAttnRNN210.py:95-286``; the body encodes every item once and runs
+the 10-step attention + GRU decoder as one fused CUDA region (``v2f_decode_fwd/bwd``)."""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import functional as Fv
+from ._base import LightningBase, current_lr, make_adafactor, wape_mae
+from ._crossattn import draw_teacher_forcing, encode_static, flatten_windows, run_decoder, sales_state
+from .modules import AdditiveAttention, AttributeEncoder, ImageEncoder, TemporalFeatureEncoder, TSEmbedder
+
+
+class CrossAttnRNN(LightningBase):
+    def __init__(self, attention_dim, embedding_dim, hidden_dim, cat_dict, col_dict, fab_dict, store_num,
+                 num_trends, use_img=True, out_len=10, use_teacher_forcing=True, teacher_forcing_ratio=0.5):
+        super().__init__()
+        self.save_hyperparameters()
+        if attention_dim != embedding_dim:
+            raise ValueError("attention_dim must equal embedding_dim (the reference's trend_linear and "
+                             "residual sum only type-check in that case)")
+        self.use_teacher_forcing = use_teacher_forcing
+        self.teacher_forcing_ratio = teacher_forcing_ratio
+        self.out_len = out_len
+        self.hidden_dim = hidden_dim
+        self.embedding_dim = embedding_dim
+        self.use_img = use_img
+        # same construction order as the reference => same default init under the same seed
+        self.image_encoder = ImageEncoder(embedding_dim)
+        self.trend_encoder = TSEmbedder(num_trends, embedding_dim)
+        self.temp_encoder = TemporalFeatureEncoder(embedding_dim)
+        self.attribute_encoder = AttributeEncoder(len(cat_dict) + 1, len(col_dict) + 1, len(fab_dict) + 1,
+                                                  store_num + 1, embedding_dim)
+        self.sales_encoder_gru = nn.GRU(input_size=1, hidden_size=hidden_dim, batch_first=True)
+        self.ts_self_attention = nn.MultiheadAttention(embedding_dim, num_heads=4, dropout=0.1)
+        self.ts_attention = AdditiveAttention(embedding_dim, hidden_dim, attention_dim)
+        self.trend_linear = nn.Linear(52 * attention_dim, embedding_dim)
+        self.img_attention = AdditiveAttention(embedding_dim, hidden_dim, attention_dim)
+        self.multimodal_attention = AdditiveAttention(embedding_dim, hidden_dim, attention_dim)
+        self.multimodal_embedder = nn.Linear(embedding_dim, embedding_dim)
+        self.decoder_gru = nn.GRU(input_size=embedding_dim + 1, hidden_size=hidden_dim, num_layers=1,
+                                  batch_first=True)
+        self.decoder_fc = nn.Linear(hidden_dim, 1)
+
+    def forward(self, X, y, categories, colors, fabrics, stores, temporal_features, gtrends, images):
+        X, y, bs, num_windows = flatten_windows(X, y)
+        tiles = encode_static(self, categories, colors, fabrics, stores, temporal_features, gtrends,
+                              images, by_proj=False)
+        h0 = sales_state(self, X)
+        x0 = X[:, -1, 0]
+        tf_mask = 0
+        if self.use_teacher_forcing and y is not None:
+            tf_mask = draw_teacher_forcing(self.out_len, self.teacher_forcing_ratio)
+        yhat, _, _ = run_decoder(self, Fv.VARIANT_210, num_windows, self.out_len, tf_mask, 0b1111, tiles,
+                                 h0, x0, y, self.decoder_gru, self.decoder_fc)
+        return yhat, None
+
+    # ---- Lightning hooks (models/CrossAttnRNN210.py:229-286)
+    def configure_optimizers(self):
+        return [make_adafactor(self.parameters())]
+
+    def on_train_epoch_start(self):
+        self.use_teacher_forcing = True
+
+    def on_validation_epoch_start(self):
+        self.use_teacher_forcing = False
+
+    def _step(self, batch):
+        (X, y, cat, col, fab, store, temp, gtrend), images = batch
+        forecasts, _ = self.forward(X, y, cat, col, fab, store, temp, gtrend, images)
+        if y.dim() == 3:
+            y = y.reshape(y.shape[0] * y.shape[1], y.shape[2])
+        return y, forecasts
+
+    def training_step(self, batch, batch_idx):
+        y, forecasts = self._step(batch)
+        loss = F.mse_loss(y, forecasts)
+        self.log("train_loss", loss)
+        return loss
+
+    def validation_step(self, batch, batch_idx):
+        return self._step(batch)
+
+    def validation_epoch_end(self, outputs):
+        gt = torch.cat([o[0] for o in outputs])
+        pred = torch.cat([o[1] for o in outputs])
+        mae, wape = wape_mae(gt, pred, abs_den=True)
+        self.log("val_mae", mae)
+        self.log("val_wWAPE", wape)
+        print(f"Validation MAE: {mae:.4f}, WAPE: {wape:.4f}, LR: {current_lr(self):.8f}")
