@@ -1,0 +1,377 @@
+"""Headline benchmark: CrossAttnRNN210 (SO-fore2-10) training step, fwd+bwd samples/s on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # reference algorithm on host cores
+
+One JSON line on stdout (rank 0).  A step = forward + mse_loss + backward + zero_grad of the
+whole model (torchvision ResNet-101 trunk + the fused head) on one synthetic VISUELLE2-shaped
+batch of 128 items per GPU (BASELINE.json configs[1]; optimizer excluded, as the metric says).
+``value``: inputs resident in HBM.  ``e2e``: the same step through the public LightningModule call
+(``training_step``) from pinned HOST buffers, host->device copies and the loss read-back inside
+the timed region.  ``roofline``: the fused recurrent-attention kernel timed with CUDA events on
+its launching stream in a separate pass (so the event records do not perturb ``value``).
+``cpu_baseline`` / ``--impl reference``: the oracle port (oracle/rnn.py, as-written algorithm) +
+torchvision trunk on the box's host cores, bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+E = A = H = 512          # train_dl.py:197-199
+OUT_LEN = 10
+LI, LT = 100, 52
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def _build_model(device, precision):
+    import visuelle2_multimodal_fusion_b200.synth as synth
+    from visuelle2_multimodal_fusion_b200.models.CrossAttnRNN210 import CrossAttnRNN
+    cat_d, col_d, fab_d = synth.label_dicts()
+    torch.manual_seed(21)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        m = CrossAttnRNN(A, E, H, cat_d, col_d, fab_d, synth.STORE_N, 3, use_img=True, out_len=OUT_LEN,
+                         use_teacher_forcing=True, teacher_forcing_ratio=0.5)
+    m = m.to(device).train()
+    m.on_train_epoch_start()
+    if precision == "bf16" and device != "cpu":
+        m.image_encoder.use_bf16_backbone(True)
+    return m
+
+
+def _batch(batch, seed, device=None, pin=False):
+    import visuelle2_multimodal_fusion_b200.synth as synth
+    data, images = synth.make_batch(batch, out_len=OUT_LEN, seed=seed)
+    if pin:
+        data = tuple(t.pin_memory() for t in data)
+        images = images.pin_memory()
+    if device is not None:
+        data = tuple(t.to(device) for t in data)
+        images = images.to(device)
+    return data, images
+
+
+def _nbytes(batch):
+    data, images = batch
+    return sum(t.numel() * t.element_size() for t in data) + images.numel() * images.element_size()
+
+
+class _Clocks:
+    """nvidia-smi sampled every 200 ms during the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "200"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.p.terminate()
+        self.p.wait()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                mx = float(c[2])
+            except ValueError:
+                continue
+            for nm, v in zip(names, c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        os.unlink(self.f.name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def _cpu_reference_step_fn(batch_items, threads):
+    """The reference's CPU implementation of the path: torchvision trunk + oracle head (as written),
+    train mode (dropout on, host teacher-forcing draws), fwd + mse + bwd + zero_grad."""
+    from oracle import rnn as orc
+    torch.set_num_threads(threads)
+    m = _build_model("cpu", "fp32")
+    cnn = m.image_encoder.cnn
+    P = {k: v for k, v in m.named_parameters() if not k.startswith("image_encoder.cnn")}
+    (X, y, cat, col, fab, store, temporal, gt), images = _batch(batch_items, seed=21)
+    params = [p for p in m.parameters() if p.requires_grad]
+
+    def step():
+        feat = cnn(images)
+        out, _ = orc.rnn210_forward(P, X, y, cat, col, fab, store, temporal, gt, feat, out_len=OUT_LEN,
+                                    use_teacher_forcing=True, teacher_forcing_ratio=0.5, training=True)
+        loss = torch.nn.functional.mse_loss(y.reshape(out.shape), out)
+        loss.backward()
+        for p in params:
+            p.grad = None
+        return float(loss.detach())
+
+    return step
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    sample = args.ref_batch
+    step = _cpu_reference_step_fn(sample, threads)
+    for _ in range(max(1, min(args.warmup, 2))):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    val = sample * args.steps / dt
+    desc = f"{sample} items/step (of the 128-item batch), full model incl. ResNet-101, fp32, {threads} threads"
+    print(json.dumps({
+        "impl": "reference", "metric": "train samples/sec (fwd+bwd) CrossAttnRNN210", "value": val,
+        "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+        "config": {"workload": "CrossAttnRNN210 SO-fore2-10 train step (BASELINE.json configs[1])",
+                   "per_gpu_batch": 128, "E": E, "A": A, "H": H, "out_len": OUT_LEN, "image": 299},
+        "cpu_baseline": {"value": val, "unit": "samples/s", "cores": threads, "kind": "port", "sample": desc},
+        "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def run_product(args):
+    import torch.distributed as dist
+    from visuelle2_multimodal_fusion_b200 import _lib
+    from visuelle2_multimodal_fusion_b200.ddp import GradReducer
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = f"cuda:{local}"
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+    B = args.batch
+    model = _build_model(dev, args.precision)
+    reducer = GradReducer(model) if world > 1 else None
+    # two distinct batches per rank, alternated: 137 MB of images each, larger than the 126 MB L2
+    host = [_batch(B, seed=21 + 1000 * rank + i, pin=True) for i in range(2)]
+    resident = [(tuple(t.to(dev) for t in d), im.to(dev)) for d, im in host]
+    h2d = _nbytes(host[0])
+    params = [p for p in model.parameters() if p.requires_grad]
+
+    def zero():
+        for p in params:
+            p.grad = None
+
+    def step_resident(i):
+        torch.manual_seed(1234 + i)          # same teacher-forcing draws on every rank
+        loss = model.training_step(resident[i & 1], i)
+        loss.backward()
+        if reducer:
+            reducer.finish()
+        zero()
+        return loss
+
+    def step_e2e(i):
+        torch.manual_seed(1234 + i)
+        d, im = host[i & 1]
+        batch = (tuple(t.to(dev, non_blocking=True) for t in d), im.to(dev, non_blocking=True))
+        loss = model.training_step(batch, i)
+        loss.backward()
+        if reducer:
+            reducer.finish()
+        zero()
+        return float(loss)                   # device->host read of the step's result
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms
+
+    for i in range(max(args.warmup, 3)):
+        step_resident(i)
+    clocks = _Clocks(local)
+    clocks.start()
+    l0 = _lib.launch_count()
+    ms = timed(step_resident, args.steps)
+    launches = _lib.launch_count() - l0
+    clk = clocks.stop()
+    for i in range(2):
+        step_e2e(i)
+    ms_e2e = timed(step_e2e, args.steps)
+
+    # ---- head-only figure (precomputed feature maps in), explains the roofline numbers
+    head_ms = None
+    roof = {}
+    if rank == 0 or world > 1:
+        feats = []
+        with torch.no_grad():
+            for d, im in resident:
+                f = model.image_encoder.cnn(im.contiguous(memory_format=torch.channels_last)
+                                            if args.precision == "bf16" else im)
+                feats.append(f.float().detach())
+        cnn = model.image_encoder.cnn
+        model.image_encoder.cnn = torch.nn.Identity()
+        saved_dtype = model.image_encoder.backbone_dtype
+        model.image_encoder.backbone_dtype = None
+
+        def step_head(i):
+            torch.manual_seed(1234 + i)
+            d, _ = resident[i & 1]
+            f = feats[i & 1].clone().requires_grad_(True)
+            loss = model.training_step((d, f), i)
+            loss.backward()
+            zero()
+
+        for i in range(3):
+            step_head(i)
+        head_ms = timed(step_head, args.steps)
+        # ---- roofline pass: CUDA events around every launch of the attention kernels
+        _lib.prof_enable(True)
+        nprof = min(args.steps, 5)
+        for i in range(nprof):
+            step_head(i)
+        torch.cuda.synchronize()
+        _lib.prof_enable(False)
+        peak, peak_src = _peaks()
+        N = B
+        tile_bytes = N * 4 * (2 * LI + 2 * LT) * E
+        small = N * 4 * (5 * H + LI + LT + 4)
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        tj = json.load(open(tpath)) if os.path.isfile(tpath) else {}
+        for name, kid, bytes_per_launch in (("attn_fwd_kernel", _lib.K_ATTN_FWD, tile_bytes + small),
+                                            ("attn_bwd_kernel", _lib.K_ATTN_BWD, tile_bytes + small),
+                                            ("tilegrad_kernel", _lib.K_TILEGRAD, None)):
+            tot, n = _lib.prof_read(kid)
+            if n == 0:
+                continue
+            avg_ms = tot / n
+            if name == "tilegrad_kernel":
+                # reads H once, writes dH and dV once; two launches (img, trend) per backward
+                bytes_per_launch = N * 4 * 3 * (LI + LT) * E / 2
+            ach = bytes_per_launch / (avg_ms * 1e-3) / 1e9
+            roof[name] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                          "traffic": tj.get(name), "kernel": name, "avg_launch_us": avg_ms * 1e3,
+                          "launches_per_step": n / nprof, "algorithmic_bytes_per_launch": bytes_per_launch,
+                          "peak_source": peak_src,
+                          "timing": "CUDA events on the launching stream around each launch, separate pass"}
+        model.image_encoder.cnn = cnn
+        model.image_encoder.backbone_dtype = saved_dtype
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        sample = args.ref_batch
+        step = _cpu_reference_step_fn(sample, threads)
+        step()
+        t0 = time.perf_counter()
+        n_it = 2
+        for _ in range(n_it):
+            step()
+        dt = (time.perf_counter() - t0) / n_it
+        cpu = {"value": sample / dt, "unit": "samples/s", "cores": threads, "kind": "port",
+               "sample": f"{sample} items/step of the same workload (full model incl. ResNet-101, fp32), "
+                         f"1 warm-up + {n_it} timed steps"}
+    if rank == 0:
+        total = B * world * args.steps
+        out = {
+            "metric": "train samples/sec (fwd+bwd) CrossAttnRNN210", "value": total / (ms * 1e-3),
+            "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if args.precision == "bf16" else "fp32", "data": "synthetic",
+            "config": {"workload": "CrossAttnRNN210 SO-fore2-10 train step (BASELINE.json configs[1]): "
+                                   "fwd + mse_loss + bwd + zero_grad, full model incl. ResNet-101 trunk",
+                       "per_gpu_batch": B, "global_batch": B * world, "E": E, "A": A, "H": H, "out_len": OUT_LEN,
+                       "image": 299, "parallelism": f"dp{world}",
+                       "precision": {"backbone": "bf16 autocast channels_last (torchvision/cuDNN, not replaced)"
+                                     if args.precision == "bf16" else "fp32",
+                                     "head": "fp32 CUDA kernels (libv2f_b200.so)"},
+                       "l2": "inputs larger than L2: two alternating batches, 137 MB of images each"},
+            "e2e": {"value": total / (ms_e2e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches, "gpu_launches_per_step": launches / args.steps,
+            "clocks": clk,
+            "head_only": {"value": (B * world * args.steps / (head_ms * 1e-3)) if head_ms else None,
+                          "unit": "samples/s", "ms_per_step": head_ms / args.steps if head_ms else None,
+                          "note": "feature maps [B,2048,10,10] in; everything libv2f_b200 covers"},
+            "roofline": roof.get("attn_fwd_kernel"),
+            "roofline_other": {k: v for k, v in roof.items() if k != "attn_fwd_kernel"},
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=128)
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--ref-batch", type=int, default=8, help="items per step of the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+        run_product(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -28,6 +28,13 @@ int v2f_version(void);
 /* Number of kernels launched by this library since load (bench.py's gpu_launches). */
 long long v2f_launch_count(void);
 
+/* Kernel ids for the optional event timing below. */
+enum { V2F_K_ATTN_FWD = 0, V2F_K_ATTN_BWD = 1, V2F_K_TILEGRAD = 2, V2F_K_COUNT = 3 };
+/* Per-kernel CUDA-event timing on the launching stream (bench.py roofline leg).  Off by default.
+ * v2f_prof_read sums the spans recorded for one kernel id since the previous read.            */
+int v2f_prof_enable(int on);
+int v2f_prof_read(int kernel_id, double* total_ms, long long* launches);
+
 /* ------------------------------------------------------------------------------------------
  * Dense projections: C[b] = op(A[b]) op(B[b]) (+bias[n]) (+beta*C[b]), optional ReLU (act=1).
  * ta=0: A stored [M,K]; ta=1: A stored [K,M].  tb=0: B stored [K,N]; tb=1: B stored [N,K].

@@ -63,4 +63,7 @@ def test_cuda_matches_oracle_default_dims(model, T):
         if p.grad is None:
             continue
         assert grads.get(k) is not None, k
-        assert_close(grads[k], p.grad, TOL, "grad:" + k, floor=1e-6 * float(p.grad.abs().max() + 1e-3))
+        # attn_linear.bias feeds a softmax, so its true gradient is exactly 0 (the kernel returns 0,
+        # autograd returns rounding noise): compare those absolutely
+        floor = 1e-6 if k.endswith("attn_linear.bias") else 1e-6 * float(p.grad.abs().max() + 1e-3)
+        assert_close(grads[k], p.grad, TOL, "grad:" + k, floor=floor)

@@ -53,7 +53,9 @@ def _declare(lib):
     lib.v2f_embed_fwd.argtypes = [c_int, c_int, c_vp, c_vp, c_vp, ctypes.POINTER(c_vp), c_vp, c_vp, c_vp, c_vp]
     lib.v2f_embed_bwd.argtypes = [c_int, c_int, c_vp, c_vp, c_vp, c_vp, ctypes.POINTER(c_int), c_vp, c_vp,
                                   ctypes.POINTER(c_vp), c_vp]
-    for name in ("v2f_gemm_f32", "v2f_colsum_f32", "v2f_mul_f32", "v2f_decode_fwd", "v2f_decode_bwd",
+    lib.v2f_prof_enable.argtypes = [c_int]
+    lib.v2f_prof_read.argtypes = [c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(c_ll)]
+    for name in ("v2f_prof_enable", "v2f_prof_read", "v2f_gemm_f32", "v2f_colsum_f32", "v2f_mul_f32", "v2f_decode_fwd", "v2f_decode_bwd",
                  "v2f_gru_seq_fwd", "v2f_gru_seq_bwd", "v2f_sdpa_fwd", "v2f_sdpa_bwd", "v2f_embed_fwd",
                  "v2f_embed_bwd"):
         getattr(lib, name).restype = c_int
@@ -101,3 +103,17 @@ def stream():
 
 def launch_count():
     return int(lib().v2f_launch_count())
+
+
+K_ATTN_FWD, K_ATTN_BWD, K_TILEGRAD = 0, 1, 2
+
+
+def prof_enable(on):
+    check(lib().v2f_prof_enable(1 if on else 0), "v2f_prof_enable")
+
+
+def prof_read(kernel_id):
+    """(total_ms, launches) of one kernel id since the previous read."""
+    ms, n = ctypes.c_double(0.0), c_ll(0)
+    check(lib().v2f_prof_read(kernel_id, ctypes.byref(ms), ctypes.byref(n)), "v2f_prof_read")
+    return ms.value, n.value

@@ -42,7 +42,7 @@ def build(force=False, verbose=False):
             sys.stderr.write(out)
         if pr.returncode != 0:
             raise RuntimeError("nvcc failed on " + src)
-    subprocess.check_call([nvcc, "-shared", "-o", LIB] + objs + ["-lcudart"])
+    subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB] + objs + ["-lcudart"])
     return LIB
 
 

@@ -28,6 +28,9 @@ extern long long g_v2f_launches;
 
 namespace v2f {
 
+void prof_begin(int id, cudaStream_t st);
+void prof_end(int id, cudaStream_t st);
+
 constexpr unsigned FULL = 0xffffffffu;
 
 __device__ __forceinline__ float warp_sum(float v) {

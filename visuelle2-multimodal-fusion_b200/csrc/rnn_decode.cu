@@ -654,7 +654,9 @@ extern "C" int v2f_decode_fwd(const v2f_decode_params* p, void* st) {
       AttnArgs a{N, p->W, E, p->Li, p->Lt, ldS, p->Himg, p->Vimg, p->Htr, p->Ptr, S, p->w_att,
                  p->beta_att, p->b_tl, C, p->alpha_img + (long long)t * N * p->Li,
                  p->alpha_tr + (long long)t * N * p->Lt, use_img ? 0 : 1};
+      prof_begin(V2F_K_ATTN_FWD, s);
       attn_fwd_kernel<<<dim3(N, (use_img ? 1 : 0) + (use_tr ? 1 : 0)), ATT_THREADS, smem, s>>>(a);
+      prof_end(V2F_K_ATTN_FWD, s);
       V2F_CHECK_LAUNCH();
       // HC = C We_mm^T  ([2N,E] view)
       GEMM(0, 1, 2 * N, E, E, C, E, p->We_mm, E, HC, E, nullptr, 0.f);
@@ -726,7 +728,9 @@ extern "C" int v2f_decode_bwd(const v2f_decode_params* p, void* st) {
                     p->alpha_img + (long long)t * N * p->Li, p->alpha_tr + (long long)t * N * p->Lt,
                     p->DE_img + (long long)t * N * p->Li, p->DE_tr + (long long)t * N * p->Lt, DS,
                     p->dw_acc, use_img ? 0 : 1};
+      prof_begin(V2F_K_ATTN_BWD, s);
       attn_bwd_kernel<<<dim3(N, (use_img ? 1 : 0) + (use_tr ? 1 : 0)), ATT_THREADS, smem, s>>>(a);
+      prof_end(V2F_K_ATTN_BWD, s);
       V2F_CHECK_LAUNCH();
     }
     // dh (+)= DS Wcat      (gru: dh holds the direct z-path part; else dh is overwritten)
@@ -768,7 +772,9 @@ extern "C" int v2f_decode_bwd(const v2f_decode_params* p, void* st) {
                     p->DC, mod ? p->dHtr : p->dHimg, mod ? p->dPtr : (byproj ? nullptr : p->dVimg)};
     // trend context always comes from Ptr (never from Htr), so byproj only affects the image tile
     if (mod) tg.byproj = 0;
+    prof_begin(V2F_K_TILEGRAD, s);
     tilegrad_kernel<<<dim3(B, (L + TG_J - 1) / TG_J), 256, 0, s>>>(tg);
+    prof_end(V2F_K_TILEGRAD, s);
     V2F_CHECK_LAUNCH();
   }
   const unsigned g2 = (unsigned)(((long long)B * 2 * E + 255) / 256);

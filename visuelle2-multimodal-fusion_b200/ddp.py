@@ -1,0 +1,108 @@
+"""Batch-sharded data parallelism: one process per GPU, bucketed gradient all-reduce overlapped
+with backward.
+
+The reference is single-process / single-GPU (``pl.Trainer(gpus=[n])``, train_dl.py:164-170); this
+layer is new.  Every item is independent in forward and backward, so the only
+exchange step is the gradient sum: parameters are grouped into ~25 MB buckets in reverse
+registration order (roughly the order their gradients become ready: the fused head first, the
+ResNet layers after it), each bucket is all-reduced on a side stream as soon as its last
+gradient has been accumulated, and ``finish()`` joins the side stream before the optimizer runs.
+``trend_linear.weight`` (54.5 MB fp32) exceeds the bucket size and travels alone.
+Parameters that receive no gradient (e.g. Demand's ``gate.fc.weight``) are skipped: the set is
+structural, hence identical on every rank, and their ``.grad`` stays ``None`` like in the reference.
+"""
+import torch
+import torch.distributed as dist
+
+
+def shard_batch(batch, rank, world):
+    """Contiguous shard of the leading (item) dimension of every tensor of a dataset_fusion.py batch
+    ``((t0, t1, ...), images)``; DistributedSampler-style without the sampler."""
+    data, images = batch
+
+    def cut(t):
+        n = t.shape[0]
+        per = n // world
+        return t[rank * per:(rank + 1) * per]
+
+    return tuple(cut(t) for t in data), cut(images)
+
+
+class GradReducer:
+    def __init__(self, module, bucket_bytes=25 << 20, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        params = [p for p in module.parameters() if p.requires_grad]
+        self.params = params[::-1]
+        self.buckets = []          # list of lists of params
+        cur, size = [], 0
+        for p in self.params:
+            nbytes = p.numel() * p.element_size()
+            if cur and size + nbytes > bucket_bytes:
+                self.buckets.append(cur)
+                cur, size = [], 0
+            cur.append(p)
+            size += nbytes
+        if cur:
+            self.buckets.append(cur)
+        self.bucket_of = {id(p): i for i, b in enumerate(self.buckets) for p in b}
+        self.cuda = any(p.is_cuda for p in params)
+        self.stream = torch.cuda.Stream() if self.cuda else None
+        self._reset()
+        self.hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in params]
+
+    def _reset(self):
+        self.pending = [len(b) for b in self.buckets]
+        self.launched = [False] * len(self.buckets)
+        self.work = []
+
+    def _on_grad(self, p):
+        if self.world == 1:
+            return
+        i = self.bucket_of[id(p)]
+        self.pending[i] -= 1
+        if self.pending[i] == 0:
+            self._launch(i)
+
+    def _launch(self, i):
+        self.launched[i] = True
+        ps = [p for p in self.buckets[i] if p.grad is not None]
+        if not ps:
+            return
+        if self.cuda:
+            self.stream.wait_stream(torch.cuda.current_stream())
+            ctx = torch.cuda.stream(self.stream)
+        else:
+            import contextlib
+            ctx = contextlib.nullcontext()
+        with ctx:
+            flat = torch.cat([p.grad.reshape(-1) for p in ps])
+            if self.cuda:
+                for p in ps:
+                    p.grad.record_stream(self.stream)
+            h = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+            self.work.append((h, flat, ps))
+
+    def finish(self):
+        """Join: launch buckets that never filled (unused parameters), wait, write the mean back."""
+        if self.world > 1:
+            for i in range(len(self.buckets)):
+                if not self.launched[i]:
+                    self._launch(i)
+            import contextlib
+            with (torch.cuda.stream(self.stream) if self.cuda else contextlib.nullcontext()):
+                for h, flat, ps in self.work:
+                    h.wait()                      # side stream waits for the collective
+                    flat.div_(self.world)
+                    off = 0
+                    for p in ps:
+                        n = p.numel()
+                        p.grad.copy_(flat[off:off + n].view_as(p.grad))
+                        off += n
+            if self.cuda:
+                torch.cuda.current_stream().wait_stream(self.stream)
+        self._reset()
+
+    def remove(self):
+        for h in self.hooks:
+            h.remove()

@@ -83,9 +83,20 @@ class ImageEncoder(nn.Module):
         self.cnn = resnet101_trunk()
         self.fc = nn.Linear(2048, embedding_dim)
         self.dropout = nn.Dropout(0.1)
+        self.backbone_dtype = None       # torch.bfloat16 -> run the torchvision trunk under autocast
+
+    def use_bf16_backbone(self, on=True):
+        """bf16 autocast + channels_last for the (unreplaced) torchvision/cuDNN trunk."""
+        self.backbone_dtype = torch.bfloat16 if on else None
+        self.cnn.to(memory_format=torch.channels_last if on else torch.contiguous_format)
+        return self
 
     def forward(self, x):
-        feat = self.cnn(x)
+        if self.backbone_dtype is not None and x.dim() == 4 and x.shape[1] == 3:
+            with torch.autocast("cuda", dtype=self.backbone_dtype):
+                feat = self.cnn(x.contiguous(memory_format=torch.channels_last))
+        else:
+            feat = self.cnn(x)
         B, C = feat.shape[0], feat.shape[1]
         rows = feat.permute(0, 2, 3, 1).reshape(B, -1, C)      # view when the trunk ran channels_last
         v = Fv.linear(rows.float(), self.fc.weight, self.fc.bias)
