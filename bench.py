@@ -55,6 +55,7 @@ def _build_model(device, precision):
     m.on_train_epoch_start()
     if precision == "bf16" and device != "cpu":
         m.image_encoder.use_bf16_backbone(True)
+        m.precision = "bf16"
     return m
 
 
@@ -336,7 +337,8 @@ def run_product(args):
                        "image": 299, "parallelism": f"dp{world}",
                        "precision": {"backbone": "bf16 autocast channels_last (torchvision/cuDNN, not replaced)"
                                      if args.precision == "bf16" else "fp32",
-                                     "head": "fp32 CUDA kernels (libv2f_b200.so)"},
+                                     "head": ("tcgen05 GEMMs: bf16 on backbone features, tf32 elsewhere; fp32 state, softmax and gates"
+                                              if args.precision == "bf16" else "fp32 CUDA-core kernels") + " (libv2f_b200.so)"},
                        "l2": "inputs larger than L2: two alternating batches, 137 MB of images each"},
             "e2e": {"value": total / (ms_e2e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},

@@ -44,6 +44,24 @@ int v2f_prof_read(int kernel_id, double* total_ms, long long* launches);
 int v2f_gemm_f32(int ta, int tb, int M, int N, int K, const float* A, int lda, long long strideA,
                  const float* B, int ldb, long long strideB, float* C, int ldc, long long strideC,
                  int batch, const float* bias, float beta, int act, void* stream);
+/* Tensor-core variant (tcgen05.mma, TMEM accumulator, TMA-staged 128B-swizzled operands):
+ *   C[M,N] (fp32) = A[M,K] B[N,K]^T (+bias) (+beta C) (ReLU), both operands K-major.
+ * kind 0: A,B bf16; kind 1: A,B fp32 consumed as tf32.  lda/ldb/ldc in elements; A,B 16-byte
+ * aligned with 16-byte-multiple row pitch.  splits>1: split-K, partial sums added atomically
+ * onto C (pre-zeroed by the caller; beta/act not applied).  Same reference call sites as
+ * v2f_gemm_f32; this is the performance path (2e-2 contract).                                 */
+int v2f_gemm_tc(int kind, int M, int N, int K, const void* A, long long lda, const void* B,
+                long long ldb, float* C, long long ldc, const float* bias, float beta, int act,
+                int splits, void* stream);
+int v2f_gemm_tc_batched(int kind, int M, int N, int K, const void* A, long long lda, long long strideA,
+                        const void* B, long long ldb, long long strideB, float* C, long long ldc,
+                        long long strideC, int batch, const float* bias, float beta, int act, int splits,
+                        void* stream);
+/* Operand preparation for the K-major form: fp32->bf16 cast, and out[cols,rows] = in[rows,cols]^T
+ * with optional conversion (kind 0 = bf16, 1 = fp32).                                         */
+int v2f_cast_bf16(long long n, const float* x, void* out, void* stream);
+int v2f_transpose(int rows, int cols, const void* in, long long ld, int in_kind, void* out,
+                  long long ldo, int out_kind, void* stream);
 /* out[n] = sum_m X[m,n] (+beta*out[n]) : bias gradients. */
 int v2f_colsum_f32(int M, int N, const float* X, int ldx, float* out, float beta, void* stream);
 
@@ -62,7 +80,7 @@ typedef struct v2f_decode_params {
   int variant;      /* 0: 210, 1: 21 (T must be 1, no GRU), 2: Demand */
   int mod_mask;     /* bit0 date (always), bit1 image, bit2 attributes, bit3 trends */
   unsigned tf_mask; /* bit t: decoder input of step t+1 is y[:,t] instead of yhat_t */
-  int reserved;
+  int precision;    /* 0: fp32 CUDA-core GEMMs (exact); 1: tf32 tcgen05 GEMMs for the per-step products */
   /* step-invariant tiles, per item */
   const float *Himg, *Vimg; /* [B,Li,E] energies source / context source (Demand: Vimg == Himg) */
   const float *Htr, *Ptr;   /* [B,Lt,E] */
@@ -103,6 +121,10 @@ typedef struct v2f_decode_params {
   float *dMst, *dHMst;                     /* [B,2,E] */
   float *dWcat, *dbcat, *dw_att, *db_tl, *dWe_mm, *dW_me, *db_me, *dW_ihc, *dw_x, *db_ih,
       *dw_fc, *db_fc;
+  /* precision 1 only (backward): scratch for transposed weights [H,3E+G],[E,3H],[E,E],[E,E] and
+   * for transposed activation stacks of the weight-gradient products                          */
+  float *WcatT, *W_ihcT, *W_meT, *We_mmT, *ws;
+  long long ws_floats;
 } v2f_decode_params;
 
 int v2f_decode_fwd(const v2f_decode_params* p, void* stream);
@@ -113,10 +135,12 @@ int v2f_decode_bwd(const v2f_decode_params* p, void* stream);
  *   TSEmbedder  models/CrossAttnRNN210.py:13-24  (52 steps, input 3)
  *   sales_encoder_gru :123,182 / SalesEncoder models/GTM_Visuelle2.py:99-107 (2 steps, input 1)
  * x [N,L,I]; h0 [N,H] or NULL (zeros); out [N,L,H]; saved RZN [L,N,3H], GHN [L,N,H];
- * GI [N,L,3H] scratch.                                                                      */
+ * GI [N,L,3H] scratch.  precision 0: fp32 CUDA-core products; 1: tf32 tcgen05 products (bwd then
+ * needs scratch w_hhT [H,3H] and ws for transposed stacks).                                   */
 int v2f_gru_seq_fwd(int N, int L, int I, int H, const float* x, const float* h0,
                     const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
-                    float* out, float* GI, float* GH, float* RZN, float* GHN, void* stream);
+                    float* out, float* GI, float* GH, float* RZN, float* GHN, int precision,
+                    void* stream);
 /* dOut [N,L,H] (may be NULL), dhL [N,H] (may be NULL).  Scratch: dh [N,H], DGI [N,L,3H],
  * DGH [L,N,3H], Hprev [L,N,H].  Outputs (any may be NULL): dx [N,L,I], dh0 [N,H], dw_ih, dw_hh,
  * db_ih, db_hh.                                                                              */
@@ -124,7 +148,8 @@ int v2f_gru_seq_bwd(int N, int L, int I, int H, const float* x, const float* h0,
                     const float* w_ih, const float* w_hh, const float* out, const float* RZN,
                     const float* GHN, const float* dOut, const float* dhL, float* dh, float* DGI,
                     float* DGH, float* Hprev, float* dx, float* dh0, float* dw_ih, float* dw_hh,
-                    float* db_ih, float* db_hh, void* stream);
+                    float* db_ih, float* db_hh, float* w_hhT, float* ws, long long ws_floats,
+                    int precision, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Scaled-dot-product attention core for short sequences (Lq,Lk <= 64), one CTA per

@@ -39,7 +39,7 @@ def test_decode_params_struct_matches_header():
         decl = decl.strip()
         if not decl:
             continue
-        decl = re.sub(r"^(const\s+)?(unsigned|int|float)\s*", "", decl)
+        decl = re.sub(r"^(const\s+)?(unsigned|int|float|long long)\s*", "", decl)
         fields += [f.strip().lstrip("*").strip() for f in decl.split(",")]
     assert fields == [f[0] for f in DecodeParams._fields_]
 

@@ -138,3 +138,46 @@ def test_embed_with_mask_and_linear_relu():
     assert _rel(y, yr) < TOL
     for p, q in zip(gm, gr):
         assert _rel(p, q) < TOL
+
+
+@pytest.mark.parametrize("kind", [0, 1])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (128, 3072, 512), (12800, 512, 2048), (300, 200, 520),
+                                   (77, 48, 40), (256, 512, 512), (128, 1536, 1536)])
+def test_gemm_tc(kind, M, N, K):
+    """tcgen05 GEMM vs an fp64 matmul of the operands as the tensor core sees them
+    (bf16-rounded, resp. tf32-truncated): only the fp32 accumulation order differs."""
+    from visuelle2_multimodal_fusion_b200 import functional as Fv
+    g = torch.Generator().manual_seed(M + N + K + kind)
+    A = torch.randn(M, K, generator=g).cuda()
+    B = torch.randn(N, K, generator=g).cuda()
+    bias = torch.randn(N, generator=g).cuda()
+    C0 = torch.randn(M, N, generator=g).cuda()
+    C = C0.clone()
+    if kind == 0:
+        Ab, Bb = Fv.cast_bf16(A), Fv.cast_bf16(B)
+        assert torch.equal(Ab, A.bfloat16()) and torch.equal(Bb, B.bfloat16())
+        Fv.gemm_tc(0, M, N, K, Ab, K, Bb, K, C, N, bias=bias, beta=1.0)
+        Ar, Br = Ab.double(), Bb.double()
+    else:
+        Fv.gemm_tc(1, M, N, K, A, K, B, K, C, N, bias=bias, beta=1.0)
+        trunc = lambda t: (t.view(torch.int32) & ~0x1FFF).view(torch.float32).double()
+        Ar, Br = trunc(A), trunc(B)
+    torch.cuda.synchronize()
+    ref = Ar @ Br.t() + bias.double() + C0.double()
+    assert _rel(C, ref) < 2e-5
+
+
+def test_gemm_tc_splitk_and_transpose():
+    from visuelle2_multimodal_fusion_b200 import functional as Fv
+    g = torch.Generator().manual_seed(5)
+    M, N, K = 512, 2048, 12800
+    dy = torch.randn(K, M, generator=g).cuda()          # [rows, M]
+    x = torch.randn(K, N, generator=g).cuda().bfloat16()  # [rows, N] bf16
+    dyT = Fv.transpose2d(dy, torch.bfloat16)             # [M, K]
+    xT = Fv.transpose2d(x)                               # [N, K]
+    assert torch.equal(dyT, dy.t().contiguous().bfloat16()) and torch.equal(xT, x.t().contiguous())
+    C = torch.zeros(M, N, device="cuda")
+    Fv.gemm_tc(0, M, N, K, dyT, K, xT, K, C, N, splits=4)
+    torch.cuda.synchronize()
+    ref = dyT.double() @ xT.double().t()
+    assert _rel(C, ref) < 2e-5

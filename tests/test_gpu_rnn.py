@@ -10,6 +10,16 @@ TOL = 1e-5
 RNN_CASES = ["rnn210_small", "rnn210_notf", "rnn21_small", "demand_small", "demand_notf"]
 
 
+TOL_TC = 2e-2   # bf16/tf32 tensor-core path (BASELINE.json north_star)
+
+
+@pytest.mark.parametrize("name", RNN_CASES)
+def test_cuda_tensorcore_path_matches_reference_golden(name):
+    rows = compare_blob(load_golden(name), TOL_TC, precision="bf16")
+    bad = [r for r in rows if not r[3]]
+    assert not bad, "\n".join(f"{w}: rel={e:.3e} scale={s:.3e}" for w, e, s, _ in bad)
+
+
 @pytest.mark.parametrize("name", RNN_CASES)
 def test_cuda_matches_reference_golden(name):
     rows = compare_blob(load_golden(name), TOL)
@@ -17,8 +27,9 @@ def test_cuda_matches_reference_golden(name):
     assert not bad, "\n".join(f"{w}: rel={e:.3e} scale={s:.3e}" for w, e, s, _ in bad)
 
 
+@pytest.mark.parametrize("precision,tol", [("fp32", TOL), ("bf16", TOL_TC)])
 @pytest.mark.parametrize("model,T", [("CrossAttnRNN210", 10), ("CrossAttnRNNDemand", 12), ("CrossAttnRNN21", 1)])
-def test_cuda_matches_oracle_default_dims(model, T):
+def test_cuda_matches_oracle_default_dims(model, T, precision, tol):
     """E=A=H=512, Li=100, Lt=52 (train_dl.py:197-199) at a small batch; oracle on CPU is the checker."""
     import visuelle2_multimodal_fusion_b200.synth as synth
     from helpers import oracle_run, product_model, product_run, assert_close
@@ -55,10 +66,11 @@ def test_cuda_matches_oracle_default_dims(model, T):
     o_out, o_loss, o_extras, P, o_feat = oracle_run(blob)
     o_loss.backward()
     m = m.cuda().eval()
+    m.precision = precision
     out, loss, extras, grads, gfeat = product_run(m, blob)
-    assert_close(out, o_out, TOL, "out")
-    assert_close(loss, o_loss, TOL, "loss")
-    assert_close(gfeat, o_feat.grad, TOL, "grad_feat")
+    assert_close(out, o_out, tol, "out")
+    assert_close(loss, o_loss, tol, "loss")
+    assert_close(gfeat, o_feat.grad, tol, "grad_feat")
     for k, p in P.items():
         if p.grad is None:
             continue
@@ -66,4 +78,4 @@ def test_cuda_matches_oracle_default_dims(model, T):
         # attn_linear.bias feeds a softmax, so its true gradient is exactly 0 (the kernel returns 0,
         # autograd returns rounding noise): compare those absolutely
         floor = 1e-6 if k.endswith("attn_linear.bias") else 1e-6 * float(p.grad.abs().max() + 1e-3)
-        assert_close(grads[k], p.grad, TOL, "grad:" + k, floor=floor)
+        assert_close(grads[k], p.grad, tol, "grad:" + k, floor=floor)

@@ -31,9 +31,9 @@ class DecodeParams(ctypes.Structure):
              "dY", "dh", "DScat", "DGI", "DCTX", "dU", "DHC", "DC", "DE_img", "DE_tr", "DYH", "dxn",
              "dw_acc", "dMst_acc", "dHMst_acc", "dHimg", "dVimg", "dHtr", "dPtr", "dMst", "dHMst",
              "dWcat", "dbcat", "dw_att", "db_tl", "dWe_mm", "dW_me", "db_me", "dW_ihc", "dw_x",
-             "db_ih", "dw_fc", "db_fc"]
-    _fields_ = ([(n, c_int) for n in _INTS] + [("tf_mask", ctypes.c_uint), ("reserved", c_int)] +
-                [(n, c_vp) for n in _PTRS])
+             "db_ih", "dw_fc", "db_fc", "WcatT", "W_ihcT", "W_meT", "We_mmT", "ws"]
+    _fields_ = ([(n, c_int) for n in _INTS] + [("tf_mask", ctypes.c_uint), ("precision", c_int)] +
+                [(n, c_vp) for n in _PTRS] + [("ws_floats", c_ll)])
 
 
 def _declare(lib):
@@ -45,17 +45,23 @@ def _declare(lib):
     lib.v2f_mul_f32.argtypes = [c_ll, c_vp, c_vp, c_vp, c_vp]
     lib.v2f_decode_fwd.argtypes = [ctypes.POINTER(DecodeParams), c_vp]
     lib.v2f_decode_bwd.argtypes = [ctypes.POINTER(DecodeParams), c_vp]
-    lib.v2f_gru_seq_fwd.argtypes = [c_int] * 4 + [c_vp] * 11 + [c_vp]
-    lib.v2f_gru_seq_bwd.argtypes = [c_int] * 4 + [c_vp] * 19 + [c_vp]
+    lib.v2f_gru_seq_fwd.argtypes = [c_int] * 4 + [c_vp] * 11 + [c_int, c_vp]
+    lib.v2f_gru_seq_bwd.argtypes = [c_int] * 4 + [c_vp] * 19 + [c_vp, c_vp, c_ll, c_int, c_vp]
     sd = [c_int] * 5 + [c_vp, c_int, c_ll] * 3
     lib.v2f_sdpa_fwd.argtypes = sd + [c_vp, c_int, c_ll, c_vp, c_vp, c_vp, c_float, c_vp]
     lib.v2f_sdpa_bwd.argtypes = sd + [c_vp, c_int, c_ll, c_vp, c_vp] + [c_vp, c_int, c_ll] * 3 + [c_float, c_vp]
     lib.v2f_embed_fwd.argtypes = [c_int, c_int, c_vp, c_vp, c_vp, ctypes.POINTER(c_vp), c_vp, c_vp, c_vp, c_vp]
     lib.v2f_embed_bwd.argtypes = [c_int, c_int, c_vp, c_vp, c_vp, c_vp, ctypes.POINTER(c_int), c_vp, c_vp,
                                   ctypes.POINTER(c_vp), c_vp]
+    lib.v2f_gemm_tc.argtypes = [c_int, c_int, c_int, c_int, c_vp, c_ll, c_vp, c_ll, c_vp, c_ll, c_vp, c_float,
+                                c_int, c_int, c_vp]
+    lib.v2f_gemm_tc_batched.argtypes = [c_int, c_int, c_int, c_int, c_vp, c_ll, c_ll, c_vp, c_ll, c_ll, c_vp, c_ll,
+                                        c_ll, c_int, c_vp, c_float, c_int, c_int, c_vp]
+    lib.v2f_cast_bf16.argtypes = [c_ll, c_vp, c_vp, c_vp]
+    lib.v2f_transpose.argtypes = [c_int, c_int, c_vp, c_ll, c_int, c_vp, c_ll, c_int, c_vp]
     lib.v2f_prof_enable.argtypes = [c_int]
     lib.v2f_prof_read.argtypes = [c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(c_ll)]
-    for name in ("v2f_prof_enable", "v2f_prof_read", "v2f_gemm_f32", "v2f_colsum_f32", "v2f_mul_f32", "v2f_decode_fwd", "v2f_decode_bwd",
+    for name in ("v2f_gemm_tc", "v2f_gemm_tc_batched", "v2f_cast_bf16", "v2f_transpose", "v2f_prof_enable", "v2f_prof_read", "v2f_gemm_f32", "v2f_colsum_f32", "v2f_mul_f32", "v2f_decode_fwd", "v2f_decode_bwd",
                  "v2f_gru_seq_fwd", "v2f_gru_seq_bwd", "v2f_sdpa_fwd", "v2f_sdpa_bwd", "v2f_embed_fwd",
                  "v2f_embed_bwd"):
         getattr(lib, name).restype = c_int

@@ -1,0 +1,433 @@
+// Tensor-core GEMM for sm_100a: tcgen05.mma (bf16 or tf32 inputs, fp32 accumulate in TMEM),
+// operands staged by TMA (cp.async.bulk.tensor, 128-byte swizzle) through an mbarrier ring.
+//
+//   C[M,N] (fp32) = A[M,K] * B[N,K]^T (+bias[n]) (+beta*C) (ReLU)      both operands K-major
+//
+// This is the "both K-major" form every dense contraction of the hot path is brought into
+// (forward: x W^T; backward: dy (W^T)^T and (dy^T)(x^T)^T with explicitly transposed copies), so
+// one kernel serves nn.Linear forward/backward in /root/reference/models/CrossAttnRNN210.py:72,
+// 84-85,126,128,132 and the per-step recurrent projections of the decoder / GRU (:135-140).
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer (one elected
+// lane issues tcgen05.mma for the CTA), warps 2..5 = epilogue (tcgen05.ld -> registers -> global;
+// warp w owns TMEM lanes 32*(w%4)..+31).  One 128 x BN output tile per CTA.
+// Every mbarrier wait is bounded: a protocol bug traps instead of hanging the GPU.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace v2f {
+
+constexpr int TC_BM = 128;           // UMMA_M
+constexpr int TC_STAGE_BYTES_K = 128;  // one 128-byte swizzle span of K per stage row
+constexpr int TC_THREADS = 192;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// bounded wait: ~seconds of polling, then trap (kernel aborts with an error instead of hanging)
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  for (uint32_t i = 0; i < (1u << 24); i++)
+    if (mbar_try_wait(bar, parity)) return;
+  __trap();
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                            int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major operand tile, 128-byte swizzle: rows of 128 B, 8-row groups 1024 B apart (SBO), LBO unused.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);          // start address  [0,14)
+  d |= (uint64_t)0 << 16;                           // leading byte offset (ignored for SW128 K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;                 // stride byte offset [32,46)
+  d |= (uint64_t)1 << 46;                           // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;                           // layout type: SWIZZLE_128B
+  return d;
+}
+
+// instruction descriptor, kind::f16 (bf16 x bf16 -> f32) or kind::tf32, both operands K-major
+template <int KIND>
+__device__ __forceinline__ uint32_t umma_idesc(int n) {
+  uint32_t d = 0;
+  d |= 1u << 4;                                     // D format: F32
+  const uint32_t fmt = KIND == 0 ? 1u : 2u;         // kind::f16: 1 = BF16; kind::tf32: 2 = TF32
+  d |= fmt << 7;                                    // A format
+  d |= fmt << 10;                                   // B format
+  // bit 15 / 16: A / B major = 0 (K-major)
+  d |= (uint32_t)(n >> 3) << 17;                    // N >> 3
+  d |= (uint32_t)(TC_BM >> 4) << 24;                // M >> 4
+  return d;
+}
+
+template <int KIND>
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  if (KIND == 0) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+
+struct TcArgs {
+  int M, N, K;
+  float* C;
+  long long ldc;
+  const float* bias;
+  float beta;
+  int act;
+  int k_blocks;   // number of 128-byte K blocks per CTA (split-K: blocks per split)
+  int atomic;     // split-K: accumulate with red.add into pre-zeroed / pre-scaled C
+  int splits;     // blockIdx.z = batch * splits + split
+  long long sC;   // batch stride of C (elements)
+};
+
+// KIND 0: bf16 (64 elements per 128-B span, UMMA_K 16); KIND 1: tf32 (32 elements, UMMA_K 8)
+template <int KIND, int BN, int STAGES>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, TcArgs a) {
+  constexpr int ELEM = KIND == 0 ? 2 : 4;
+  constexpr int BK = TC_STAGE_BYTES_K / ELEM;       // elements of K per stage
+  constexpr int UK = 32 / ELEM;                     // UMMA_K
+  constexpr int A_BYTES = TC_BM * TC_STAGE_BYTES_K;
+  constexpr int B_BYTES = BN * TC_STAGE_BYTES_K;
+  constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * A_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * B_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tmem_full = empty + STAGES;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;
+  const int bz = blockIdx.z / a.splits, split = blockIdx.z - bz * a.splits;
+  const int kb0 = split * a.k_blocks;
+  int nkb = a.k_blocks;
+  const int total_kb = (a.K + BK - 1) / BK;
+  if (kb0 + nkb > total_kb) nkb = total_kb - kb0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; s++) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)),
+                 "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = *tmem_ptr;
+
+  if (warp == 0) {
+    if (lane == 0 && nkb > 0) {
+      for (int i = 0; i < nkb; i++) {
+        const int s = i % STAGES, r = i / STAGES;
+        mbar_wait(&empty[s], (r & 1) ^ 1);
+        mbar_expect_tx(&full[s], A_BYTES + B_BYTES);
+        const int kc = (kb0 + i) * BK;
+        tma_load_3d(sA + s * A_BYTES, &mapA, &full[s], kc, m0, bz);
+        tma_load_3d(sB + s * B_BYTES, &mapB, &full[s], kc, n0, bz);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && nkb > 0) {
+      const uint32_t idesc = umma_idesc<KIND>(BN);
+      for (int i = 0; i < nkb; i++) {
+        const int s = i % STAGES, r = i / STAGES;
+        mbar_wait(&full[s], r & 1);
+        tc_fence_after();
+        const uint64_t ad = umma_desc_sw128(smem_u32(sA + s * A_BYTES));
+        const uint64_t bd = umma_desc_sw128(smem_u32(sB + s * B_BYTES));
+#pragma unroll
+        for (int k = 0; k < BK / UK; k++) {
+          // advance 32 bytes of K inside the swizzle span: +2 in the (address >> 4) field
+          umma<KIND>(tmem_d, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (i | k) ? 1u : 0u);
+        }
+        umma_commit(&empty[s]);     // frees the smem slot when the MMAs above have read it
+      }
+      umma_commit(tmem_full);       // accumulator complete
+    }
+  } else {
+    // ---- epilogue: warp w reads TMEM lanes 32*(w%4) .. +31  == output rows m0 + 32*(w%4) + lane
+    const int q = warp & 3;
+    const int row = m0 + q * 32 + lane;
+    if (nkb > 0) {
+      mbar_wait(tmem_full, 0);
+      tc_fence_after();
+    }
+#pragma unroll
+    for (int c0 = 0; c0 < BN; c0 += 16) {
+      uint32_t v[16];
+      if (nkb > 0) {
+        const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+              "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+            : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; j++) v[j] = 0u;
+      }
+      if (row < a.M) {
+        if (a.act & 2) {
+          // bf16 output (e.g. the gradient handed back to the bf16 backbone): no beta / atomics
+          __nv_bfloat16* crow = reinterpret_cast<__nv_bfloat16*>(a.C) + (long long)bz * a.sC + (long long)row * a.ldc;
+#pragma unroll
+          for (int j = 0; j < 16; j++) {
+            const int col = n0 + c0 + j;
+            if (col < a.N) {
+              float x = __uint_as_float(v[j]);
+              if (a.bias) x += a.bias[col];
+              if (a.act & 1) x = fmaxf(x, 0.f);
+              crow[col] = __float2bfloat16_rn(x);
+            }
+          }
+        } else {
+          float* crow = a.C + (long long)bz * a.sC + (long long)row * a.ldc;
+#pragma unroll
+          for (int j = 0; j < 16; j++) {
+            const int col = n0 + c0 + j;
+            if (col < a.N) {
+              float x = __uint_as_float(v[j]);
+              if (a.atomic) {
+                if (a.bias && split == 0) x += a.bias[col];
+                atomicAdd(crow + col, x);
+              } else {
+                if (a.bias) x += a.bias[col];
+                if (a.beta != 0.f) x += a.beta * crow[col];
+                if (a.act & 1) x = fmaxf(x, 0.f);
+                crow[col] = x;
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// batch x row-major [rows, cols] (cols contiguous, row stride ld, batch stride bs, in elements),
+// box = [1, box_rows, 128 bytes]
+static int make_map(CUtensorMap* map, int kind, const void* ptr, long long rows, long long cols, long long ld,
+                    long long batch, long long bs, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return V2F_ERR_UNSUPPORTED;
+  const int elem = kind == 0 ? 2 : 4;
+  if (batch <= 1) { batch = 1; bs = rows * ld; }
+  cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)batch};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * elem, (cuuint64_t)bs * elem};
+  cuuint32_t box[3] = {(cuuint32_t)(128 / elem), (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, kind == 0 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
+                  const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? V2F_OK : V2F_ERR_BAD_ARG;
+}
+
+template <int KIND, int BN>
+static int launch_tc(const CUtensorMap& mA, const CUtensorMap& mB, const TcArgs& a, int gz, cudaStream_t s) {
+  constexpr int STAGES = BN >= 128 ? 4 : 6;
+  constexpr size_t smem = 1024 + (size_t)STAGES * (TC_BM + BN) * 128 + (2 * STAGES + 1) * 8 + 16;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(gemm_tc_kernel<KIND, BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)smem) != cudaSuccess)
+      return V2F_ERR_LAUNCH;
+    attr_set = true;
+  }
+  dim3 grid((a.N + BN - 1) / BN, (a.M + TC_BM - 1) / TC_BM, gz);
+  gemm_tc_kernel<KIND, BN, STAGES><<<grid, TC_THREADS, smem, s>>>(mA, mB, a);
+  V2F_CHECK_LAUNCH();
+  return V2F_OK;
+}
+
+}  // namespace v2f
+
+using namespace v2f;
+
+// C[b][M,N] = A[b][M,K] B[b][N,K]^T (+bias) (+beta C) (act).  kind 0: A,B bf16; kind 1: A,B fp32 read as
+// tf32.  ld*/s* in elements.  splits > 1: split-K with atomic accumulation (C must hold the value to
+// accumulate onto, e.g. zeros; beta/act are then not applied).
+extern "C" int v2f_gemm_tc_batched(int kind, int M, int N, int K, const void* A, long long lda, long long sA,
+                                   const void* B, long long ldb, long long sB, float* C, long long ldc,
+                                   long long sC, int batch, const float* bias, float beta, int act, int splits,
+                                   void* stream) {
+  V2F_REQUIRE(kind == 0 || kind == 1, V2F_ERR_BAD_ARG);
+  V2F_REQUIRE(M > 0 && N > 0 && K > 0 && batch > 0 && A && B && C, V2F_ERR_BAD_ARG);
+  const int elem = kind == 0 ? 2 : 4;
+  V2F_REQUIRE(aligned16(A) && aligned16(B), V2F_ERR_ALIGN);
+  V2F_REQUIRE((lda * elem) % 16 == 0 && (ldb * elem) % 16 == 0, V2F_ERR_ALIGN);
+  V2F_REQUIRE(batch == 1 || ((sA * elem) % 16 == 0 && (sB * elem) % 16 == 0), V2F_ERR_ALIGN);
+  if (splits < 1) splits = 1;
+  V2F_REQUIRE(splits == 1 || (beta == 0.f && act == 0), V2F_ERR_BAD_ARG);
+  V2F_REQUIRE(!(act & 2) || beta == 0.f, V2F_ERR_BAD_ARG);
+  V2F_REQUIRE((long long)batch * splits <= 65535, V2F_ERR_BAD_ARG);
+  // tile width: keep >= ~1 wave of CTAs on 148 SMs for the small-M recurrent GEMMs
+  const int mt = (M + TC_BM - 1) / TC_BM;
+  int bn = 128;
+  while (bn > 16 && (long long)mt * ((N + bn - 1) / bn) * splits * batch < 120) bn >>= 1;
+  const int bk = 128 / elem;
+  const int total_kb = (K + bk - 1) / bk;
+  TcArgs a{M, N, K, C, ldc, bias, beta, act, (total_kb + splits - 1) / splits, splits > 1 ? 1 : 0, splits, sC};
+  CUtensorMap mA, mB;
+  V2F_TRY(make_map(&mA, kind, A, M, K, lda, batch, sA, TC_BM));
+  V2F_TRY(make_map(&mB, kind, B, N, K, ldb, batch, sB, bn));
+  cudaStream_t s = (cudaStream_t)stream;
+  const int gz = batch * splits;
+#define DISPATCH(KIND_)                                      \
+  switch (bn) {                                              \
+    case 128: return launch_tc<KIND_, 128>(mA, mB, a, gz, s); \
+    case 64: return launch_tc<KIND_, 64>(mA, mB, a, gz, s);   \
+    case 32: return launch_tc<KIND_, 32>(mA, mB, a, gz, s);   \
+    default: return launch_tc<KIND_, 16>(mA, mB, a, gz, s);   \
+  }
+  if (kind == 0) {
+    DISPATCH(0)
+  } else {
+    DISPATCH(1)
+  }
+#undef DISPATCH
+  return V2F_OK;
+}
+
+extern "C" int v2f_gemm_tc(int kind, int M, int N, int K, const void* A, long long lda, const void* B,
+                           long long ldb, float* C, long long ldc, const float* bias, float beta, int act,
+                           int splits, void* stream) {
+  return v2f_gemm_tc_batched(kind, M, N, K, A, lda, 0, B, ldb, 0, C, ldc, 0, 1, bias, beta, act, splits, stream);
+}
+
+// ------------------------------------------------------------------------------------------
+// fp32 -> bf16 cast and transposing cast (operand preparation for the K-major GEMM form)
+namespace v2f {
+__global__ void cast_bf16_kernel(long long n, const float* __restrict__ x, __nv_bfloat16* __restrict__ out) {
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i + 3 < n) {
+    const float4 v = ld4(x + i);
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    *reinterpret_cast<__nv_bfloat162*>(out + i) = a;
+    *reinterpret_cast<__nv_bfloat162*>(out + i + 2) = b;
+  } else {
+    for (long long j = i; j < n; j++) out[j] = __float2bfloat16_rn(x[j]);
+  }
+}
+
+// out[c, r] = cast(in[r, c]);  in: [rows, cols] with row stride ld.  32x32 smem tile.
+template <typename TIN, typename TOUT>
+__global__ void transpose_kernel(int rows, int cols, const TIN* __restrict__ in, long long ld,
+                                 TOUT* __restrict__ out, long long ldo) {
+  __shared__ float tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < rows && c < cols) ? (float)in[(long long)r * ld + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (c < cols && r < rows) out[(long long)c * ldo + r] = (TOUT)tile[threadIdx.x][i];
+  }
+}
+}  // namespace v2f
+
+extern "C" int v2f_cast_bf16(long long n, const float* x, void* out, void* stream) {
+  V2F_REQUIRE(n >= 0 && x && out, V2F_ERR_BAD_ARG);
+  if (n == 0) return V2F_OK;
+  V2F_REQUIRE(aligned16(x) && aligned16(out), V2F_ERR_ALIGN);
+  const long long thr = (n + 3) / 4;
+  cast_bf16_kernel<<<(unsigned)((thr + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n, x, (__nv_bfloat16*)out);
+  V2F_CHECK_LAUNCH();
+  return V2F_OK;
+}
+
+// out[cols, rows] = in[rows, cols]^T.  in_kind / out_kind: 0 = bf16, 1 = fp32.
+extern "C" int v2f_transpose(int rows, int cols, const void* in, long long ld, int in_kind, void* out,
+                             long long ldo, int out_kind, void* stream) {
+  V2F_REQUIRE(rows > 0 && cols > 0 && in && out, V2F_ERR_BAD_ARG);
+  dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (in_kind == 1 && out_kind == 1)
+    transpose_kernel<float, float><<<grid, block, 0, s>>>(rows, cols, (const float*)in, ld, (float*)out, ldo);
+  else if (in_kind == 1 && out_kind == 0)
+    transpose_kernel<float, __nv_bfloat16><<<grid, block, 0, s>>>(rows, cols, (const float*)in, ld, (__nv_bfloat16*)out, ldo);
+  else if (in_kind == 0 && out_kind == 0)
+    transpose_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, block, 0, s>>>(rows, cols, (const __nv_bfloat16*)in, ld, (__nv_bfloat16*)out, ldo);
+  else if (in_kind == 0 && out_kind == 1)
+    transpose_kernel<__nv_bfloat16, float><<<grid, block, 0, s>>>(rows, cols, (const __nv_bfloat16*)in, ld, (float*)out, ldo);
+  else
+    return V2F_ERR_BAD_ARG;
+  V2F_CHECK_LAUNCH();
+  return V2F_OK;
+}

@@ -7,12 +7,7 @@
 //   h' = (1-z) n + z h
 // The input projection of all steps is one GEMM; the recurrent part is a GEMM + gate kernel per
 // step (v0).  Saved for BPTT: r,z,n and gh_n.
-#include "common.cuh"
-
-extern "C" int v2f_gemm_f32(int, int, int, int, int, const float*, int, long long, const float*,
-                            int, long long, float*, int, long long, int, const float*, float, int,
-                            void*);
-extern "C" int v2f_colsum_f32(int, int, const float*, int, float*, float, void*);
+#include "gemm_dispatch.cuh"
 
 namespace v2f {
 
@@ -74,15 +69,16 @@ using namespace v2f;
 extern "C" int v2f_gru_seq_fwd(int N, int L, int I, int H, const float* x, const float* h0,
                                const float* w_ih, const float* w_hh, const float* b_ih,
                                const float* b_hh, float* out, float* GI, float* GH, float* RZN,
-                               float* GHN, void* st) {
+                               float* GHN, int precision, void* st) {
   V2F_REQUIRE(N > 0 && L > 0 && I > 0 && H > 0, V2F_ERR_BAD_ARG);
   V2F_REQUIRE(x && h0 && w_ih && w_hh && b_ih && b_hh && out && GI && GH && RZN && GHN, V2F_ERR_BAD_ARG);
   cudaStream_t s = (cudaStream_t)st;
-  V2F_TRY(v2f_gemm_f32(0, 1, N * L, 3 * H, I, x, I, 0, w_ih, I, 0, GI, 3 * H, 0, 1, b_ih, 0.f, 0, st));
+  const GemmCtx gx{precision, nullptr, 0, st};
+  V2F_TRY(gemm_nt(gx, N * L, 3 * H, I, x, I, w_ih, I, GI, 3 * H, b_ih, 0.f));
   for (int t = 0; t < L; t++) {
     const float* hp = t == 0 ? h0 : out + (long long)(t - 1) * H;
     const int ldh = t == 0 ? H : L * H;
-    V2F_TRY(v2f_gemm_f32(0, 1, N, 3 * H, H, hp, ldh, 0, w_hh, H, 0, GH, 3 * H, 0, 1, b_hh, 0.f, 0, st));
+    V2F_TRY(gemm_nt(gx, N, 3 * H, H, hp, ldh, w_hh, H, GH, 3 * H, b_hh, 0.f));
     gru_gates_fwd_kernel<<<N, 256, 0, s>>>(N, L, H, t, GI, GH, hp, ldh, out, RZN, GHN);
     V2F_CHECK_LAUNCH();
   }
@@ -94,10 +90,14 @@ extern "C" int v2f_gru_seq_bwd(int N, int L, int I, int H, const float* x, const
                                const float* RZN, const float* GHN, const float* dOut,
                                const float* dhL, float* dh, float* DGI, float* DGH, float* Hprev,
                                float* dx, float* dh0, float* dw_ih, float* dw_hh, float* db_ih,
-                               float* db_hh, void* st) {
+                               float* db_hh, float* w_hhT, float* ws, long long ws_floats,
+                               int precision, void* st) {
   V2F_REQUIRE(N > 0 && L > 0 && I > 0 && H > 0, V2F_ERR_BAD_ARG);
   V2F_REQUIRE(x && h0 && w_ih && w_hh && out && RZN && GHN && dh && DGI && DGH && Hprev, V2F_ERR_BAD_ARG);
   cudaStream_t s = (cudaStream_t)st;
+  const GemmCtx gx{precision, ws, ws_floats, st};
+  const bool tc = precision != 0 && w_hhT;
+  if (tc) V2F_TRY(v2f_transpose(3 * H, H, w_hh, H, 1, w_hhT, 3 * H, 1, st));
   if (dhL)
     cudaMemcpyAsync(dh, dhL, sizeof(float) * (size_t)N * H, cudaMemcpyDeviceToDevice, s);
   else
@@ -108,15 +108,15 @@ extern "C" int v2f_gru_seq_bwd(int N, int L, int I, int H, const float* x, const
     gru_gates_bwd_kernel<<<N, 256, 0, s>>>(N, L, H, t, RZN, GHN, hp, ldh, dOut, dh, DGI, DGH, Hprev);
     V2F_CHECK_LAUNCH();
     // dh += DGH[t] W_hh
-    V2F_TRY(v2f_gemm_f32(0, 0, N, H, 3 * H, DGH + (long long)t * N * 3 * H, 3 * H, 0, w_hh, H, 0, dh, H,
-                         0, 1, nullptr, 1.f, 0, st));
+    V2F_TRY(gemm_nn(gx, N, H, 3 * H, DGH + (long long)t * N * 3 * H, 3 * H, w_hh, H, tc ? w_hhT : nullptr,
+                    3 * H, dh, H, 1.f));
   }
   if (dh0) cudaMemcpyAsync(dh0, dh, sizeof(float) * (size_t)N * H, cudaMemcpyDeviceToDevice, s);
   const int NL = N * L;
-  if (dw_ih) V2F_TRY(v2f_gemm_f32(1, 0, 3 * H, I, NL, DGI, 3 * H, 0, x, I, 0, dw_ih, I, 0, 1, nullptr, 0.f, 0, st));
+  if (dw_ih) V2F_TRY(gemm_tn(gx, 3 * H, I, NL, DGI, 3 * H, x, I, dw_ih, I));
   if (db_ih) V2F_TRY(v2f_colsum_f32(NL, 3 * H, DGI, 3 * H, db_ih, 0.f, st));
-  if (dw_hh) V2F_TRY(v2f_gemm_f32(1, 0, 3 * H, H, NL, DGH, 3 * H, 0, Hprev, H, 0, dw_hh, H, 0, 1, nullptr, 0.f, 0, st));
+  if (dw_hh) V2F_TRY(gemm_tn(gx, 3 * H, H, NL, DGH, 3 * H, Hprev, H, dw_hh, H));
   if (db_hh) V2F_TRY(v2f_colsum_f32(NL, 3 * H, DGH, 3 * H, db_hh, 0.f, st));
-  if (dx) V2F_TRY(v2f_gemm_f32(0, 0, NL, I, 3 * H, DGI, 3 * H, 0, w_ih, I, 0, dx, I, 0, 1, nullptr, 0.f, 0, st));
+  if (dx) V2F_TRY(gemm_nn(gx, NL, I, 3 * H, DGI, 3 * H, w_ih, I, nullptr, 0, dx, I, 0.f));
   return V2F_OK;
 }

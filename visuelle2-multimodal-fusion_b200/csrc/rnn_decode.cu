@@ -8,12 +8,7 @@
 // once (forward) and once more (backward); their gradients are produced after the time loop
 // in one pass that re-derives tanh from the saved per-step scalars, so each gradient tile is
 // written once (SURVEY.md section 8d byte model).
-#include "common.cuh"
-
-extern "C" int v2f_gemm_f32(int, int, int, int, int, const float*, int, long long, const float*,
-                            int, long long, float*, int, long long, int, const float*, float, int,
-                            void*);
-extern "C" int v2f_colsum_f32(int, int, const float*, int, float*, float, void*);
+#include "gemm_dispatch.cuh"
 
 namespace v2f {
 
@@ -621,8 +616,10 @@ static size_t attn_smem(int E, bool bwd) {
 
 using namespace v2f;
 
-#define GEMM(ta, tb, M, N, K, A, lda, B, ldb, C, ldc, bias, beta) \
-  V2F_TRY(v2f_gemm_f32(ta, tb, M, N, K, A, lda, 0, B, ldb, 0, C, ldc, 0, 1, bias, beta, 0, st))
+#define NT(M, N, K, A, lda, B, ldb, C, ldc, bias, beta) V2F_TRY(gemm_nt(gx, M, N, K, A, lda, B, ldb, C, ldc, bias, beta))
+#define NN(M, N, K, A, lda, B, ldb, BT, ldbt, C, ldc, beta) \
+  V2F_TRY(gemm_nn(gx, M, N, K, A, lda, B, ldb, BT, ldbt, C, ldc, beta))
+#define TN(M, N, K, A, lda, B, ldb, C, ldc) V2F_TRY(gemm_tn(gx, M, N, K, A, lda, B, ldb, C, ldc))
 
 extern "C" int v2f_decode_fwd(const v2f_decode_params* p, void* st) {
   V2F_TRY(check_params(p));
@@ -631,6 +628,7 @@ extern "C" int v2f_decode_fwd(const v2f_decode_params* p, void* st) {
   const bool gru = p->variant != 1;
   const int G = gru ? 3 * H : 0, ldS = 3 * E + G;
   const bool use_img = (p->mod_mask >> 1) & 1, use_tr = (p->mod_mask >> 3) & 1;
+  const GemmCtx gx{p->precision, nullptr, 0, st};
   const size_t smem = attn_smem(E, false);
   if (smem > 48 * 1024)
     cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -649,7 +647,7 @@ extern "C" int v2f_decode_fwd(const v2f_decode_params* p, void* st) {
     float* U = p->U + (long long)t * N * E;
     float* CTX = p->CTX + (long long)t * N * E;
     // S = h Wcat^T + bcat  (s_img | s_tr | s_mm | gh)
-    GEMM(0, 1, N, ldS, H, h, H, p->Wcat, H, S, ldS, p->bcat, 0.f);
+    NT(N, ldS, H, h, H, p->Wcat, H, S, ldS, p->bcat, 0.f);
     if (use_img || use_tr) {
       AttnArgs a{N, p->W, E, p->Li, p->Lt, ldS, p->Himg, p->Vimg, p->Htr, p->Ptr, S, p->w_att,
                  p->beta_att, p->b_tl, C, p->alpha_img + (long long)t * N * p->Li,
@@ -659,15 +657,15 @@ extern "C" int v2f_decode_fwd(const v2f_decode_params* p, void* st) {
       prof_end(V2F_K_ATTN_FWD, s);
       V2F_CHECK_LAUNCH();
       // HC = C We_mm^T  ([2N,E] view)
-      GEMM(0, 1, 2 * N, E, E, C, E, p->We_mm, E, HC, E, nullptr, 0.f);
+      NT(2 * N, E, E, C, E, p->We_mm, E, HC, E, nullptr, 0.f);
     }
     MmArgs m{N, p->W, E, ldS, p->variant == 2, p->mod_mask, p->Mst, p->HMst, C, HC, S, p->w_att,
              p->beta_att, p->alpha_mm + (long long)t * N * 4, U};
     mm_fwd_kernel<<<N, 256, 0, s>>>(m);
     V2F_CHECK_LAUNCH();
-    GEMM(0, 1, N, E, E, U, E, p->W_me, E, CTX, E, p->b_me, 0.f);
+    NT(N, E, E, U, E, p->W_me, E, CTX, E, p->b_me, 0.f);
     if (gru) {
-      GEMM(0, 1, N, 3 * H, E, CTX, E, p->W_ihc, E, p->GI, 3 * H, p->b_ih, 0.f);
+      NT(N, 3 * H, E, CTX, E, p->W_ihc, E, p->GI, 3 * H, p->b_ih, 0.f);
       GateArgs g{N, H, T, t, ldS, 3 * E, (int)((p->tf_mask >> t) & 1u), p->GI, S, h,
                  p->xin + (long long)t * N, p->w_x, p->w_fc, p->b_fc, p->y,
                  p->RZN + (long long)t * N * 3 * H, p->h_all + (long long)(t + 1) * N * H, p->yhat,
@@ -690,6 +688,18 @@ extern "C" int v2f_decode_bwd(const v2f_decode_params* p, void* st) {
   const int G = gru ? 3 * H : 0, ldS = 3 * E + G;
   const bool use_img = (p->mod_mask >> 1) & 1, use_tr = (p->mod_mask >> 3) & 1;
   const int byproj = p->variant == 2;
+  const GemmCtx gx{p->precision, p->ws, p->ws_floats, st};
+  const bool tc = p->precision != 0 && p->WcatT && p->W_meT && p->We_mmT && (!gru || p->W_ihcT);
+  if (tc) {  // transposed weight copies for the dx-type products (K-major operands for tcgen05)
+    V2F_TRY(v2f_transpose(ldS, H, p->Wcat, H, 1, p->WcatT, ldS, 1, st));
+    V2F_TRY(v2f_transpose(E, E, p->W_me, E, 1, p->W_meT, E, 1, st));
+    V2F_TRY(v2f_transpose(E, E, p->We_mm, E, 1, p->We_mmT, E, 1, st));
+    if (gru) V2F_TRY(v2f_transpose(3 * H, E, p->W_ihc, E, 1, p->W_ihcT, 3 * H, 1, st));
+  }
+  const float* WcatT = tc ? p->WcatT : nullptr;
+  const float* W_meT = tc ? p->W_meT : nullptr;
+  const float* We_mmT = tc ? p->We_mmT : nullptr;
+  const float* W_ihcT = tc ? p->W_ihcT : nullptr;
   const size_t smem = attn_smem(E, true);
   if (smem > 48 * 1024)
     cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -709,13 +719,13 @@ extern "C" int v2f_decode_bwd(const v2f_decode_params* p, void* st) {
       gates_bwd_kernel<<<N, 256, 0, s>>>(g);
       V2F_CHECK_LAUNCH();
       // dCTX = DGI W_ihc
-      GEMM(0, 0, N, E, 3 * H, p->DGI + (long long)t * N * 3 * H, 3 * H, p->W_ihc, E, DCTX, E, nullptr, 0.f);
+      NN(N, E, 3 * H, p->DGI + (long long)t * N * 3 * H, 3 * H, p->W_ihc, E, W_ihcT, 3 * H, DCTX, E, 0.f);
     } else {
       fc_bwd_kernel<<<(unsigned)(((long long)N * E + 255) / 256), 256, 0, s>>>(N, E, p->dY, p->w_fc, DCTX, p->DYH);
       V2F_CHECK_LAUNCH();
     }
     // dU = dCTX W_me
-    GEMM(0, 0, N, E, E, DCTX, E, p->W_me, E, p->dU, E, nullptr, 0.f);
+    NN(N, E, E, DCTX, E, p->W_me, E, W_meT, E, p->dU, E, 0.f);
     MmBwdArgs m{N, p->W, E, ldS, byproj, p->mod_mask, p->Mst, p->HMst, p->C + (long long)t * N * 2 * E,
                 p->HC + (long long)t * N * 2 * E, S, p->w_att, p->alpha_mm + (long long)t * N * 4,
                 p->dU, DS, DHC, DC, p->dMst_acc, p->dHMst_acc, p->dw_acc};
@@ -723,7 +733,7 @@ extern "C" int v2f_decode_bwd(const v2f_decode_params* p, void* st) {
     V2F_CHECK_LAUNCH();
     if (use_img || use_tr) {
       // dC += DHC We_mm
-      GEMM(0, 0, 2 * N, E, E, DHC, E, p->We_mm, E, DC, E, nullptr, 1.f);
+      NN(2 * N, E, E, DHC, E, p->We_mm, E, We_mmT, E, DC, E, 1.f);
       AttnBwdArgs a{N, p->W, E, p->Li, p->Lt, ldS, p->Himg, p->Vimg, p->Htr, p->Ptr, S, p->w_att, DC,
                     p->alpha_img + (long long)t * N * p->Li, p->alpha_tr + (long long)t * N * p->Lt,
                     p->DE_img + (long long)t * N * p->Li, p->DE_tr + (long long)t * N * p->Lt, DS,
@@ -734,32 +744,32 @@ extern "C" int v2f_decode_bwd(const v2f_decode_params* p, void* st) {
       V2F_CHECK_LAUNCH();
     }
     // dh (+)= DS Wcat      (gru: dh holds the direct z-path part; else dh is overwritten)
-    GEMM(0, 0, N, H, ldS, DS, ldS, p->Wcat, H, p->dh, H, nullptr, gru ? 1.f : 0.f);
+    NN(N, H, ldS, DS, ldS, p->Wcat, H, WcatT, ldS, p->dh, H, gru ? 1.f : 0.f);
   }
   // ---- parameter gradients: one GEMM each over all T*N rows
-  const int TN = T * N;
-  GEMM(1, 0, ldS, H, TN, p->DScat, ldS, p->h_all, H, p->dWcat, H, nullptr, 0.f);
-  V2F_TRY(v2f_colsum_f32(TN, ldS, p->DScat, ldS, p->dbcat, 0.f, st));
-  GEMM(1, 0, E, E, TN, p->DCTX, E, p->U, E, p->dW_me, E, nullptr, 0.f);
-  V2F_TRY(v2f_colsum_f32(TN, E, p->DCTX, E, p->db_me, 0.f, st));
+  const int TNr = T * N;
+  TN(ldS, H, TNr, p->DScat, ldS, p->h_all, H, p->dWcat, H);
+  V2F_TRY(v2f_colsum_f32(TNr, ldS, p->DScat, ldS, p->dbcat, 0.f, st));
+  TN(E, E, TNr, p->DCTX, E, p->U, E, p->dW_me, E);
+  V2F_TRY(v2f_colsum_f32(TNr, E, p->DCTX, E, p->db_me, 0.f, st));
   if (use_img || use_tr) {
-    GEMM(1, 0, E, E, 2 * TN, p->DHC, E, p->C, E, p->dWe_mm, E, nullptr, 0.f);
+    TN(E, E, 2 * TNr, p->DHC, E, p->C, E, p->dWe_mm, E);
   } else {
     cudaMemsetAsync(p->dWe_mm, 0, sizeof(float) * E * E, s);
   }
   if (gru) {
-    GEMM(1, 0, 3 * H, E, TN, p->DGI, 3 * H, p->CTX, E, p->dW_ihc, E, nullptr, 0.f);
-    V2F_TRY(v2f_colsum_f32(TN, 3 * H, p->DGI, 3 * H, p->db_ih, 0.f, st));
-    GEMM(1, 0, 3 * H, 1, TN, p->DGI, 3 * H, p->xin, 1, p->dw_x, 1, nullptr, 0.f);
-    GEMM(1, 0, H, 1, TN, p->h_all + (long long)N * H, H, p->DYH, 1, p->dw_fc, 1, nullptr, 0.f);
+    TN(3 * H, E, TNr, p->DGI, 3 * H, p->CTX, E, p->dW_ihc, E);
+    V2F_TRY(v2f_colsum_f32(TNr, 3 * H, p->DGI, 3 * H, p->db_ih, 0.f, st));
+    TN(3 * H, 1, TNr, p->DGI, 3 * H, p->xin, 1, p->dw_x, 1);
+    TN(H, 1, TNr, p->h_all + (long long)N * H, H, p->DYH, 1, p->dw_fc, 1);
   } else {
-    GEMM(1, 0, E, 1, TN, p->CTX, E, p->DYH, 1, p->dw_fc, 1, nullptr, 0.f);
+    TN(E, 1, TNr, p->CTX, E, p->DYH, 1, p->dw_fc, 1);
   }
-  V2F_TRY(v2f_colsum_f32(TN, 1, p->DYH, 1, p->db_fc, 0.f, st));
+  V2F_TRY(v2f_colsum_f32(TNr, 1, p->DYH, 1, p->db_fc, 0.f, st));
   V2F_TRY(v2f_colsum_f32(N, 3 * E, p->dw_acc, 3 * E, p->dw_att, 0.f, st));
   if (use_tr) {
     // db_tl = sum_{t,n} dC[t,n,1,:]
-    V2F_TRY(v2f_colsum_f32(TN, E, p->DC + E, 2 * E, p->db_tl, 0.f, st));
+    V2F_TRY(v2f_colsum_f32(TNr, E, p->DC + E, 2 * E, p->db_tl, 0.f, st));
   } else {
     cudaMemsetAsync(p->db_tl, 0, sizeof(float) * E, s);
   }

@@ -11,6 +11,38 @@ from . import _lib
 from ._lib import DecodeParams, check, ptr, stream
 
 
+_PRECISION = "fp32"
+
+
+def set_precision(mode):
+    """'fp32': exact CUDA-core GEMMs (1e-5 contract).  'bf16': tcgen05 tensor-core GEMMs -- bf16
+    operands where the data already is bf16 (backbone features), tf32 elsewhere (2e-2 contract)."""
+    global _PRECISION
+    if mode not in ("fp32", "bf16"):
+        raise ValueError(mode)
+    _PRECISION = mode
+
+
+def get_precision():
+    return _PRECISION
+
+
+class precision:
+    def __init__(self, mode):
+        self.mode = mode
+
+    def __enter__(self):
+        self.prev = _PRECISION
+        set_precision(self.mode)
+
+    def __exit__(self, *a):
+        set_precision(self.prev)
+
+
+def _tc():
+    return _PRECISION == "bf16"
+
+
 def _f32(*shape, device, zero=False):
     return (torch.zeros if zero else torch.empty)(*shape, device=device, dtype=torch.float32)
 
@@ -32,9 +64,58 @@ def colsum(X, M, N, ldx, out, x_off=0):
     check(_lib.lib().v2f_colsum_f32(M, N, X.data_ptr() + 4 * x_off, ldx, ptr(out), 0.0, stream()), "v2f_colsum_f32")
 
 
+KIND_BF16, KIND_TF32 = 0, 1
+
+
+def gemm_tc(kind, M, N, K, A, lda, B, ldb, C, ldc, bias=None, beta=0.0, act=0, splits=1, a_off=0, b_off=0, c_off=0):
+    """C[M,N] = A[M,K] B[N,K]^T on tcgen05 tensor cores (kind: bf16 or fp32-as-tf32 operands)."""
+    es = 2 if kind == KIND_BF16 else 4
+    check(_lib.lib().v2f_gemm_tc(kind, M, N, K, A.data_ptr() + es * a_off, lda, B.data_ptr() + es * b_off, ldb,
+                                 C.data_ptr() + 4 * c_off, ldc, ptr(bias, allow_none=True), float(beta), act,
+                                 splits, stream()), "v2f_gemm_tc")
+
+
+def gemm_tc_batched(kind, M, N, K, A, lda, sA, B, ldb, sB, C, ldc, sC, batch, bias=None, beta=0.0, act=0, splits=1):
+    check(_lib.lib().v2f_gemm_tc_batched(kind, M, N, K, A.data_ptr(), lda, sA, B.data_ptr(), ldb, sB, C.data_ptr(),
+                                         ldc, sC, batch, ptr(bias, allow_none=True), float(beta), act, splits,
+                                         stream()), "v2f_gemm_tc_batched")
+
+
+def cast_bf16(x):
+    x = _c(x)
+    out = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+    check(_lib.lib().v2f_cast_bf16(x.numel(), ptr(x), out.data_ptr(), stream()), "v2f_cast_bf16")
+    return out
+
+
+def transpose2d(x, out_dtype=None, pad=False):
+    """[rows, cols] -> [cols, rows], optionally converting fp32 <-> bf16.  ``pad``: round the row pitch of
+    the result up to 16 bytes (TMA requirement) and return ``(buffer, pitch)``; the tail is never read."""
+    assert x.dim() == 2 and x.stride(1) == 1
+    out_dtype = out_dtype or x.dtype
+    kinds = {torch.bfloat16: 0, torch.float32: 1}
+    rows, cols = x.shape
+    q = 8 if out_dtype == torch.bfloat16 else 4
+    pitch = (rows + q - 1) // q * q if pad else rows
+    out = torch.empty(cols, pitch, device=x.device, dtype=out_dtype)
+    check(_lib.lib().v2f_transpose(rows, cols, x.data_ptr(), x.stride(0), kinds[x.dtype], out.data_ptr(), pitch,
+                                   kinds[out_dtype], stream()), "v2f_transpose")
+    return (out, pitch) if pad else out
+
+
 # --------------------------------------------------------------------------- linear
+def _splits_for(M, N, K, kb):
+    """split-K so that a weight-gradient product with few output tiles still fills the 148 SMs."""
+    tiles = ((M + 127) // 128) * ((N + 127) // 128)
+    s = 1
+    while tiles * s < 96 and (K // kb) // (s * 2) >= 8 and s < 16:
+        s *= 2
+    return s
+
+
 class _Linear(torch.autograd.Function):
-    """y = x W^T + b over the last dim (nn.Linear)."""
+    """y = x W^T + b over the last dim (nn.Linear).  fp32 mode: exact CUDA-core GEMM.  bf16 mode:
+    tcgen05 GEMM, bf16 operands if x already is bf16 (backbone features) else tf32."""
 
     @staticmethod
     def forward(ctx, x, W, b, act):
@@ -44,11 +125,21 @@ class _Linear(torch.autograd.Function):
         M = x.numel() // K
         N = W.shape[0]
         y = _f32(*x.shape[:-1], N, device=x.device)
-        ptr(x), ptr(W)
-        gemm(0, 1, M, N, K, x, K, W, K, y, N, bias=b, act=act)
+        ptr(W)
+        q = 8 if x.dtype == torch.bfloat16 else 4
+        tc = _tc() and K % q == 0 and K >= 16 and N % 4 == 0
+        if x.dtype == torch.bfloat16 and not tc:
+            x = x.float()
+        if tc:
+            kind = KIND_BF16 if x.dtype == torch.bfloat16 else KIND_TF32
+            Wk = cast_bf16(W) if kind == KIND_BF16 else W
+            gemm_tc(kind, M, N, K, x, K, Wk, K, y, N, bias=b, act=act)
+        else:
+            ptr(x)
+            gemm(0, 1, M, N, K, x, K, W, K, y, N, bias=b, act=act)
         ctx.save_for_backward(x, W, y if act else None)
         ctx.has_bias = b is not None
-        ctx.act = act
+        ctx.act, ctx.tc = act, tc
         return y
 
     @staticmethod
@@ -61,12 +152,27 @@ class _Linear(torch.autograd.Function):
         M = x.numel() // K
         N = W.shape[0]
         dx = dW = db = None
+        x2, dy2 = x.view(M, K), dy.view(M, N)
         if ctx.needs_input_grad[0]:
-            dx = torch.empty_like(x)
-            gemm(0, 0, M, K, N, dy, N, W, K, dx, K)
+            if ctx.tc:
+                WT = transpose2d(W)                                   # [K,N]
+                dx = torch.empty(x.shape, device=x.device, dtype=x.dtype)
+                gemm_tc(KIND_TF32, M, K, N, dy2, N, WT, N, dx, K, act=2 if x.dtype == torch.bfloat16 else 0)
+            else:
+                dx = torch.empty_like(x)
+                gemm(0, 0, M, K, N, dy, N, W, K, dx, K)
         if ctx.needs_input_grad[1]:
-            dW = torch.empty_like(W)
-            gemm(1, 0, N, K, M, dy, N, x, K, dW, K)
+            if ctx.tc:
+                bf = x.dtype == torch.bfloat16
+                dt = torch.bfloat16 if bf else torch.float32
+                dyT, pm = transpose2d(dy2, dt, pad=True)              # [N,Mp]
+                xT, _ = transpose2d(x2, dt, pad=True)                 # [K,Mp]
+                splits = _splits_for(N, K, M, 64 if bf else 32)
+                dW = (torch.zeros if splits > 1 else torch.empty)(W.shape, device=W.device, dtype=torch.float32)
+                gemm_tc(KIND_BF16 if bf else KIND_TF32, N, K, M, dyT, pm, xT, pm, dW, K, splits=splits)
+            else:
+                dW = torch.empty_like(W)
+                gemm(1, 0, N, K, M, dy, N, x, K, dW, K)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = _f32(N, device=x.device)
             colsum(dy, M, N, N, db)
@@ -122,8 +228,13 @@ class _TrendProj(torch.autograd.Function):
         assert W.shape[1] == L * E
         P = _f32(B, L, Eo, device=V.device)
         ptr(V), ptr(W)
-        gemm(0, 1, B, Eo, E, V, L * E, W, L * E, P, L * Eo, batch=L, sA=E, sB=E, sC=Eo)
+        tc = _tc() and E % 4 == 0 and Eo % 4 == 0 and E >= 16
+        if tc:
+            gemm_tc_batched(KIND_TF32, B, Eo, E, V, L * E, E, W, L * E, E, P, L * Eo, Eo, L)
+        else:
+            gemm(0, 1, B, Eo, E, V, L * E, W, L * E, P, L * Eo, batch=L, sA=E, sB=E, sC=Eo)
         ctx.save_for_backward(V, W)
+        ctx.tc = tc
         return P
 
     @staticmethod
@@ -134,8 +245,15 @@ class _TrendProj(torch.autograd.Function):
         Eo = W.shape[0]
         dV = torch.empty_like(V)
         dW = torch.empty_like(W)
-        gemm(0, 0, B, E, Eo, dP, L * Eo, W, L * E, dV, L * E, batch=L, sA=Eo, sB=E, sC=E)
-        gemm(1, 0, Eo, E, B, dP, L * Eo, V, L * E, dW, L * E, batch=L, sA=Eo, sB=E, sC=E)
+        if ctx.tc:
+            WT = transpose2d(W)                                           # [L*E, Eo]; block j = W_j^T
+            gemm_tc_batched(KIND_TF32, B, E, Eo, dP, L * Eo, Eo, WT, Eo, E * Eo, dV, L * E, E, L)
+            dPT, pb = transpose2d(dP.view(B, L * Eo), pad=True)           # [L*Eo, Bp]
+            VT, _ = transpose2d(V.view(B, L * E), pad=True)               # [L*E, Bp]
+            gemm_tc_batched(KIND_TF32, Eo, E, B, dPT, pb, Eo * pb, VT, pb, E * pb, dW, L * E, E, L)
+        else:
+            gemm(0, 0, B, E, Eo, dP, L * Eo, W, L * E, dV, L * E, batch=L, sA=Eo, sB=E, sC=E)
+            gemm(1, 0, Eo, E, B, dP, L * Eo, V, L * E, dW, L * E, batch=L, sA=Eo, sB=E, sC=E)
         return dV, dW
 
 
@@ -156,10 +274,12 @@ class _GruSeq(torch.autograd.Function):
         GH = _f32(N, 3 * H, device=dev)
         RZN = _f32(L, N, 3 * H, device=dev)
         GHN = _f32(L, N, H, device=dev)
+        prec = 1 if (_tc() and H % 4 == 0) else 0
         check(_lib.lib().v2f_gru_seq_fwd(N, L, I, H, ptr(x), ptr(h0), ptr(w_ih), ptr(w_hh), ptr(b_ih),
-                                         ptr(b_hh), ptr(out), ptr(GI), ptr(GH), ptr(RZN), ptr(GHN),
+                                         ptr(b_hh), ptr(out), ptr(GI), ptr(GH), ptr(RZN), ptr(GHN), prec,
                                          stream()), "v2f_gru_seq_fwd")
         ctx.save_for_backward(x, h0, w_ih, w_hh, out, RZN, GHN)
+        ctx.prec = prec
         return out
 
     @staticmethod
@@ -177,11 +297,18 @@ class _GruSeq(torch.autograd.Function):
         dh0 = _f32(N, H, device=dev) if ctx.needs_input_grad[1] else None
         dw_ih, dw_hh = torch.empty_like(w_ih), torch.empty_like(w_hh)
         db_ih, db_hh = _f32(3 * H, device=dev), _f32(3 * H, device=dev)
+        w_hhT = ws = None
+        ws_n = 0
+        if ctx.prec:
+            w_hhT = _f32(H, 3 * H, device=dev)
+            ws_n = (3 * H + H) * ((N * L + 3) // 4 * 4)
+            ws = _f32(ws_n, device=dev)
         check(_lib.lib().v2f_gru_seq_bwd(N, L, I, H, ptr(x), ptr(h0), ptr(w_ih), ptr(w_hh), ptr(out),
                                          ptr(RZN), ptr(GHN), ptr(dOut), None, ptr(dh), ptr(DGI), ptr(DGH),
                                          ptr(Hprev), ptr(dx, allow_none=True), ptr(dh0, allow_none=True),
-                                         ptr(dw_ih), ptr(dw_hh), ptr(db_ih), ptr(db_hh), stream()),
-              "v2f_gru_seq_bwd")
+                                         ptr(dw_ih), ptr(dw_hh), ptr(db_ih), ptr(db_hh),
+                                         ptr(w_hhT, allow_none=True), ptr(ws, allow_none=True), ws_n, ctx.prec,
+                                         stream()), "v2f_gru_seq_bwd")
         return dx, dh0, dw_ih, dw_hh, db_ih, db_hh
 
 
@@ -362,6 +489,8 @@ class _Decode(torch.autograd.Function):
         p = DecodeParams()
         p.N, p.B, p.W, p.E, p.H, p.Li, p.Lt, p.T = N, B, W, E, H, Li, Lt, T
         p.variant, p.mod_mask, p.tf_mask = variant, mod_mask, tf_mask if y is not None else 0
+        prec = 1 if (_tc() and E % 4 == 0 and H % 4 == 0) else 0
+        p.precision = prec
         keep = dict(Himg=Himg, Vimg=Vimg, Htr=Htr, Ptr=Ptr, Mst=Mst, HMst=HMst, h0=h0,
                     x0=_c(x0) if x0 is not None else None, y=_c(y) if y is not None else None,
                     Wcat=Wcat, bcat=bcat, w_att=w_att, beta_att=beta_att, b_tl=_c(b_tl), We_mm=_c(We_mm),
@@ -379,7 +508,7 @@ class _Decode(torch.autograd.Function):
             setattr(p, k, ptr(v, allow_none=True))
         check(_lib.lib().v2f_decode_fwd(ctypes.byref(p), stream()), "v2f_decode_fwd")
         ctx.keep, ctx.dims = keep, (variant, W, T, mod_mask, N, B, E, H, Li, Lt, G)
-        ctx.tf_mask = p.tf_mask
+        ctx.tf_mask, ctx.prec = p.tf_mask, prec
         yhat, a_img, a_mm = keep["yhat"], keep["alpha_img"], keep["alpha_mm"]
         ctx.mark_non_differentiable(a_img, a_mm)
         return yhat, a_img, a_mm
@@ -395,6 +524,7 @@ class _Decode(torch.autograd.Function):
         p = DecodeParams()
         p.N, p.B, p.W, p.E, p.H, p.Li, p.Lt, p.T = N, B, W, E, H, Li, Lt, T
         p.variant, p.mod_mask, p.tf_mask = variant, mod_mask, ctx.tf_mask
+        p.precision = ctx.prec
         H3 = max(3 * H, 1)
         g = dict(
             dY=_c(dY), dh=_f32(N, H, device=dev, zero=True), DScat=_f32(T, N, 3 * E + G, device=dev, zero=z),
@@ -413,6 +543,13 @@ class _Decode(torch.autograd.Function):
             dW_me=_f32(E, E, device=dev), db_me=_f32(E, device=dev),
             dW_ihc=_f32(H3, E, device=dev), dw_x=_f32(H3, device=dev), db_ih=_f32(H3, device=dev),
             dw_fc=_f32(H if gru else E, device=dev), db_fc=_f32(1, device=dev))
+        if ctx.prec:
+            ldS = 3 * E + G
+            tn4, rows = (T * N + 3) // 4 * 4, (2 * T * N + 3) // 4 * 4
+            ws_n = max((ldS + H) * tn4, (3 * H + E) * tn4, 2 * E * rows) + 64
+            g.update(WcatT=_f32(H, ldS, device=dev), W_ihcT=_f32(E, H3, device=dev), W_meT=_f32(E, E, device=dev),
+                     We_mmT=_f32(E, E, device=dev), ws=_f32(ws_n, device=dev))
+            p.ws_floats = ws_n
         for k, v in keep.items():
             setattr(p, k, ptr(v, allow_none=True))
         for k, v in g.items():

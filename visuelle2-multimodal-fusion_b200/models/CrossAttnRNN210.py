@@ -44,7 +44,13 @@ class CrossAttnRNN(LightningBase):
                                   batch_first=True)
         self.decoder_fc = nn.Linear(hidden_dim, 1)
 
+    precision = "fp32"     # "bf16": tcgen05 tensor-core GEMMs (2e-2 contract), see functional.set_precision
+
     def forward(self, X, y, categories, colors, fabrics, stores, temporal_features, gtrends, images):
+        with Fv.precision(self.precision):
+            return self._forward(X, y, categories, colors, fabrics, stores, temporal_features, gtrends, images)
+
+    def _forward(self, X, y, categories, colors, fabrics, stores, temporal_features, gtrends, images):
         X, y, bs, num_windows = flatten_windows(X, y)
         tiles = encode_static(self, categories, colors, fabrics, stores, temporal_features, gtrends,
                               images, by_proj=False)

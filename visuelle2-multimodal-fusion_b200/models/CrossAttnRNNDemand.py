@@ -57,7 +57,13 @@ class CrossAttnRNN(LightningBase):
         self.decoder_fc = nn.Linear(hidden_dim, 1)
         self.save_hyperparameters()
 
+    precision = "fp32"     # "bf16": tcgen05 tensor-core GEMMs (2e-2 contract), see functional.set_precision
+
     def forward(self, ts, categories, colors, fabrics, stores, temporal_features, gtrends, images):
+        with Fv.precision(self.precision):
+            return self._forward(ts, categories, colors, fabrics, stores, temporal_features, gtrends, images)
+
+    def _forward(self, ts, categories, colors, fabrics, stores, temporal_features, gtrends, images):
         bs = ts.shape[0]
         tiles = encode_static(self, categories, colors, fabrics, stores, temporal_features, gtrends,
                               images, by_proj=True, use_trends=bool(self.use_trends))

@@ -99,7 +99,7 @@ class ImageEncoder(nn.Module):
             feat = self.cnn(x)
         B, C = feat.shape[0], feat.shape[1]
         rows = feat.permute(0, 2, 3, 1).reshape(B, -1, C)      # view when the trunk ran channels_last
-        v = Fv.linear(rows.float(), self.fc.weight, self.fc.bias)
+        v = Fv.linear(rows, self.fc.weight, self.fc.bias)          # bf16 rows feed the bf16 tcgen05 GEMM directly
         return Fv.dropout(v, self.dropout.p, self.training)
 
 
