@@ -77,50 +77,59 @@ def _nbytes(batch):
 
 
 class _Clocks:
-    """nvidia-smi sampled every 200 ms during the timed region (B200_PROFILING.md clocks line)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled every 100 ms DURING the timed region through NVML (the
+    source nvidia-smi reads; polling nvidia-smi itself at 200 ms perturbed the step time by 2x)."""
 
     def __init__(self, gpu_index):
+        import threading
         self.idx = gpu_index
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        self.p = None
+        self.sm, self.mx, self.reasons = [], None, set()
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        except Exception:
+            self.nv = None
+
+    def _poll(self):
+        nv = self.nv
+        bits = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
+                "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        while not self._stop.is_set():
+            try:
+                self.sm.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, b in bits.items():
+                    if r & b:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
 
     def start(self):
+        if self.nv is None:
+            return
+        import threading
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
-                                       "--format=csv,noheader,nounits", "-lms", "200"], stdout=self.f,
-                                      stderr=subprocess.DEVNULL)
-        except OSError:
-            self.p = None
+            self.mx = self.nv.nvmlDeviceGetMaxClockInfo(self.h, self.nv.NVML_CLOCK_SM)
+        except Exception:
+            self.mx = None
+        self._thr = threading.Thread(target=self._poll, daemon=True)
+        self._thr.start()
 
     def stop(self):
-        if self.p is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.25)
-        self.p.terminate()
-        self.p.wait()
-        self.f.flush()
-        self.f.seek(0)
-        sm, mx, reasons = [], None, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.f.read().splitlines():
-            c = [x.strip() for x in line.split(",")]
-            if len(c) < 9:
-                continue
-            try:
-                sm.append(float(c[1]))
-                mx = float(c[2])
-            except ValueError:
-                continue
-            for nm, v in zip(names, c[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        os.unlink(self.f.name)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        if self._thr is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable"]}
+        self._stop.set()
+        self._thr.join()
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.mx, "reasons": sorted(self.reasons),
+                "samples": len(sm), "source": "NVML (pynvml), 100 ms"}
 
 
 def _cpu_reference_step_fn(batch_items, threads):
@@ -217,22 +226,26 @@ def run_product(args):
         if reducer:
             reducer.finish()
         zero()
-        return float(loss)                   # device->host read of the step's result
+        return float(loss.detach())          # device->host read of the step's result
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    step_ms = {}
+
+    def timed(fn, steps, tag=None):
         barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        ev[0].record()
         for i in range(steps):
             fn(i)
-        e1.record()
+            ev[i + 1].record()
         barrier()
-        ms = e0.elapsed_time(e1)
+        ms = ev[0].elapsed_time(ev[steps])
+        if tag:
+            step_ms[tag] = [round(ev[i].elapsed_time(ev[i + 1]), 3) for i in range(steps)]
         if world > 1:
             t = torch.tensor([ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -244,12 +257,12 @@ def run_product(args):
     clocks = _Clocks(local)
     clocks.start()
     l0 = _lib.launch_count()
-    ms = timed(step_resident, args.steps)
+    ms = timed(step_resident, args.steps, "resident")
     launches = _lib.launch_count() - l0
     clk = clocks.stop()
     for i in range(2):
         step_e2e(i)
-    ms_e2e = timed(step_e2e, args.steps)
+    ms_e2e = timed(step_e2e, args.steps, "e2e")
 
     # ---- head-only figure (precomputed feature maps in), explains the roofline numbers
     head_ms = None
@@ -343,7 +356,7 @@ def run_product(args):
             "e2e": {"value": total / (ms_e2e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "gpu_launches_per_step": launches / args.steps,
-            "clocks": clk,
+            "clocks": clk, "step_ms": step_ms,
             "head_only": {"value": (B * world * args.steps / (head_ms * 1e-3)) if head_ms else None,
                           "unit": "samples/s", "ms_per_step": head_ms / args.steps if head_ms else None,
                           "note": "feature maps [B,2048,10,10] in; everything libv2f_b200 covers"},

@@ -135,21 +135,51 @@ gemm_f32_kernel(int M, int N, int K, const float* __restrict__ A, int lda, long 
   }
 }
 
-// out[n] = sum_m X[m,n] (+ beta*out[n]);  grid = ceil(N/32), block (32,8)
-__global__ void colsum_kernel(int M, int N, const float* __restrict__ X, int ldx,
-                              float* __restrict__ out, float beta) {
-  __shared__ float red[8][33];
+// out[n] = sum_m X[m,n] (+ beta*out[n]);  grid = (ceil(N/32), chunks), block (32,32).
+// chunks > 1: rows are split over gridDim.y and partial sums added atomically to a pre-zeroed out.
+__global__ void __launch_bounds__(1024)
+colsum_kernel(int M, int N, const float* __restrict__ X, int ldx, float* __restrict__ out, float beta) {
+  __shared__ float red[32][33];
   const int n = blockIdx.x * 32 + threadIdx.x;
+  const int rows_per = (M + gridDim.y - 1) / gridDim.y;
+  const int m_lo = blockIdx.y * rows_per, m_hi = min(M, m_lo + rows_per);
   float s = 0.f;
   if (n < N)
-    for (int m = threadIdx.y; m < M; m += 8) s += X[(long long)m * ldx + n];
+    for (int m = m_lo + threadIdx.y; m < m_hi; m += 32) s += X[(long long)m * ldx + n];
   red[threadIdx.y][threadIdx.x] = s;
   __syncthreads();
   if (threadIdx.y == 0 && n < N) {
     float t = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; i++) t += red[i][threadIdx.x];
-    out[n] = (beta != 0.f ? beta * out[n] : 0.f) + t;
+    for (int i = 0; i < 32; i++) t += red[i][threadIdx.x];
+    if (gridDim.y > 1) atomicAdd(out + n, t);
+    else out[n] = (beta != 0.f ? beta * out[n] : 0.f) + t;
+  }
+}
+
+// C[m,n] = sum_k A[k,m] B[k,n] for skinny outputs (N <= 4): weight gradients of scalar inputs
+// (decoder w_x, decoder_fc, the 3-feature trend GRU input).  grid = ceil(M/32), block (32,32).
+__global__ void __launch_bounds__(1024)
+skinny_tn_kernel(int M, int N, int K, const float* __restrict__ A, int lda, const float* __restrict__ B,
+                 int ldb, float* __restrict__ C, int ldc) {
+  __shared__ float red[4][32][33];
+  const int m = blockIdx.x * 32 + threadIdx.x;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  if (m < M)
+    for (int k = threadIdx.y; k < K; k += 32) {
+      const float a = A[(long long)k * lda + m];
+#pragma unroll
+      for (int n = 0; n < 4; n++)
+        if (n < N) acc[n] = fmaf(a, B[(long long)k * ldb + n], acc[n]);
+    }
+#pragma unroll
+  for (int n = 0; n < 4; n++) red[n][threadIdx.y][threadIdx.x] = acc[n];
+  __syncthreads();
+  if (threadIdx.y < N && m < M) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; i++) t += red[threadIdx.y][i][threadIdx.x];
+    C[(long long)m * ldc + threadIdx.y] = t;
   }
 }
 
@@ -164,6 +194,11 @@ extern "C" int v2f_gemm_f32(int ta, int tb, int M, int N, int K, const float* A,
   if (M == 0 || N == 0 || batch == 0) return V2F_OK;
   V2F_REQUIRE(A && B && C, V2F_ERR_BAD_ARG);
   V2F_REQUIRE(batch <= 65535, V2F_ERR_BAD_ARG);
+  if (ta == 1 && tb == 0 && N <= 4 && batch == 1 && !bias && beta == 0.f && act == 0 && K >= 256) {
+    skinny_tn_kernel<<<(M + 31) / 32, dim3(32, 32), 0, (cudaStream_t)stream>>>(M, N, K, A, lda, B, ldb, C, ldc);
+    V2F_CHECK_LAUNCH();
+    return V2F_OK;
+  }
   dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, batch), block(256);
   cudaStream_t s = (cudaStream_t)stream;
 #define LAUNCH(TA_, TB_) \
@@ -180,7 +215,13 @@ extern "C" int v2f_gemm_f32(int ta, int tb, int M, int N, int K, const float* A,
 
 extern "C" int v2f_colsum_f32(int M, int N, const float* X, int ldx, float* out, float beta, void* stream) {
   V2F_REQUIRE(M >= 0 && N > 0 && X && out, V2F_ERR_BAD_ARG);
-  v2f::colsum_kernel<<<(N + 31) / 32, dim3(32, 8), 0, (cudaStream_t)stream>>>(M, N, X, ldx, out, beta);
+  int chunks = 1;
+  if (beta == 0.f && M >= 4096) {   // long reductions: split rows over the grid, atomics onto zeros
+    chunks = (M + 1023) / 1024;
+    if (chunks > 64) chunks = 64;
+    cudaMemsetAsync(out, 0, sizeof(float) * (size_t)N, (cudaStream_t)stream);
+  }
+  v2f::colsum_kernel<<<dim3((N + 31) / 32, chunks), dim3(32, 32), 0, (cudaStream_t)stream>>>(M, N, X, ldx, out, beta);
   V2F_CHECK_LAUNCH();
   return V2F_OK;
 }

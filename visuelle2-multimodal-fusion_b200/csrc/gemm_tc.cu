@@ -337,8 +337,11 @@ extern "C" int v2f_gemm_tc_batched(int kind, int M, int N, int K, const void* A,
   V2F_REQUIRE((long long)batch * splits <= 65535, V2F_ERR_BAD_ARG);
   // tile width: keep >= ~1 wave of CTAs on 148 SMs for the small-M recurrent GEMMs
   const int mt = (M + TC_BM - 1) / TC_BM;
+  // smallest tile width that still fits the whole problem in one wave of 148 CTAs (every CTA must
+  // stream the full 128 x K slab of A, so fewer, wider tiles re-read A less); else 128
   int bn = 128;
-  while (bn > 16 && (long long)mt * ((N + bn - 1) / bn) * splits * batch < 120) bn >>= 1;
+  for (int cand = 16; cand < 128; cand <<= 1)
+    if ((long long)mt * ((N + cand - 1) / cand) * splits * batch <= 148) { bn = cand; break; }
   const int bk = 128 / elem;
   const int total_kb = (K + bk - 1) / bk;
   TcArgs a{M, N, K, C, ldc, bias, beta, act, (total_kb + splits - 1) / splits, splits > 1 ? 1 : 0, splits, sC};
