@@ -125,6 +125,9 @@ typedef struct v2f_decode_params {
    * for transposed activation stacks of the weight-gradient products                          */
   float *WcatT, *W_ihcT, *W_meT, *We_mmT, *ws;
   long long ws_floats;
+  /* optional scratch that enables the streaming (TMA-staged, 148-way balanced) attention kernels:
+   * N * (ceil(Li/8)+ceil(Lt/8)) * (E+2) floats.  NULL selects the simple per-(row,modality) kernels. */
+  float *attn_ws;
 } v2f_decode_params;
 
 int v2f_decode_fwd(const v2f_decode_params* p, void* stream);

@@ -79,3 +79,38 @@ def test_cuda_matches_oracle_default_dims(model, T, precision, tol):
         # autograd returns rounding noise): compare those absolutely
         floor = 1e-6 if k.endswith("attn_linear.bias") else 1e-6 * float(p.grad.abs().max() + 1e-3)
         assert_close(grads[k], p.grad, tol, "grad:" + k, floor=floor)
+
+
+def test_streaming_attention_equals_simple_kernels():
+    """The TMA-staged streaming attention (148-way split + partial-softmax combine) against the
+    simple per-(row, modality) kernels, B=40 rows at the default dims."""
+    import visuelle2_multimodal_fusion_b200.functional as Fv
+    import visuelle2_multimodal_fusion_b200.synth as synth
+    import torch.nn as nn
+    import visuelle2_multimodal_fusion_b200.models.modules as mods
+    from visuelle2_multimodal_fusion_b200.models import CrossAttnRNN210
+    orig = mods.resnet101_trunk
+    mods.resnet101_trunk = lambda: nn.Identity()
+    try:
+        torch.manual_seed(0)
+        cat_d, col_d, fab_d = synth.label_dicts()
+        m = CrossAttnRNN210.CrossAttnRNN(512, 512, 512, cat_d, col_d, fab_d, synth.STORE_N, 3).cuda().eval()
+    finally:
+        mods.resnet101_trunk = orig
+    data, feat = synth.make_batch(40, out_len=10, seed=3, feat_hw=10)
+    data = tuple(t.cuda() for t in data)
+    res = {}
+    for flag in (True, False):
+        Fv.STREAM_ATTENTION = flag
+        try:
+            f = feat.cuda().clone().requires_grad_(True)
+            torch.manual_seed(9)
+            out, _ = m(*data, f)
+            out.square().mean().backward()
+            res[flag] = (out.detach().clone(), f.grad.clone(),
+                         m.img_attention.encoder_linear.weight.grad.clone(), m.trend_linear.weight.grad.clone())
+            m.zero_grad(set_to_none=True)
+        finally:
+            Fv.STREAM_ATTENTION = True
+    for a, b in zip(res[True], res[False]):
+        assert float((a - b).abs().max()) <= 2e-5 * float(b.abs().max()) + 1e-9

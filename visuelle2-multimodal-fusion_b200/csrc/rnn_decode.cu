@@ -8,6 +8,7 @@
 // once (forward) and once more (backward); their gradients are produced after the time loop
 // in one pass that re-derives tanh from the saved per-step scalars, so each gradient tile is
 // written once (SURVEY.md section 8d byte model).
+#include "attn.cuh"
 #include "gemm_dispatch.cuh"
 
 namespace v2f {
@@ -35,18 +36,6 @@ __device__ __forceinline__ void block_sum(float (&v)[NV], float* red) {
     v[i] = t;
   }
 }
-
-struct AttnArgs {
-  int N, W, E, Li, Lt, ldS;
-  const float *Himg, *Vimg, *Htr, *Ptr;
-  const float* S;       // [N, ldS] of this step: s_img | s_tr | s_mm | gh
-  const float* w_att;   // [3,E]
-  const float* beta_att;
-  const float* b_tl;
-  float* C;             // [N,2,E] of this step
-  float *alpha_img, *alpha_tr;  // [N,Li], [N,Lt] of this step
-  int mod_first;        // grid.y index 0 maps to modality mod_first (0 img, 1 trend)
-};
 
 // One CTA per (row, modality): energies -> softmax -> context.  Tiles streamed with 128-bit loads.
 __global__ void __launch_bounds__(ATT_THREADS)
@@ -135,19 +124,6 @@ attn_fwd_kernel(AttnArgs a) {
     a.C[((long long)n * 2 + mod) * E + x] = t;
   }
 }
-
-struct AttnBwdArgs {
-  int N, W, E, Li, Lt, ldS;
-  const float *Himg, *Vimg, *Htr, *Ptr;
-  const float* S;
-  const float* w_att;
-  const float* DC;                 // [N,2,E] of this step
-  const float *alpha_img, *alpha_tr;
-  float *DE_img, *DE_tr;           // [N,L] of this step
-  float* DS;                       // [N,ldS] of this step (writes cols mod*E ..)
-  float* dw_acc;                   // [N,3,E]
-  int mod_first;
-};
 
 __global__ void __launch_bounds__(ATT_THREADS)
 attn_bwd_kernel(AttnBwdArgs a) {
@@ -652,10 +628,14 @@ extern "C" int v2f_decode_fwd(const v2f_decode_params* p, void* st) {
       AttnArgs a{N, p->W, E, p->Li, p->Lt, ldS, p->Himg, p->Vimg, p->Htr, p->Ptr, S, p->w_att,
                  p->beta_att, p->b_tl, C, p->alpha_img + (long long)t * N * p->Li,
                  p->alpha_tr + (long long)t * N * p->Lt, use_img ? 0 : 1};
-      prof_begin(V2F_K_ATTN_FWD, s);
-      attn_fwd_kernel<<<dim3(N, (use_img ? 1 : 0) + (use_tr ? 1 : 0)), ATT_THREADS, smem, s>>>(a);
-      prof_end(V2F_K_ATTN_FWD, s);
-      V2F_CHECK_LAUNCH();
+      if (p->attn_ws && attn_stream_supported(E)) {
+        V2F_TRY(attn_stream_fwd(a, use_img, use_tr, p->attn_ws, s));
+      } else {
+        prof_begin(V2F_K_ATTN_FWD, s);
+        attn_fwd_kernel<<<dim3(N, (use_img ? 1 : 0) + (use_tr ? 1 : 0)), ATT_THREADS, smem, s>>>(a);
+        prof_end(V2F_K_ATTN_FWD, s);
+        V2F_CHECK_LAUNCH();
+      }
       // HC = C We_mm^T  ([2N,E] view)
       NT(2 * N, E, E, C, E, p->We_mm, E, HC, E, nullptr, 0.f);
     }

@@ -452,6 +452,7 @@ def embed(temporal, Wt, bt, tables, idx, drop=None):
 
 # --------------------------------------------------------------------------- fused decoder
 VARIANT_210, VARIANT_21, VARIANT_DEMAND = 0, 1, 2
+STREAM_ATTENTION = True      # TMA-staged streaming attention kernels when the dims allow (E % 256 == 0)
 
 
 class _Decode(torch.autograd.Function):
@@ -504,6 +505,8 @@ class _Decode(torch.autograd.Function):
             U=_f32(T, N, E, device=dev), CTX=_f32(T, N, E, device=dev),
             GI=_f32(N, max(3 * H, 1), device=dev), RZN=_f32(T, N, max(3 * H, 1), device=dev),
             xin=_f32(T + 1, N, device=dev, zero=True))
+        if STREAM_ATTENTION and E % 256 == 0 and E <= 1024:
+            keep["attn_ws"] = _f32(N * ((Li + 7) // 8 + (Lt + 7) // 8) * (E + 2), device=dev)
         for k, v in keep.items():
             setattr(p, k, ptr(v, allow_none=True))
         check(_lib.lib().v2f_decode_fwd(ctypes.byref(p), stream()), "v2f_decode_fwd")
