@@ -126,7 +126,7 @@ typedef struct v2f_decode_params {
   float *WcatT, *W_ihcT, *W_meT, *We_mmT, *ws;
   long long ws_floats;
   /* optional scratch that enables the streaming (TMA-staged, 148-way balanced) attention kernels:
-   * N * (ceil(Li/8)+ceil(Lt/8)) * (E+2) floats.  NULL selects the simple per-(row,modality) kernels. */
+   * N * (ceil(Li/8)+ceil(Lt/8)) * (2E+2) floats.  NULL selects the simple per-(row,modality) kernels. */
   float *attn_ws;
 } v2f_decode_params;
 

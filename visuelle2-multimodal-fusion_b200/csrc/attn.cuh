@@ -14,6 +14,7 @@ struct AttnArgs {
   float* C;             // [N,2,E] of this step
   float *alpha_img, *alpha_tr;  // [N,Li], [N,Lt] of this step
   int mod_first;        // grid.y index 0 maps to modality mod_first (0 img, 1 trend)
+  int approx;           // 1: MUFU.TANH in the streaming kernels (tensor-core precision mode)
 };
 
 struct AttnBwdArgs {
@@ -36,5 +37,7 @@ struct AttnBwdArgs {
 bool attn_stream_supported(int E);
 long long attn_stream_ws_floats(int N, int Li, int Lt, int E);
 int attn_stream_fwd(const AttnArgs& a, bool use_img, bool use_tr, float* ws, cudaStream_t s);
+int attn_stream_bwd(const AttnBwdArgs& a, const float* C, const float* b_tl, bool use_img, bool use_tr,
+                    int approx, float* ws, cudaStream_t s);
 
 }  // namespace v2f

@@ -50,6 +50,21 @@ __device__ __forceinline__ float tanh_acc(float x) {
   float t = __expf(2.0f * x);
   return 1.0f - __fdividef(2.0f, t + 1.0f);
 }
+// Lean variants for the streaming attention kernels (issue-bound there): raw ex2/rcp without the
+// denormal / huge-argument slow paths (ftz saturates correctly: e^{2x} -> inf gives 1, -> 0 gives -1),
+// |err| ~ 4e-7; APPROX = the single-instruction MUFU.TANH (|err| ~ 5e-4, tensor-core mode only).
+template <bool APPROX>
+__device__ __forceinline__ float tanh_fast(float x) {
+  if (APPROX) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+  }
+  float t, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(x * 2.885390081777927f));   // e^{2x}
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t + 1.0f));
+  return fmaf(-2.0f, r, 1.0f);
+}
 // sigmoid, same construction.
 __device__ __forceinline__ float sigmoid_acc(float x) {
   return __fdividef(1.0f, 1.0f + __expf(-x));

@@ -627,7 +627,7 @@ extern "C" int v2f_decode_fwd(const v2f_decode_params* p, void* st) {
     if (use_img || use_tr) {
       AttnArgs a{N, p->W, E, p->Li, p->Lt, ldS, p->Himg, p->Vimg, p->Htr, p->Ptr, S, p->w_att,
                  p->beta_att, p->b_tl, C, p->alpha_img + (long long)t * N * p->Li,
-                 p->alpha_tr + (long long)t * N * p->Lt, use_img ? 0 : 1};
+                 p->alpha_tr + (long long)t * N * p->Lt, use_img ? 0 : 1, p->precision != 0};
       if (p->attn_ws && attn_stream_supported(E)) {
         V2F_TRY(attn_stream_fwd(a, use_img, use_tr, p->attn_ws, s));
       } else {
@@ -718,10 +718,15 @@ extern "C" int v2f_decode_bwd(const v2f_decode_params* p, void* st) {
                     p->alpha_img + (long long)t * N * p->Li, p->alpha_tr + (long long)t * N * p->Lt,
                     p->DE_img + (long long)t * N * p->Li, p->DE_tr + (long long)t * N * p->Lt, DS,
                     p->dw_acc, use_img ? 0 : 1};
-      prof_begin(V2F_K_ATTN_BWD, s);
-      attn_bwd_kernel<<<dim3(N, (use_img ? 1 : 0) + (use_tr ? 1 : 0)), ATT_THREADS, smem, s>>>(a);
-      prof_end(V2F_K_ATTN_BWD, s);
-      V2F_CHECK_LAUNCH();
+      if (p->attn_ws && attn_stream_supported(E)) {
+        V2F_TRY(attn_stream_bwd(a, p->C + (long long)t * N * 2 * E, p->b_tl, use_img, use_tr, p->precision != 0,
+                                p->attn_ws, s));
+      } else {
+        prof_begin(V2F_K_ATTN_BWD, s);
+        attn_bwd_kernel<<<dim3(N, (use_img ? 1 : 0) + (use_tr ? 1 : 0)), ATT_THREADS, smem, s>>>(a);
+        prof_end(V2F_K_ATTN_BWD, s);
+        V2F_CHECK_LAUNCH();
+      }
     }
     // dh (+)= DS Wcat      (gru: dh holds the direct z-path part; else dh is overwritten)
     NN(N, H, ldS, DS, ldS, p->Wcat, H, WcatT, ldS, p->dh, H, gru ? 1.f : 0.f);

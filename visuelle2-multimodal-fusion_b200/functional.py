@@ -506,7 +506,7 @@ class _Decode(torch.autograd.Function):
             GI=_f32(N, max(3 * H, 1), device=dev), RZN=_f32(T, N, max(3 * H, 1), device=dev),
             xin=_f32(T + 1, N, device=dev, zero=True))
         if STREAM_ATTENTION and E % 256 == 0 and E <= 1024:
-            keep["attn_ws"] = _f32(N * ((Li + 7) // 8 + (Lt + 7) // 8) * (E + 2), device=dev)
+            keep["attn_ws"] = _f32(N * ((Li + 7) // 8 + (Lt + 7) // 8) * (2 * E + 2), device=dev)
         for k, v in keep.items():
             setattr(p, k, ptr(v, allow_none=True))
         check(_lib.lib().v2f_decode_fwd(ctypes.byref(p), stream()), "v2f_decode_fwd")
