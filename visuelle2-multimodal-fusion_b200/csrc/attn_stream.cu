@@ -169,10 +169,19 @@ attn_stream_fwd_kernel(StreamArgs sa) {
     m_run = m_new;
 #pragma unroll
     for (int i = 0; i < CPT; i++) cacc[i] *= scale;
-    for (int j = 0; j < nj; j++) {
-      const float p = __shfl_sync(FULL, pj, j);
+    if (nj == ST_CH) {     // full chunk: fully unrolled, loads batched ahead of the FMAs
 #pragma unroll
-      for (int i = 0; i < CPT; i++) cacc[i] = fmaf(p, Vs[j * E + tid + 256 * i], cacc[i]);
+      for (int j = 0; j < ST_CH; j++) {
+        const float p = __shfl_sync(FULL, pj, j);
+#pragma unroll
+        for (int i = 0; i < CPT; i++) cacc[i] = fmaf(p, Vs[j * E + tid + 256 * i], cacc[i]);
+      }
+    } else {
+      for (int j = 0; j < nj; j++) {
+        const float p = __shfl_sync(FULL, pj, j);
+#pragma unroll
+        for (int i = 0; i < CPT; i++) cacc[i] = fmaf(p, Vs[j * E + tid + 256 * i], cacc[i]);
+      }
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[s]);
@@ -348,13 +357,26 @@ attn_stream_bwd_kernel(StreamBwdArgs sa) {
       eb[warp] = 0.f;
     }
     named_bar_sync(1, ST_CONS);
-    for (int j = 0; j < nj; j++) {
-      const float de = eb[j];
+    if (nj == ST_CH) {
 #pragma unroll
-      for (int i = 0; i < CPT; i++) {
-        const float q = tanh_fast<APPROX>(Hs[j * E + tid + 256 * i] + scol[i]);
-        sacc[i] = fmaf(de, 1.f - q * q, sacc[i]);
-        wacc[i] = fmaf(de, q, wacc[i]);
+      for (int j = 0; j < ST_CH; j++) {
+        const float de = eb[j];
+#pragma unroll
+        for (int i = 0; i < CPT; i++) {
+          const float q = tanh_fast<APPROX>(Hs[j * E + tid + 256 * i] + scol[i]);
+          sacc[i] = fmaf(de, fmaf(-q, q, 1.f), sacc[i]);
+          wacc[i] = fmaf(de, q, wacc[i]);
+        }
+      }
+    } else {
+      for (int j = 0; j < nj; j++) {
+        const float de = eb[j];
+#pragma unroll
+        for (int i = 0; i < CPT; i++) {
+          const float q = tanh_fast<APPROX>(Hs[j * E + tid + 256 * i] + scol[i]);
+          sacc[i] = fmaf(de, fmaf(-q, q, 1.f), sacc[i]);
+          wacc[i] = fmaf(de, q, wacc[i]);
+        }
       }
     }
     __syncwarp();
