@@ -180,7 +180,7 @@ def run_reference(args):
                    "per_gpu_batch": 128, "E": E, "A": A, "H": H, "out_len": OUT_LEN, "image": 299},
         "cpu_baseline": {"value": val, "unit": "samples/s", "cores": threads, "kind": "port", "sample": desc},
         "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    }), flush=True)
 
 
 def run_product(args):
@@ -364,7 +364,7 @@ def run_product(args):
             "roofline_other": {k: v for k, v in roof.items() if k != "attn_fwd_kernel"},
             "cpu_baseline": cpu,
         }
-        print(json.dumps(out))
+        print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
