@@ -52,6 +52,14 @@ def oracle_run(blob, requires_grad=True):
                                          use_teacher_forcing=cfg["tf"], tf_mask=blob["tf_mask"])
         extras = dict(img_alphas=torch.stack(ia), mm_alphas=torch.stack(ma))
         loss = torch.nn.functional.mse_loss(inp["ts"], out.squeeze())
+    elif model.startswith("GTM:"):
+        from oracle import gtm
+        train = cfg["mode"] != "eval"
+        out, _ = gtm.gtm_family_forward(model[4:], P, inp["item_sales"], inp["cat"], inp["col"], inp["fab"],
+                                        inp["store"], inp["temporal"], inp["gtrends"], feat, output_len=cfg["T"],
+                                        heads=cfg["heads"], autoregressive=cfg["autoregressive"], training=train,
+                                        drop=False, query_modality=cfg["query_modality"])
+        loss = torch.nn.functional.mse_loss(inp["y"].reshape(-1), out.reshape(-1))
     else:
         raise KeyError(model)
     return out, loss, extras, P, feat
