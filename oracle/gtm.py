@@ -239,7 +239,7 @@ def encoder_layer_v2(x, P, prefix, heads, mask, p_drop, drop):
     hd = D // heads
     o, qh = _qkv_attention(x, x, P, prefix + "self_attn.", heads, mask, p_drop, drop)
     oh = o.reshape(L, N * heads, hd).transpose(0, 1)                     # [N*heads, L, hd]
-    oh = oh * torch.sigmoid(lin(qh / (hd ** -0.5), P, prefix + "self_attn.gate_proj."))
+    oh = oh * torch.sigmoid(lin(qh, P, prefix + "self_attn.gate_proj."))
     o = lin(oh.transpose(0, 1).reshape(L, N, D), P, prefix + "self_attn.out_proj.")
     x = layer_norm(x + F.dropout(o, p_drop, drop), P, prefix + "norm1.")
     f = lin(F.dropout(F.relu(lin(x, P, prefix + "linear1.")), p_drop, drop), P, prefix + "linear2.")

@@ -16,12 +16,13 @@ GTM_CASES = ["gtm_demand_eval", "gtm_demand_train", "gtm_sofore1_train", "gtm_ar
 def test_oracle_matches_reference_golden(name):
     # GTM family: two fp32 CPU evaluations of the same graph already differ by 1.1e-5 on one tensor
     # (conv / einsum summation order amplified by BatchNorm batch statistics), so the fp32 noise floor
-    # there is taken as 3e-5; the RNN family stays at the 1e-5 contract.
+    # there is taken as 3e-5; the RNN family stays at the 1e-5 contract.  Gradients that are exactly zero
+    # in exact arithmetic (a bias feeding train-mode BatchNorm) are rounding noise ~2e-6 on both sides.
     tol = TOL if name in RNN_CASES else 3e-5
-    _check(name, tol)
+    _check(name, tol, 1e-7 if name in RNN_CASES else 3e-6)
 
 
-def _check(name, TOL):
+def _check(name, TOL, floor):
     blob = load_golden(name)
     out, loss, extras, P, feat = oracle_run(blob)
     assert_close(out, blob["out"], TOL, name + ":out")
@@ -35,4 +36,4 @@ def _check(name, TOL):
             assert P[k].grad is None or float(P[k].grad.abs().max()) == 0.0, f"{name}: {k} should get no grad"
         else:
             assert P[k].grad is not None, f"{name}: {k} has no oracle grad"
-            assert_close(P[k].grad, g, TOL, f"{name}:grad:{k}")
+            assert_close(P[k].grad, g, TOL, f"{name}:grad:{k}", floor=floor)
