@@ -28,6 +28,17 @@ def assert_close(a, b, tol, what, floor=1e-7):
     assert diff <= tol * scale + floor, f"{what}: max|diff|={diff:.3e} scale={scale:.3e} rel={diff / max(scale, 1e-30):.3e} > {tol}"
 
 
+def noise_only_grads(blob):
+    """Parameters whose gradient is exactly zero in exact arithmetic (both the reference's autograd and
+    ours return rounding noise there): a bias added right before train-mode BatchNorm (GTM fusion) and the
+    attn_linear biases feeding a softmax (RNN family).  Compared absolutely."""
+    names = set()
+    if blob["model"] == "GTM:gtm" and blob["cfg"]["mode"] != "eval":
+        names |= {"image_encoder.projection.bias", "dummy_encoder.dummy_fusion.bias"}
+    names |= {k for k in blob["grads"] if k.endswith("attn_linear.bias")}
+    return names
+
+
 def oracle_run(blob, requires_grad=True):
     """Run the oracle on a golden blob's inputs/weights; returns (out, extras, P, feat)."""
     from oracle import rnn

@@ -2,7 +2,7 @@
 import pytest
 import torch
 
-from helpers import assert_close, load_golden, oracle_run
+from helpers import assert_close, load_golden, noise_only_grads, oracle_run
 
 RNN_CASES = ["rnn210_small", "rnn210_notf", "rnn21_small", "demand_small", "demand_notf"]
 TOL = 1e-5   # fp32 contract, SURVEY.md section 8d
@@ -19,7 +19,7 @@ def test_oracle_matches_reference_golden(name):
     # there is taken as 3e-5; the RNN family stays at the 1e-5 contract.  Gradients that are exactly zero
     # in exact arithmetic (a bias feeding train-mode BatchNorm) are rounding noise ~2e-6 on both sides.
     tol = TOL if name in RNN_CASES else 3e-5
-    _check(name, tol, 1e-7 if name in RNN_CASES else 3e-6)
+    _check(name, tol, 1e-7)
 
 
 def _check(name, TOL, floor):
@@ -30,10 +30,11 @@ def _check(name, TOL, floor):
     for k, v in extras.items():
         assert_close(v, blob[k], TOL, f"{name}:{k}")
     loss.backward()
+    noisy = noise_only_grads(blob)
     assert_close(feat.grad, blob["grad_feat"], TOL, name + ":grad_feat")
     for k, g in blob["grads"].items():
         if g is None:
             assert P[k].grad is None or float(P[k].grad.abs().max()) == 0.0, f"{name}: {k} should get no grad"
         else:
             assert P[k].grad is not None, f"{name}: {k} has no oracle grad"
-            assert_close(P[k].grad, g, TOL, f"{name}:grad:{k}", floor=floor)
+            assert_close(P[k].grad, g, TOL, f"{name}:grad:{k}", floor=2e-5 if k in noisy else floor)
