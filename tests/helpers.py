@@ -35,6 +35,7 @@ def noise_only_grads(blob):
     names = set()
     if blob["model"] == "GTM:gtm" and blob["cfg"]["mode"] != "eval":
         names |= {"image_encoder.projection.bias", "dummy_encoder.dummy_fusion.bias"}
+        names |= {f"dummy_encoder.{n}_emb.bias" for n in ("day", "week", "month", "year")}
     names |= {k for k in blob["grads"] if k.endswith("attn_linear.bias")}
     return names
 
