@@ -188,6 +188,68 @@ int v2f_embed_bwd(int B, int E, const float* temporal, const long long* idx, con
  * TSEmbedder / ImageEncoder, models/CrossAttnRNN210.py:21-24,67-72.                           */
 int v2f_mul_f32(long long n, const float* x, const float* m, float* out, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Row-local operators of the GTM family (GTM_Visuelle2, Proposed_model v1-v4); csrc/gtm_ops.cu.
+ * ------------------------------------------------------------------------------------------ */
+/* y = LayerNorm(x + a*m) * gamma + beta over the last dim D (<= 1024) of [M,D]; a, m optional
+ * (m: dropout keep-mask of the residual branch, already scaled).  Saves xhat [M,D], rstd [M].
+ * Post-LN residuals of nn.TransformerEncoderLayer/DecoderLayer (models/GTM_Visuelle2.py:52-53,
+ * 200-202), GatedResidualBlock.norm (models/Proposed_model.py:147-155), fusion_fc LayerNorm
+ * (models/Proposed_model_v4.py:177).                                                          */
+int v2f_add_ln_fwd(int M, int D, const float* x, const float* a, const float* m, const float* gamma,
+                   const float* beta, float eps, float* y, float* xhat, float* rstd, void* stream);
+/* Number of partial-sum blocks the backward uses: part must hold blocks*2*D floats. */
+int v2f_add_ln_bwd_blocks(int M);
+/* dx [M,D] (= gradient of x), da [M,D] or NULL (= dx*m), dgb [2,D] = (dgamma, dbeta). */
+int v2f_add_ln_bwd(int M, int D, const float* dy, const float* xhat, const float* rstd,
+                   const float* gamma, const float* m, float* dx, float* da, float* part, float* dgb,
+                   void* stream);
+/* nn.BatchNorm1d over [B,D] (models/GTM_Visuelle2.py:158; FusionBlock models/Proposed_model_v3.py:163):
+ * training!=0: batch statistics (biased variance) and running-stat update (unbiased variance,
+ * momentum); else running statistics.  Saves the mean / rstd used, [D] each.                   */
+int v2f_bn1d_fwd(int B, int D, const float* x, const float* gamma, const float* beta, float* run_mean,
+                 float* run_var, int training, float momentum, float eps, float* y, float* save_mean,
+                 float* save_rstd, void* stream);
+int v2f_bn1d_bwd(int B, int D, const float* x, const float* dy, const float* gamma,
+                 const float* save_mean, const float* save_rstd, int training, float* dx,
+                 float* dgamma, float* dbeta, void* stream);
+/* Sigmoid gates: mode 0: out = x*sigmoid(g) (models/Proposed_model.py:217, _v2.py:598,682,
+ * _v3.py:222-227); mode 1: out = x + x*sigmoid(g) (Proposed_model.py:154, _v2.py:635, _v4.py:186-192). */
+int v2f_gate_fwd(long long n, const float* x, const float* g, int mode, float* out, void* stream);
+int v2f_gate_bwd(long long n, const float* x, const float* g, const float* dout, int mode, float* dx,
+                 float* dg, void* stream);
+/* out = a + b (decoder_input = sales_base + static_context, models/GTM_Visuelle2.py:246-247). */
+int v2f_add_f32(long long n, const float* a, const float* b, float* out, void* stream);
+/* out = max(x, 0) (ReLU after LayerNorm in fusion_fc, models/Proposed_model_v4.py:176-179) and
+ * out = dy where y > 0 else 0 (its backward, also the backward of the ReLU epilogue of v2f_gemm_*). */
+int v2f_relu_fwd(long long n, const float* x, float* out, void* stream);
+int v2f_relu_bwd(long long n, const float* dy, const float* y, float* out, void* stream);
+/* out[r, i] = x[r, i] + p[i], i < n: PositionalEncoding.forward (models/GTM_Visuelle2.py:26-28). */
+int v2f_add_bcast(long long rows, long long n, const float* x, const float* p, float* out, void* stream);
+/* Strided 2-D copy (column concatenation / slicing: torch.cat of the fusion networks). */
+int v2f_copy2d(int rows, int cols, const float* src, long long lds, float* dst, long long ldd, void* stream);
+/* repeat_interleave over windows, out[b*W+w,:] = x[b,:] (models/GTM_Visuelle2.py:231-235), and
+ * its gradient dx[b,:] = sum_w dout[b*W+w,:].                                                  */
+int v2f_repeat_rows(int B, int W, long long D, const float* x, float* out, void* stream);
+int v2f_fold_rows(int B, int W, long long D, const float* dout, float* dx, void* stream);
+/* AttributeEncoder of the GTM family (models/GTM_Visuelle2.py:81-96): out [B,4,E] = stacked rows of
+ * the four embedding tables (idx [4,B] int64), times the optional keep-mask drop [B,4,E].        */
+int v2f_gather4_fwd(int B, int E, const float* const* tables, const long long* idx, const float* drop,
+                    float* out, void* stream);
+int v2f_gather4_bwd(int B, int E, const long long* idx, const float* drop, const float* dout,
+                    const int* table_rows, float* const* dtables, void* stream);
+/* DummyEmbedder / TemporalEmbedder front (models/GTM_Visuelle2.py:129-145):
+ * out [B,4,E], out[b,k,:] = temporal[b,k] * Wt[k,:] + bt[k,:].                                  */
+int v2f_feat4_fwd(int B, int E, const float* temporal, const float* Wt, const float* bt, float* out,
+                  void* stream);
+int v2f_feat4_bwd(int B, int E, const float* temporal, const float* dout, float* dWt, float* dbt,
+                  void* stream);
+/* Global average pool of the trunk's feature map (ImageEncoder.pool, models/GTM_Visuelle2.py:117,
+ * 123-125), taken before the 1x1 projection (SURVEY.md 8a identity 5).  layout 0: x [B,C,L];
+ * layout 1: x [B,L,C] (channels_last).  kind 0: bf16, 1: fp32.  out/dout [B,C] fp32; dx as x.    */
+int v2f_meanpool_fwd(int B, int L, int C, const void* x, int layout, int kind, float* out, void* stream);
+int v2f_meanpool_bwd(int B, int L, int C, const float* dout, int layout, int kind, void* dx, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

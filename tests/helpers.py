@@ -78,6 +78,32 @@ def oracle_run(blob, requires_grad=True):
 
 
 # ------------------------------------------------------------------ product side (CUDA only)
+_GTM_TRUNK_PATCH = []
+
+
+def gtm_product_ctor(variant):
+    """The GTM-family drop-in class for a variant, with the backbone factory patched to identity."""
+    import importlib
+    import torch.nn as nn
+    modname, clsname = {"gtm": ("GTM_Visuelle2", "GTM_Visuelle2"), "v1": ("Proposed_model", "GatedMultimodal_Visuelle2"),
+                        "v2": ("Proposed_model_v2", "GatedMultimodal_Visuelle2"),
+                        "v3": ("Proposed_model_v3", "TARG_M4FT_Visuelle2"),
+                        "v4": ("Proposed_model_v4", "GatedMultimodal_Visuelle2")}[variant]
+    import visuelle2_multimodal_fusion_b200.models._gtm as g
+    v3 = importlib.import_module("visuelle2_multimodal_fusion_b200.models.Proposed_model_v3")
+    for holder in (g, v3):
+        _GTM_TRUNK_PATCH.append((holder, holder.resnet101_trunk))
+        holder.resnet101_trunk = lambda: nn.Identity()
+    mod = importlib.import_module("visuelle2_multimodal_fusion_b200.models." + modname)
+    return getattr(mod, clsname)
+
+
+def _restore_gtm_trunk():
+    while _GTM_TRUNK_PATCH:
+        holder, fn = _GTM_TRUNK_PATCH.pop()
+        holder.resnet101_trunk = fn
+
+
 def product_model(blob, device="cuda"):
     """The drop-in module for a golden blob, backbone replaced by identity, weights loaded."""
     import torch.nn as nn
@@ -98,14 +124,28 @@ def product_model(blob, device="cuda"):
             m = CrossAttnRNNDemand.CrossAttnRNN(cfg["E"], cfg["E"], 3, cfg["H"], cat_d, col_d, fab_d,
                                                 synth.STORE_N, True, True, True, True, out_len=cfg["T"],
                                                 use_teacher_forcing=cfg["tf"])
+        elif name.startswith("GTM:"):
+            m = gtm_product_ctor(name[4:])(cfg["E"], cfg["H"], cfg["T"], cfg["heads"], 1, 1, 1, cat_d, col_d, fab_d,
+                                           synth.STORE_N, 52, 3, 0, use_encoder_mask=1,
+                                           autoregressive=cfg["autoregressive"],
+                                           **(dict(query_modality=cfg["query_modality"]) if name == "GTM:v3" else {}))
         else:
             raise KeyError(name)
     finally:
         mods.resnet101_trunk = orig
+        _restore_gtm_trunk()
     missing, unexpected = m.load_state_dict(blob["state"], strict=False)
     assert not unexpected, unexpected
     assert all(k.startswith("image_encoder.cnn") for k in missing), missing
-    return m.to(device).eval()
+    m = m.to(device).eval()
+    if name.startswith("GTM:") and cfg["mode"] != "eval":
+        m.train()            # goldens of mode train_nodrop: BatchNorm batch statistics, every dropout p = 0
+        for mod in m.modules():
+            if isinstance(mod, nn.Dropout):
+                mod.p = 0.0
+            if isinstance(mod, nn.MultiheadAttention):
+                mod.dropout = 0.0
+    return m
 
 
 def product_run(m, blob, device="cuda"):
@@ -116,7 +156,11 @@ def product_run(m, blob, device="cuda"):
     torch.manual_seed(blob["cfg"]["seed"] + 1)       # host teacher-forcing draws, as in make_golden
     name = blob["model"]
     extras = {}
-    if name == "CrossAttnRNNDemand":
+    if name.startswith("GTM:"):
+        out, _ = m(inp["item_sales"], inp["cat"], inp["col"], inp["fab"], inp["store"], inp["temporal"],
+                   inp["gtrends"], feat)
+        loss = F.mse_loss(inp["y"].reshape(-1), out.reshape(-1))
+    elif name == "CrossAttnRNNDemand":
         out, ia, ma = m(inp["ts"], inp["cat"], inp["col"], inp["fab"], inp["store"], inp["temporal"],
                         inp["gtrends"], feat)
         extras = dict(img_alphas=torch.stack(ia), mm_alphas=torch.stack(ma))
@@ -151,10 +195,15 @@ def compare_blob(blob, tol, report=None, precision="fp32"):
     for k, v in extras.items():
         cmp(k, v, blob[k])
     cmp("grad_feat", gfeat, blob["grad_feat"])
+    noisy = noise_only_grads(blob)
     for k, g in blob["grads"].items():
         if k.startswith("image_encoder.cnn"):
             continue
         mine = grads.get(k)
+        if k in noisy and g is not None and mine is not None:
+            d = float((mine.detach().double().cpu() - g.double()).abs().max())
+            rows.append(("grad:" + k + " (noise-only)", d, float(g.abs().max()), d <= 2e-5))
+            continue
         if g is None:
             rows.append(("grad:" + k + " (none)", 0.0, 0.0, mine is None or float(mine.abs().max()) == 0.0))
         elif mine is None:

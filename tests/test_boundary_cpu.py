@@ -44,7 +44,8 @@ def test_decode_params_struct_matches_header():
     assert fields == [f[0] for f in DecodeParams._fields_]
 
 
-@pytest.mark.parametrize("name", ["rnn210_small", "rnn21_small", "demand_small"])
+@pytest.mark.parametrize("name", ["rnn210_small", "rnn21_small", "demand_small", "gtm_demand_eval", "gtm_ar_eval",
+                                  "v1_demand_train", "v2_demand_train", "v3_demand_train", "v4_demand_train"])
 def test_state_dict_keys_match_reference(name):
     from helpers import product_model
     blob = load_golden(name)
@@ -87,6 +88,42 @@ def test_same_seed_same_init_as_reference():
         tvm.resnet101 = orig_tv
         mods.resnet101_trunk = orig
     rs, ms = r.state_dict(), m.state_dict()
+    assert set(rs) == set(ms)
+    for k in rs:
+        assert torch.equal(rs[k], ms[k]), k
+
+
+@pytest.mark.parametrize("variant", ["gtm", "v1", "v2", "v3", "v4"])
+def test_gtm_family_same_seed_same_init_as_reference(variant):
+    """GTM family: same constructor arguments + same seed => bit-identical parameters and buffers."""
+    from oracle import refshim
+    if not refshim.reference_available():
+        pytest.skip("reference tree not mounted")
+    import visuelle2_multimodal_fusion_b200.synth as synth
+    from helpers import _restore_gtm_trunk, gtm_product_ctor
+    from oracle.make_golden_gtm import build_reference
+    cat_d, col_d, fab_d = synth.label_dicts()
+    import torch.nn as nn
+    import torchvision.models as tvm
+    refshim.load_reference_module("GTM_Visuelle2")           # installs the shims once
+    orig_tv = tvm.resnet101
+    fake = lambda *a, **k: nn.Sequential(nn.Identity(), nn.Identity(), nn.Identity())   # consumes no RNG
+    fake._v2f_patched = True
+    tvm.resnet101 = fake
+    try:
+        torch.manual_seed(5)
+        r = build_reference(variant, 8, 16, 12, 4, False, "image")
+    finally:
+        tvm.resnet101 = orig_tv
+    try:
+        ctor = gtm_product_ctor(variant)
+        torch.manual_seed(5)
+        m = ctor(8, 16, 12, 4, 1, 1, 1, cat_d, col_d, fab_d, synth.STORE_N, 52, 3, 0, use_encoder_mask=1,
+                 autoregressive=False)
+    finally:
+        _restore_gtm_trunk()
+    rs = {k: v for k, v in r.state_dict().items() if not k.startswith("image_encoder.cnn")}
+    ms = {k: v for k, v in m.state_dict().items() if not k.startswith("image_encoder.cnn")}
     assert set(rs) == set(ms)
     for k in rs:
         assert torch.equal(rs[k], ms[k]), k

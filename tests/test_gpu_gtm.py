@@ -1,0 +1,272 @@
+"""GPU parity of the GTM-family CUDA path (GTM_Visuelle2, Proposed_model v1-v4; through the C ABI)
+against the reference-generated goldens, against the oracle at the reference's default dims
+(E=32, H=64, 4 heads: train_GTM_visuelle2.py:165-166), and of each row operator against plain torch."""
+import pytest
+import torch
+
+from helpers import (_restore_gtm_trunk, assert_close, compare_blob, gtm_product_ctor, load_golden, noise_only_grads,
+                     oracle_run, product_run)
+
+pytestmark = pytest.mark.gpu
+GTM_CASES = ["gtm_demand_eval", "gtm_demand_train", "gtm_sofore1_train", "gtm_ar_eval", "v4_demand_train",
+             "v4_sofore10_eval", "v3_demand_train", "v1_demand_train", "v2_demand_train"]
+TOL_TC = 2e-2
+
+
+def _tol(name):
+    # same fp32 noise floor as the oracle-vs-reference test (tests/test_oracle_golden.py): two fp32 evaluations of
+    # this graph differ by ~1e-5 once BatchNorm batch statistics amplify summation-order differences
+    return 1e-4 if name == "gtm_sofore1_train" else 3e-5
+
+
+@pytest.mark.parametrize("name", GTM_CASES)
+def test_cuda_matches_reference_golden(name):
+    rows = compare_blob(load_golden(name), _tol(name))
+    bad = [r for r in rows if not r[3]]
+    assert not bad, "\n".join(f"{w}: rel={e:.3e} scale={s:.3e}" for w, e, s, _ in bad)
+
+
+@pytest.mark.parametrize("name", GTM_CASES)
+def test_cuda_tensorcore_path_matches_reference_golden(name):
+    rows = compare_blob(load_golden(name), TOL_TC, precision="bf16")
+    bad = [r for r in rows if not r[3]]
+    assert not bad, "\n".join(f"{w}: rel={e:.3e} scale={s:.3e}" for w, e, s, _ in bad)
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 3e-5), ("bf16", TOL_TC)])
+@pytest.mark.parametrize("variant,demand,T,ar", [("gtm", True, 12, False), ("v4", True, 12, False),
+                                                 ("gtm", False, 10, False), ("v4", False, 1, False),
+                                                 ("v1", True, 12, False), ("v2", True, 12, False),
+                                                 ("v3", True, 12, False), ("gtm", True, 12, True)])
+def test_cuda_matches_oracle_default_dims(variant, demand, T, ar, precision, tol):
+    import visuelle2_multimodal_fusion_b200.synth as synth
+    E, H, heads, B = 32, 64, 4, 16
+    cat_d, col_d, fab_d = synth.label_dicts()
+    try:
+        ctor = gtm_product_ctor(variant)
+        torch.manual_seed(7)
+        m = ctor(E, H, T, heads, 1, 1, 1, cat_d, col_d, fab_d, synth.STORE_N, 52, 3, 0, use_encoder_mask=1,
+                 autoregressive=ar, **(dict(query_modality="text") if variant == "v3" else {}))
+    finally:
+        _restore_gtm_trunk()
+    cfg = dict(E=E, H=H, T=T, B=B, heads=heads, mode="train_nodrop", seed=5, demand=demand, autoregressive=ar,
+               query_modality="text")
+    blob = dict(model="GTM:" + variant, cfg=cfg, tf_mask=None, grads={},
+                state={k: v.detach().clone() for k, v in m.state_dict().items()})
+    data, feat = synth.make_batch(B, out_len=T if not demand else 10, demand=demand, seed=5, feat_hw=10)
+    if demand:
+        ts, cat, col, fab, store, temporal, gt = data
+        y, item_sales = ts[:, :T].contiguous(), torch.zeros(B, 1, 2)
+    else:
+        item_sales, y, cat, col, fab, store, temporal, gt = data
+    blob["inputs"] = dict(item_sales=item_sales, y=y, cat=cat, col=col, fab=fab, store=store, temporal=temporal,
+                          gtrends=gt, feat=feat)
+    o_out, o_loss, _, P, o_feat = oracle_run(blob)
+    o_loss.backward()
+    import torch.nn as nn
+    m = m.cuda().train()
+    for mod in m.modules():
+        if isinstance(mod, nn.Dropout):
+            mod.p = 0.0
+        if isinstance(mod, nn.MultiheadAttention):
+            mod.dropout = 0.0
+    m.precision = precision
+    out, loss, _, grads, gfeat = product_run(m, blob)
+    assert_close(out, o_out, tol, "out", floor=1e-6)
+    assert_close(loss, o_loss, tol, "loss")
+    assert_close(gfeat, o_feat.grad, tol, "grad_feat", floor=1e-9 if precision == "fp32" else 1e-7)
+    noisy = noise_only_grads(blob)
+    for k, p in P.items():
+        if p.grad is None:
+            assert grads.get(k) is None or float(grads[k].abs().max()) == 0.0, k
+            continue
+        assert grads.get(k) is not None, k
+        floor = 2e-5 if k in noisy else (1e-6 if precision == "fp32" else 2e-2) * float(p.grad.abs().max() + 1e-4)
+        assert_close(grads[k], p.grad, tol, "grad:" + k, floor=floor)
+
+
+def test_train_mode_runs_with_dropout_and_updates_running_stats():
+    """train(): dropout masks on, BatchNorm running statistics move, unused parameters get no gradient."""
+    import visuelle2_multimodal_fusion_b200.synth as synth
+    cat_d, col_d, fab_d = synth.label_dicts()
+    try:
+        torch.manual_seed(1)
+        m = gtm_product_ctor("gtm")(32, 64, 12, 4, 1, 1, 1, cat_d, col_d, fab_d, synth.STORE_N, 52, 3, 0)
+    finally:
+        _restore_gtm_trunk()
+    m = m.cuda().train()
+    data, feat = synth.make_batch(8, out_len=10, demand=True, seed=2, feat_hw=10)
+    data = tuple(t.cuda() for t in data)
+    rm0 = m.fusion_network.feature_fusion[0].running_mean.clone()
+    loss = m.training_step((data, feat.cuda()), 0)
+    loss.backward()
+    assert torch.isfinite(loss)
+    assert not torch.equal(rm0, m.fusion_network.feature_fusion[0].running_mean)
+    assert int(m.fusion_network.feature_fusion[0].num_batches_tracked) == 1
+    assert m.decoder_linear.module.weight.grad is None          # constructed, never used (GTM_Visuelle2.py:199)
+    assert m.gtrend_encoder.encoder.layers[0].linear1.weight.grad is not None
+    m.eval()
+    with torch.no_grad():
+        y, f = m.validation_step((data, feat.cuda()), 0)
+    assert f.shape == y.shape
+
+
+# --------------------------------------------------------------------------- row operators vs torch
+def _rel(a, b):
+    return float((a.double().cpu() - b.double().cpu()).abs().max() / max(float(b.abs().max()), 1e-30))
+
+
+@pytest.mark.parametrize("M,D", [(7, 16), (6656, 64), (33, 100), (5, 512), (3, 1000)])
+@pytest.mark.parametrize("with_a,with_m", [(False, False), (True, False), (True, True)])
+def test_add_layer_norm(M, D, with_a, with_m):
+    from visuelle2_multimodal_fusion_b200 import functional_gtm as Fg
+    g = torch.Generator().manual_seed(M + D)
+    x = torch.randn(M, D, generator=g).cuda().requires_grad_(True)
+    a = torch.randn(M, D, generator=g).cuda().requires_grad_(True) if with_a else None
+    m = (torch.rand(M, D, generator=g) > 0.2).float().div(0.8).cuda() if with_m else None
+    w = torch.randn(D, generator=g).cuda().requires_grad_(True)
+    b = torch.randn(D, generator=g).cuda().requires_grad_(True)
+    dy = torch.randn(M, D, generator=g).cuda()
+    y = Fg.add_layer_norm(x, a, m, w, b, 1e-5)
+    y.backward(dy)
+    xd, wd, bd = (t.detach().double().requires_grad_(True) for t in (x, w, b))
+    ad = a.detach().double().requires_grad_(True) if with_a else None
+    z = xd + (ad * (m.double() if with_m else 1.0) if with_a else 0.0)
+    ref = torch.nn.functional.layer_norm(z, (D,), wd, bd, 1e-5)
+    ref.backward(dy.double())
+    assert _rel(y, ref) < 1e-5
+    assert _rel(x.grad, xd.grad) < 1e-5 and _rel(w.grad, wd.grad) < 1e-5 and _rel(b.grad, bd.grad) < 1e-5
+    if with_a:
+        assert _rel(a.grad, ad.grad) < 1e-5
+
+
+@pytest.mark.parametrize("B,D", [(4, 48), (128, 192), (1280, 192), (30, 33)])
+@pytest.mark.parametrize("training", [True, False])
+def test_batch_norm1d(B, D, training):
+    import torch.nn as nn
+    from visuelle2_multimodal_fusion_b200 import functional_gtm as Fg
+    torch.manual_seed(B + D)
+    bn = nn.BatchNorm1d(D).cuda()
+    ref = nn.BatchNorm1d(D).cuda().double()
+    with torch.no_grad():
+        for t in (bn.weight, bn.bias):
+            t.normal_()
+        bn.running_mean.uniform_(-0.2, 0.2)
+        bn.running_var.uniform_(0.5, 1.5)
+        ref.load_state_dict({k: v.double() if v.is_floating_point() else v for k, v in bn.state_dict().items()})
+    bn.train(training)
+    ref.train(training)
+    x = torch.randn(B, D, device="cuda").requires_grad_(True)
+    dy = torch.randn(B, D, device="cuda")
+    y = Fg.batch_norm1d(x, bn, training)
+    y.backward(dy)
+    xd = x.detach().double().requires_grad_(True)
+    yr = ref(xd)
+    yr.backward(dy.double())
+    assert _rel(y, yr) < 1e-5 and _rel(x.grad, xd.grad) < 2e-5
+    assert _rel(bn.weight.grad, ref.weight.grad) < 1e-5 and _rel(bn.bias.grad, ref.bias.grad) < 1e-5
+    assert _rel(bn.running_mean, ref.running_mean) < 1e-5 and _rel(bn.running_var, ref.running_var) < 1e-5
+    assert int(bn.num_batches_tracked) == int(ref.num_batches_tracked)
+
+
+@pytest.mark.parametrize("residual", [False, True])
+def test_gate(residual):
+    from visuelle2_multimodal_fusion_b200 import functional_gtm as Fg
+    x = torch.randn(37, 50, device="cuda", requires_grad=True)
+    g = torch.randn(37, 50, device="cuda", requires_grad=True)
+    d = torch.randn(37, 50, device="cuda")
+    out = Fg.gate(x, g, residual)
+    out.backward(d)
+    xd, gd = x.detach().double().requires_grad_(True), g.detach().double().requires_grad_(True)
+    ref = xd * torch.sigmoid(gd) + (xd if residual else 0.0)
+    ref.backward(d.double())
+    assert _rel(out, ref) < 1e-6 and _rel(x.grad, xd.grad) < 1e-6 and _rel(g.grad, gd.grad) < 1e-6
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("channels_last", [False, True])
+def test_mean_pool(dtype, channels_last):
+    from visuelle2_multimodal_fusion_b200 import functional_gtm as Fg
+    feat = torch.randn(6, 2048, 10, 10, device="cuda").to(dtype)
+    if channels_last:
+        feat = feat.contiguous(memory_format=torch.channels_last)
+    feat.requires_grad_(True)
+    out = Fg.mean_pool(feat)
+    d = torch.randn(6, 2048, device="cuda")
+    out.backward(d)
+    ref = feat.detach().double().mean((2, 3))
+    assert out.dtype == torch.float32 and _rel(out, ref) < 1e-6
+    gref = (d.double() / 100)[:, :, None, None].expand(6, 2048, 10, 10)
+    assert feat.grad.dtype == dtype and feat.grad.shape == feat.shape
+    assert _rel(feat.grad, gref) < (1e-6 if dtype == torch.float32 else 5e-3)
+
+
+def test_static_encoders_repeat_concat():
+    from visuelle2_multimodal_fusion_b200 import functional_gtm as Fg
+    g = torch.Generator().manual_seed(3)
+    B, E = 9, 24
+    tabs = [torch.randn(r, E, generator=g).cuda().requires_grad_(True) for r in (5, 4, 7, 11)]
+    idx = [torch.randint(0, r, (B,), generator=g).cuda() for r in (5, 4, 7, 11)]
+    out = Fg.gather4(tabs, *idx, 0.0, False)
+    ref = torch.stack([t[i] for t, i in zip(tabs, idx)], 1)
+    assert torch.equal(out, ref)
+    d = torch.randn(B, 4, E, generator=g).cuda()
+    out.backward(d)
+    for k in range(4):
+        gr = torch.zeros_like(tabs[k]).index_add_(0, idx[k], d[:, k])
+        assert _rel(tabs[k].grad, gr) < 1e-6
+    import torch.nn as nn
+    lins = [nn.Linear(1, E).cuda() for _ in range(4)]
+    t = torch.rand(B, 4, device="cuda")
+    f = Fg.feat4(t, lins)
+    fr = torch.stack([lins[k](t[:, k:k + 1]) for k in range(4)], 1)
+    assert _rel(f, fr) < 1e-6
+    d = torch.randn(B, 4, E, device="cuda")
+    gw = torch.autograd.grad(fr, [l.weight for l in lins] + [l.bias for l in lins], d, retain_graph=True)
+    f.backward(d)
+    for k in range(4):
+        assert _rel(lins[k].weight.grad, gw[k]) < 1e-5 and _rel(lins[k].bias.grad, gw[4 + k]) < 1e-5
+    x = torch.randn(B, 3, 5, device="cuda", requires_grad=True)
+    r = Fg.repeat_rows(x, 4)
+    assert torch.equal(r, x.repeat_interleave(4, 0))
+    d = torch.randn_like(r)
+    r.backward(d)
+    assert _rel(x.grad, d.view(B, 4, 3, 5).sum(1)) < 1e-6
+    a = torch.randn(B, 3, device="cuda", requires_grad=True)
+    b = torch.randn(B, 8, device="cuda", requires_grad=True)
+    c = Fg.concat_cols(a, b)
+    assert torch.equal(c, torch.cat([a, b], 1))
+    d = torch.randn_like(c)
+    c.backward(d)
+    assert torch.equal(a.grad, d[:, :3]) and torch.equal(b.grad, d[:, 3:])
+    s = torch.randn(B, 2, 6, device="cuda", requires_grad=True)
+    last = Fg.take_step(s, -1)
+    assert torch.equal(last, s[:, -1])
+    last.backward(torch.ones_like(last))
+    assert float(s.grad[:, 0].abs().max()) == 0.0 and float((s.grad[:, 1] - 1).abs().max()) == 0.0
+
+
+def test_cross_attention_pieces():
+    """cross_proj + sdpa_kv + out projection == nn.MultiheadAttention(query, memory, memory)."""
+    import torch.nn as nn
+    from visuelle2_multimodal_fusion_b200 import functional as Fv
+    from visuelle2_multimodal_fusion_b200 import functional_gtm as Fg
+    torch.manual_seed(0)
+    D, heads, N, Lq, Lk = 64, 4, 10, 3, 52
+    mha = nn.MultiheadAttention(D, heads).cuda()
+    x = torch.randn(N, Lq, D, device="cuda", requires_grad=True)
+    mem = torch.randn(N, Lk, D, device="cuda", requires_grad=True)
+    q, kv = Fg.cross_proj(x, mem, mha.in_proj_weight, mha.in_proj_bias)
+    o = Fv.linear(Fg.sdpa_kv(q, kv, heads), mha.out_proj.weight, mha.out_proj.bias)
+    d = torch.randn_like(o)
+    o.backward(d)
+    mine = [x.grad.clone(), mem.grad.clone(), mha.in_proj_weight.grad.clone(), mha.in_proj_bias.grad.clone()]
+    for t in (x, mem, mha.in_proj_weight, mha.in_proj_bias, mha.out_proj.weight, mha.out_proj.bias):
+        t.grad = None
+    torch.backends.cuda.matmul.allow_tf32 = False
+    ref, _ = mha(x.transpose(0, 1), mem.transpose(0, 1), mem.transpose(0, 1), need_weights=False)
+    ref = ref.transpose(0, 1)
+    ref.backward(d)
+    assert _rel(o, ref) < 2e-5
+    for a, b in zip(mine, [x.grad, mem.grad, mha.in_proj_weight.grad, mha.in_proj_bias.grad]):
+        assert _rel(a, b) < 5e-5

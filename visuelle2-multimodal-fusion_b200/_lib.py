@@ -61,6 +61,33 @@ def _declare(lib):
     lib.v2f_transpose.argtypes = [c_int, c_int, c_vp, c_ll, c_int, c_vp, c_ll, c_int, c_vp]
     lib.v2f_prof_enable.argtypes = [c_int]
     lib.v2f_prof_read.argtypes = [c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(c_ll)]
+    # ---- GTM-family row operators (csrc/gtm_ops.cu)
+    lib.v2f_add_ln_fwd.argtypes = [c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_float, c_vp, c_vp, c_vp, c_vp]
+    lib.v2f_add_ln_bwd_blocks.argtypes = [c_int]
+    lib.v2f_add_ln_bwd.argtypes = [c_int, c_int] + [c_vp] * 10
+    lib.v2f_bn1d_fwd.argtypes = [c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_float, c_float, c_vp, c_vp,
+                                 c_vp, c_vp]
+    lib.v2f_bn1d_bwd.argtypes = [c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_vp]
+    lib.v2f_gate_fwd.argtypes = [c_ll, c_vp, c_vp, c_int, c_vp, c_vp]
+    lib.v2f_gate_bwd.argtypes = [c_ll, c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_vp]
+    lib.v2f_add_f32.argtypes = [c_ll, c_vp, c_vp, c_vp, c_vp]
+    lib.v2f_relu_bwd.argtypes = [c_ll, c_vp, c_vp, c_vp, c_vp]
+    lib.v2f_relu_fwd.argtypes = [c_ll, c_vp, c_vp, c_vp]
+    lib.v2f_add_bcast.argtypes = [c_ll, c_ll, c_vp, c_vp, c_vp, c_vp]
+    lib.v2f_copy2d.argtypes = [c_int, c_int, c_vp, c_ll, c_vp, c_ll, c_vp]
+    lib.v2f_repeat_rows.argtypes = [c_int, c_int, c_ll, c_vp, c_vp, c_vp]
+    lib.v2f_fold_rows.argtypes = [c_int, c_int, c_ll, c_vp, c_vp, c_vp]
+    lib.v2f_gather4_fwd.argtypes = [c_int, c_int, ctypes.POINTER(c_vp), c_vp, c_vp, c_vp, c_vp]
+    lib.v2f_gather4_bwd.argtypes = [c_int, c_int, c_vp, c_vp, c_vp, ctypes.POINTER(c_int), ctypes.POINTER(c_vp), c_vp]
+    lib.v2f_feat4_fwd.argtypes = [c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp]
+    lib.v2f_feat4_bwd.argtypes = [c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp]
+    lib.v2f_meanpool_fwd.argtypes = [c_int, c_int, c_int, c_vp, c_int, c_int, c_vp, c_vp]
+    lib.v2f_meanpool_bwd.argtypes = [c_int, c_int, c_int, c_vp, c_int, c_int, c_vp, c_vp]
+    for name in ("v2f_add_ln_fwd", "v2f_add_ln_bwd_blocks", "v2f_add_ln_bwd", "v2f_bn1d_fwd", "v2f_bn1d_bwd",
+                 "v2f_gate_fwd", "v2f_gate_bwd", "v2f_add_f32", "v2f_relu_bwd", "v2f_relu_fwd", "v2f_add_bcast", "v2f_copy2d",
+                 "v2f_repeat_rows", "v2f_fold_rows", "v2f_gather4_fwd", "v2f_gather4_bwd", "v2f_feat4_fwd",
+                 "v2f_feat4_bwd", "v2f_meanpool_fwd", "v2f_meanpool_bwd"):
+        getattr(lib, name).restype = c_int
     for name in ("v2f_gemm_tc", "v2f_gemm_tc_batched", "v2f_cast_bf16", "v2f_transpose", "v2f_prof_enable", "v2f_prof_read", "v2f_gemm_f32", "v2f_colsum_f32", "v2f_mul_f32", "v2f_decode_fwd", "v2f_decode_bwd",
                  "v2f_gru_seq_fwd", "v2f_gru_seq_bwd", "v2f_sdpa_fwd", "v2f_sdpa_bwd", "v2f_embed_fwd",
                  "v2f_embed_bwd"):

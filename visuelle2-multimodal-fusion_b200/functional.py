@@ -147,7 +147,9 @@ class _Linear(torch.autograd.Function):
         x, W, y = ctx.saved_tensors
         dy = _c(dy)
         if ctx.act:
-            dy = MaskMul.apply(dy, (y > 0).float())
+            g = torch.empty_like(dy)
+            check(_lib.lib().v2f_relu_bwd(dy.numel(), ptr(dy), ptr(y), ptr(g), stream()), "v2f_relu_bwd")
+            dy = g
         K = x.shape[-1]
         M = x.numel() // K
         N = W.shape[0]
