@@ -254,6 +254,12 @@ def run_product(args):
 
     for i in range(max(args.warmup, 3)):
         step_resident(i)
+    # a generation-2 pass of Python's cyclic GC over the (large, import-heavy) heap stalls the launching
+    # thread for ~200 ms and shows up as an isolated 3-4x step: park the start-up heap in the permanent
+    # generation, as a long-running trainer would
+    import gc
+    gc.collect()
+    gc.freeze()
     clocks = _Clocks(local)
     clocks.start()
     l0 = _lib.launch_count()

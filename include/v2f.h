@@ -46,7 +46,9 @@ int v2f_gemm_f32(int ta, int tb, int M, int N, int K, const float* A, int lda, l
                  int batch, const float* bias, float beta, int act, void* stream);
 /* Tensor-core variant (tcgen05.mma, TMEM accumulator, TMA-staged 128B-swizzled operands):
  *   C[M,N] (fp32) = A[M,K] B[N,K]^T (+bias) (+beta C) (ReLU), both operands K-major.
- * kind 0: A,B bf16; kind 1: A,B fp32 consumed as tf32.  lda/ldb/ldc in elements; A,B 16-byte
+ * kind 0: A,B bf16; kind 1: A,B fp32 consumed as tf32 (the hardware truncates the low 13 mantissa
+ * bits; act bit 2 (value 4) rounds each staged tile to nearest tf32 instead, at the cost of one
+ * shared-memory pass).  act bit 0: ReLU; bit 1: C is bf16.  lda/ldb/ldc in elements; A,B 16-byte
  * aligned with 16-byte-multiple row pitch.  splits>1: split-K, partial sums added atomically
  * onto C (pre-zeroed by the caller; beta/act not applied).  Same reference call sites as
  * v2f_gemm_f32; this is the performance path (2e-2 contract).                                 */

@@ -40,7 +40,9 @@ def test_cuda_tensorcore_path_matches_reference_golden(name):
                                                  ("v3", True, 12, False), ("gtm", True, 12, True)])
 def test_cuda_matches_oracle_default_dims(variant, demand, T, ar, precision, tol):
     import visuelle2_multimodal_fusion_b200.synth as synth
-    E, H, heads, B = 32, 64, 4, 16
+    # the tensor-core leg runs at a batch closer to the reference's 128: with 16 rows a weight gradient is a sum of
+    # 16 nearly cancelling terms and the tf32 operand rounding (2^-11) is amplified past the 2e-2 contract
+    E, H, heads, B = 32, 64, 4, (16 if precision == "fp32" else 64)
     cat_d, col_d, fab_d = synth.label_dicts()
     try:
         ctor = gtm_product_ctor(variant)
@@ -81,7 +83,7 @@ def test_cuda_matches_oracle_default_dims(variant, demand, T, ar, precision, tol
             assert grads.get(k) is None or float(grads[k].abs().max()) == 0.0, k
             continue
         assert grads.get(k) is not None, k
-        floor = 2e-5 if k in noisy else (1e-6 if precision == "fp32" else 2e-2) * float(p.grad.abs().max() + 1e-4)
+        floor = 2e-5 if k in noisy else (1e-7 if precision == "fp32" else 1e-5)
         assert_close(grads[k], p.grad, tol, "grad:" + k, floor=floor)
 
 

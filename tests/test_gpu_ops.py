@@ -162,6 +162,12 @@ def test_gemm_tc(kind, M, N, K):
         Fv.gemm_tc(1, M, N, K, A, K, B, K, C, N, bias=bias, beta=1.0)
         trunc = lambda t: (t.view(torch.int32) & ~0x1FFF).view(torch.float32).double()
         Ar, Br = trunc(A), trunc(B)
+        # act bit 2: operands rounded to nearest tf32 (ties away from zero, cvt.rna) instead of truncated
+        C2 = C0.clone()
+        Fv.gemm_tc(1, M, N, K, A, K, B, K, C2, N, bias=bias, beta=1.0, act=4)
+        rna = lambda t: ((t.view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32).double()
+        torch.cuda.synchronize()
+        assert _rel(C2, rna(A) @ rna(B).t() + bias.double() + C0.double()) < 2e-5
     torch.cuda.synchronize()
     ref = Ar @ Br.t() + bias.double() + C0.double()
     assert _rel(C, ref) < 2e-5

@@ -110,7 +110,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * B_BYTES);
   uint64_t* empty = full + STAGES;
   uint64_t* tmem_full = empty + STAGES;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  uint64_t* conv = tmem_full + 1;    // tf32 only: stage rounded to tf32 in place, ready for the MMA
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(conv + STAGES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;
@@ -124,6 +125,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     for (int s = 0; s < STAGES; s++) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
+      mbar_init(&conv[s], TC_THREADS - 64);
     }
     mbar_init(tmem_full, 1);
     mbar_fence_init();
@@ -155,7 +157,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       const uint32_t idesc = umma_idesc<KIND>(BN);
       for (int i = 0; i < nkb; i++) {
         const int s = i % STAGES, r = i / STAGES;
-        mbar_wait(&full[s], r & 1);
+        mbar_wait((KIND == 1 && (a.act & 4)) ? &conv[s] : &full[s], r & 1);
         tc_fence_after();
         const uint64_t ad = umma_desc_sw128(smem_u32(sA + s * A_BYTES));
         const uint64_t bd = umma_desc_sw128(smem_u32(sB + s * B_BYTES));
@@ -172,6 +174,46 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     // ---- epilogue: warp w reads TMEM lanes 32*(w%4) .. +31  == output rows m0 + 32*(w%4) + lane
     const int q = warp & 3;
     const int row = m0 + q * 32 + lane;
+    if (KIND == 1 && (a.act & 4)) {
+      // kind::tf32 ignores the low 13 mantissa bits of each fp32 operand, i.e. truncates: a biased error
+      // (every product shrinks by ~7e-4) that survives the cancellations of a backward pass through
+      // BatchNorm / LayerNorm.  On request (act bit 2) the warps that are idle until the accumulator is
+      // complete round each landed stage to nearest tf32 in place (cvt.rna), publish it to the async
+      // proxy and hand it to the MMA thread.  Costs one shared-memory read+write of the stage, so it is
+      // used for the small GEMMs of the GTM family, not for the streaming projections.
+      constexpr int NT = TC_THREADS - 64;
+      constexpr int A_V = A_BYTES / 16 / NT;          // float4 per thread, A tile (8)
+      constexpr int B_V = (B_BYTES / 16 + NT - 1) / NT;
+      const int t = threadIdx.x - 64;
+      for (int i = 0; i < nkb; i++) {
+        const int s = i % STAGES, r = i / STAGES;
+        mbar_wait(&full[s], r & 1);
+        float4* pa = reinterpret_cast<float4*>(sA + s * A_BYTES);
+        float4* pb = reinterpret_cast<float4*>(sB + s * B_BYTES);
+        float4 v[A_V + B_V];
+#pragma unroll
+        for (int j = 0; j < A_V; j++) v[j] = pa[t + j * NT];
+#pragma unroll
+        for (int j = 0; j < B_V; j++)
+          if (t + j * NT < B_BYTES / 16) v[A_V + j] = pb[t + j * NT];
+#pragma unroll
+        for (int j = 0; j < A_V + B_V; j++) {
+          uint32_t x, y, z, w;
+          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(x) : "f"(v[j].x));
+          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(y) : "f"(v[j].y));
+          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(z) : "f"(v[j].z));
+          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(w) : "f"(v[j].w));
+          v[j] = make_float4(__uint_as_float(x), __uint_as_float(y), __uint_as_float(z), __uint_as_float(w));
+        }
+#pragma unroll
+        for (int j = 0; j < A_V; j++) pa[t + j * NT] = v[j];
+#pragma unroll
+        for (int j = 0; j < B_V; j++)
+          if (t + j * NT < B_BYTES / 16) pb[t + j * NT] = v[A_V + j];
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive(&conv[s]);
+      }
+    }
     if (nkb > 0) {
       mbar_wait(tmem_full, 0);
       tc_fence_after();
@@ -273,7 +315,7 @@ static int make_map(CUtensorMap* map, int kind, const void* ptr, long long rows,
 template <int KIND, int BN>
 static int launch_tc(const CUtensorMap& mA, const CUtensorMap& mB, const TcArgs& a, int gz, cudaStream_t s) {
   constexpr int STAGES = BN >= 128 ? 4 : 6;
-  constexpr size_t smem = 1024 + (size_t)STAGES * (TC_BM + BN) * 128 + (2 * STAGES + 1) * 8 + 16;
+  constexpr size_t smem = 1024 + (size_t)STAGES * (TC_BM + BN) * 128 + (3 * STAGES + 1) * 8 + 16;
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(gemm_tc_kernel<KIND, BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -305,7 +347,7 @@ extern "C" int v2f_gemm_tc_batched(int kind, int M, int N, int K, const void* A,
   V2F_REQUIRE((lda * elem) % 16 == 0 && (ldb * elem) % 16 == 0, V2F_ERR_ALIGN);
   V2F_REQUIRE(batch == 1 || ((sA * elem) % 16 == 0 && (sB * elem) % 16 == 0), V2F_ERR_ALIGN);
   if (splits < 1) splits = 1;
-  V2F_REQUIRE(splits == 1 || (beta == 0.f && act == 0), V2F_ERR_BAD_ARG);
+  V2F_REQUIRE(splits == 1 || (beta == 0.f && (act & 3) == 0), V2F_ERR_BAD_ARG);
   V2F_REQUIRE(!(act & 2) || beta == 0.f, V2F_ERR_BAD_ARG);
   V2F_REQUIRE((long long)batch * splits <= 65535, V2F_ERR_BAD_ARG);
   // tile width: keep >= ~1 wave of CTAs on 148 SMs for the small-M recurrent GEMMs

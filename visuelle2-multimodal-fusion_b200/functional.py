@@ -12,6 +12,7 @@ from ._lib import DecodeParams, check, ptr, stream
 
 
 _PRECISION = "fp32"
+_TF32_ROUND = False      # tensor-core mode: round tf32 operands to nearest instead of the hardware truncation
 
 
 def set_precision(mode):
@@ -28,15 +29,27 @@ def get_precision():
 
 
 class precision:
-    def __init__(self, mode):
+    """Context: precision mode, and (tensor-core mode) whether tf32 operands are rounded to nearest
+    (v2f_gemm_tc act bit 2): unbiased, for the small cancellation-prone GEMMs of the GTM family."""
+
+    def __init__(self, mode, round_tf32=False):
         self.mode = mode
+        self.round_tf32 = round_tf32
 
     def __enter__(self):
-        self.prev = _PRECISION
+        global _TF32_ROUND
+        self.prev = (_PRECISION, _TF32_ROUND)
         set_precision(self.mode)
+        _TF32_ROUND = self.round_tf32
 
     def __exit__(self, *a):
-        set_precision(self.prev)
+        global _TF32_ROUND
+        set_precision(self.prev[0])
+        _TF32_ROUND = self.prev[1]
+
+
+def _rnd():
+    return 4 if _TF32_ROUND else 0
 
 
 def _tc():
@@ -65,6 +78,7 @@ def colsum(X, M, N, ldx, out, x_off=0):
 
 
 KIND_BF16, KIND_TF32 = 0, 1
+TC_MIN_MACS = 1 << 24
 
 
 def gemm_tc(kind, M, N, K, A, lda, B, ldb, C, ldc, bias=None, beta=0.0, act=0, splits=1, a_off=0, b_off=0, c_off=0):
@@ -127,19 +141,20 @@ class _Linear(torch.autograd.Function):
         y = _f32(*x.shape[:-1], N, device=x.device)
         ptr(W)
         q = 8 if x.dtype == torch.bfloat16 else 4
-        tc = _tc() and K % q == 0 and K >= 16 and N % 4 == 0
+        # below ~16 M multiply-adds a product is launch-latency bound on either path: keep it exact
+        tc = _tc() and K % q == 0 and K >= 16 and N % 4 == 0 and M * N * K >= TC_MIN_MACS
         if x.dtype == torch.bfloat16 and not tc:
             x = x.float()
         if tc:
             kind = KIND_BF16 if x.dtype == torch.bfloat16 else KIND_TF32
             Wk = cast_bf16(W) if kind == KIND_BF16 else W
-            gemm_tc(kind, M, N, K, x, K, Wk, K, y, N, bias=b, act=act)
+            gemm_tc(kind, M, N, K, x, K, Wk, K, y, N, bias=b, act=act | _rnd())
         else:
             ptr(x)
             gemm(0, 1, M, N, K, x, K, W, K, y, N, bias=b, act=act)
         ctx.save_for_backward(x, W, y if act else None)
         ctx.has_bias = b is not None
-        ctx.act, ctx.tc = act, tc
+        ctx.act, ctx.tc, ctx.rnd = act, tc, _rnd()
         return y
 
     @staticmethod
@@ -159,7 +174,8 @@ class _Linear(torch.autograd.Function):
             if ctx.tc:
                 WT = transpose2d(W)                                   # [K,N]
                 dx = torch.empty(x.shape, device=x.device, dtype=x.dtype)
-                gemm_tc(KIND_TF32, M, K, N, dy2, N, WT, N, dx, K, act=2 if x.dtype == torch.bfloat16 else 0)
+                gemm_tc(KIND_TF32, M, K, N, dy2, N, WT, N, dx, K,
+                        act=(2 if x.dtype == torch.bfloat16 else 0) | ctx.rnd)
             else:
                 dx = torch.empty_like(x)
                 gemm(0, 0, M, K, N, dy, N, W, K, dx, K)
@@ -171,7 +187,7 @@ class _Linear(torch.autograd.Function):
                 xT, _ = transpose2d(x2, dt, pad=True)                 # [K,Mp]
                 splits = _splits_for(N, K, M, 64 if bf else 32)
                 dW = (torch.zeros if splits > 1 else torch.empty)(W.shape, device=W.device, dtype=torch.float32)
-                gemm_tc(KIND_BF16 if bf else KIND_TF32, N, K, M, dyT, pm, xT, pm, dW, K, splits=splits)
+                gemm_tc(KIND_BF16 if bf else KIND_TF32, N, K, M, dyT, pm, xT, pm, dW, K, act=ctx.rnd, splits=splits)
             else:
                 dW = torch.empty_like(W)
                 gemm(1, 0, N, K, M, dy, N, x, K, dW, K)
@@ -276,7 +292,7 @@ class _GruSeq(torch.autograd.Function):
         GH = _f32(N, 3 * H, device=dev)
         RZN = _f32(L, N, 3 * H, device=dev)
         GHN = _f32(L, N, H, device=dev)
-        prec = 1 if (_tc() and H % 4 == 0) else 0
+        prec = 1 if (_tc() and H % 4 == 0 and N * 3 * H * H >= TC_MIN_MACS) else 0
         check(_lib.lib().v2f_gru_seq_fwd(N, L, I, H, ptr(x), ptr(h0), ptr(w_ih), ptr(w_hh), ptr(b_ih),
                                          ptr(b_hh), ptr(out), ptr(GI), ptr(GH), ptr(RZN), ptr(GHN), prec,
                                          stream()), "v2f_gru_seq_fwd")

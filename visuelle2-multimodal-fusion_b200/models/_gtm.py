@@ -266,7 +266,7 @@ class GTMFamilyBase(LightningBase):
 
     # -- forward
     def forward(self, item_sales, category, color, fabric, store, temporal_features, gtrends, images):
-        with Fv.precision(self.precision):
+        with Fv.precision(self.precision, round_tf32=True):
             return self._forward(item_sales, category, color, fabric, store, temporal_features, gtrends, images)
 
     def _forward(self, item_sales, category, color, fabric, store, temporal_features, gtrends, images):
