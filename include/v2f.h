@@ -252,6 +252,28 @@ int v2f_feat4_bwd(int B, int E, const float* temporal, const float* dout, float*
 int v2f_meanpool_fwd(int B, int L, int C, const void* x, int layout, int kind, float* out, void* stream);
 int v2f_meanpool_bwd(int B, int L, int C, const float* dout, int layout, int kind, void* dx, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Fused BatchNorm2d (+ residual add) (+ ReLU) over bf16 channels_last activations viewed as
+ * [R = N*H*W, C] (C % 8 == 0): the normalisation / add / ReLU between the cuDNN convolutions of the
+ * torchvision ResNet-101 trunk (ImageEncoder, models/CrossAttnRNN210.py:58-72; Bottleneck =
+ * conv-bn-relu, conv-bn-relu, conv-bn, +identity, relu).  csrc/bn_act.cu.
+ *   y = act(BN(x) (+ res));  training != 0: batch statistics (biased variance), running statistics
+ *   updated with `momentum` (unbiased variance) unless run_mean is NULL; else running statistics.
+ * x, res, y, dy, dz, dx: bf16 [R,C].  save_mean/save_rstd [C]; scale_shift [2,C] scratch;
+ * part: v2f_bn2d_blocks(R,C)*2*C floats of scratch; coef [3,C] scratch.
+ * Backward: dz = dy*[y>0] (relu) is what a residual branch receives; pass dz != NULL to have it
+ * stored (bf16 [R,C]).  dx = gamma*rstd*(dz - mean(dz) - xhat*mean(dz*xhat)) (training) or
+ * gamma*rstd*dz (eval); dgamma = sum dz*xhat, dbeta = sum dz.                                   */
+int v2f_bn2d_blocks(long long R, int C);
+int v2f_bn2d_act_fwd(long long R, int C, const void* x, const void* res, const float* gamma,
+                     const float* beta, float* run_mean, float* run_var, int training, float momentum,
+                     float eps, int relu, void* y, float* save_mean, float* save_rstd,
+                     float* scale_shift, float* part, void* stream);
+int v2f_bn2d_act_bwd(long long R, int C, const void* dy, const void* x, const void* y,
+                     const float* gamma, const float* save_mean, const float* save_rstd, int training,
+                     int relu, void* dz, void* dx, float* dgamma, float* dbeta, float* coef, float* part,
+                     void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,106 @@
+"""GPU parity of the fused BatchNorm2d(+add)(+ReLU) sweeps (csrc/bn_act.cu) and of the fused trunk walk
+against torch's own BatchNorm2d / torchvision forward on the same bf16 channels_last inputs."""
+import pytest
+import torch
+import torch.nn as nn
+
+pytestmark = pytest.mark.gpu
+CL = torch.channels_last
+
+
+def _rel(a, b):
+    return float((a.double() - b.double()).abs().max() / max(float(b.double().abs().max()), 1e-30))
+
+
+@pytest.mark.parametrize("N,C,H,W", [(4, 64, 9, 7), (8, 256, 19, 19), (3, 2048, 10, 10), (2, 192, 5, 5), (16, 64, 75, 75)])
+@pytest.mark.parametrize("relu,res", [(True, False), (False, False), (True, True)])
+@pytest.mark.parametrize("training", [True, False])
+def test_bn_act_matches_torch(N, C, H, W, relu, res, training):
+    from visuelle2_multimodal_fusion_b200 import trunk
+    torch.manual_seed(N * C + H)
+    bn = nn.BatchNorm2d(C).cuda()
+    ref = nn.BatchNorm2d(C).cuda().double()
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5)
+        bn.bias.normal_()
+        bn.running_mean.uniform_(-0.3, 0.3)
+        bn.running_var.uniform_(0.5, 1.5)
+        ref.load_state_dict({k: (v.double() if v.is_floating_point() else v.clone()) for k, v in bn.state_dict().items()})
+    bn.train(training)
+    ref.train(training)
+    x = (torch.randn(N, C, H, W, device="cuda") * 1.7 + 0.4).bfloat16().contiguous(memory_format=CL).requires_grad_(True)
+    r = torch.randn(N, C, H, W, device="cuda").bfloat16().contiguous(memory_format=CL).requires_grad_(True) if res else None
+    dy = torch.randn(N, C, H, W, device="cuda").bfloat16().contiguous(memory_format=CL)
+    y = trunk.bn_act(x, bn, relu=relu, res=r)
+    assert y.dtype == torch.bfloat16 and y.is_contiguous(memory_format=CL)
+    y.backward(dy)
+    xd = x.detach().double().requires_grad_(True)
+    rd = r.detach().double().requires_grad_(True) if res else None
+    z = ref(xd) + (rd if res else 0.0)
+    yr = torch.relu(z) if relu else z
+    yr.backward(dy.double())
+    assert _rel(y, yr) < 8e-3                     # one bf16 ulp of the output
+    assert _rel(bn.running_mean, ref.running_mean) < 1e-5 and _rel(bn.running_var, ref.running_var) < 1e-5
+    assert int(bn.num_batches_tracked) == int(ref.num_batches_tracked)
+    assert _rel(x.grad, xd.grad) < 1.2e-2
+    assert _rel(bn.weight.grad, ref.weight.grad) < 5e-3 and _rel(bn.bias.grad, ref.bias.grad) < 5e-3
+    if res:
+        assert _rel(r.grad, rd.grad) < 8e-3
+
+
+def test_fused_trunk_matches_torchvision_forward_backward():
+    """Whole ResNet-101 trunk, same weights, three executions: fp32 torchvision (the truth), torchvision under
+    bf16 autocast, and the fused walk.  A 101-layer random-init network amplifies bf16 rounding, so the fused
+    walk is required to be as close to the fp32 truth as torch's own bf16 execution is (not to match it)."""
+    import copy
+    import warnings
+    from visuelle2_multimodal_fusion_b200 import trunk
+    from visuelle2_multimodal_fusion_b200.models._base import resnet101_trunk
+    torch.manual_seed(0)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        truth = resnet101_trunk().cuda().train()
+    cnn = copy.deepcopy(truth).to(memory_format=CL)
+    ref = copy.deepcopy(truth).to(memory_format=CL)
+    assert trunk.supported(cnn)
+    x = torch.randn(8, 3, 299, 299, device="cuda")
+    g = torch.randn(8, 2048, 10, 10, device="cuda")
+    ft = truth(x)
+    ft.backward(g)
+    f = trunk.forward(cnn, x)
+    f.backward(g.bfloat16())
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        fr = ref(x.contiguous(memory_format=CL))
+    fr.backward(g.bfloat16())
+    assert f.shape == fr.shape == (8, 2048, 10, 10) and f.dtype == torch.bfloat16
+
+    def cos(a, b):
+        a, b = a.double().flatten(), b.double().flatten()
+        return float(a @ b / (a.norm() * b.norm() + 1e-30))
+
+    c_fused, c_torch = cos(f, ft), cos(fr, ft)
+    print(f"feature map cos vs fp32: fused {c_fused:.5f}  torch-bf16 {c_torch:.5f}")
+    assert c_fused > 0.99 and c_fused >= c_torch - 5e-3
+    st, sd, sr = truth.state_dict(), cnn.state_dict(), ref.state_dict()
+    for k in sd:
+        if k.endswith("running_mean") or k.endswith("running_var"):
+            e_f, e_t = _rel(sd[k], st[k]), _rel(sr[k], st[k])
+            assert e_f <= 2.0 * e_t + 2e-2, (k, e_f, e_t)
+        if k.endswith("num_batches_tracked"):
+            assert int(sd[k]) == int(st[k]) == 1
+    pt, pr = dict(truth.named_parameters()), dict(ref.named_parameters())
+    checked, worst = 0, 1.0
+    for n, p in cnn.named_parameters():
+        assert (p.grad is None) == (pt[n].grad is None), n
+        if p.grad is None:
+            continue
+        cf, ct = cos(p.grad, pt[n].grad), cos(pr[n].grad, pt[n].grad)
+        worst = min(worst, cf - ct)
+        assert cf >= ct - 0.03 and cf > 0.9, (n, cf, ct)
+        checked += 1
+    print(f"{checked} gradient tensors, worst cos(fused) - cos(torch-bf16) = {worst:.4f}")
+    assert checked > 150
+    # frozen part (conv1 .. layer2) gets no gradient, as in the reference
+    assert all(p.grad is None for n, p in cnn.named_parameters() if n.split(".")[0] in ("0", "1", "4", "5"))

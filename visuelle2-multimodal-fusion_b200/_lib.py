@@ -83,6 +83,14 @@ def _declare(lib):
     lib.v2f_feat4_bwd.argtypes = [c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp]
     lib.v2f_meanpool_fwd.argtypes = [c_int, c_int, c_int, c_vp, c_int, c_int, c_vp, c_vp]
     lib.v2f_meanpool_bwd.argtypes = [c_int, c_int, c_int, c_vp, c_int, c_int, c_vp, c_vp]
+    # ---- fused BatchNorm2d (+add) (+ReLU) for the bf16 channels_last trunk (csrc/bn_act.cu)
+    lib.v2f_bn2d_blocks.argtypes = [c_ll, c_int]
+    lib.v2f_bn2d_act_fwd.argtypes = [c_ll, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_float, c_float, c_int,
+                                     c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]
+    lib.v2f_bn2d_act_bwd.argtypes = [c_ll, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_vp,
+                                     c_vp, c_vp, c_vp, c_vp]
+    for name in ("v2f_bn2d_blocks", "v2f_bn2d_act_fwd", "v2f_bn2d_act_bwd"):
+        getattr(lib, name).restype = c_int
     for name in ("v2f_add_ln_fwd", "v2f_add_ln_bwd_blocks", "v2f_add_ln_bwd", "v2f_bn1d_fwd", "v2f_bn1d_bwd",
                  "v2f_gate_fwd", "v2f_gate_bwd", "v2f_add_f32", "v2f_relu_bwd", "v2f_relu_fwd", "v2f_add_bcast", "v2f_copy2d",
                  "v2f_repeat_rows", "v2f_fold_rows", "v2f_gather4_fwd", "v2f_gather4_bwd", "v2f_feat4_fwd",

@@ -1,0 +1,468 @@
+// Fused BatchNorm2d (+ residual add) (+ ReLU) over bf16 channels_last activations, forward and
+// backward.  sm_100a.
+//
+// Reference arithmetic: the torchvision ResNet-101 trunk of ImageEncoder
+// (/root/reference/models/CrossAttnRNN210.py:58-72; layer3/layer4 trainable :63-65, the whole trunk
+// in train() mode so every BatchNorm2d normalises with batch statistics and updates its running
+// statistics): torchvision Bottleneck.forward = conv1-bn1-relu, conv2-bn2-relu, conv3-bn3,
+// (+ downsample conv-bn), add, relu.  The convolutions stay cuDNN; the normalisation, the residual
+// add and the ReLU between them are HBM-bound row sweeps over [R = N*H*W, C] and are done here in
+// two passes per direction instead of torch's 4-5 separate elementwise / reduction kernels:
+//   forward : stats (read x)  ->  finalize (per channel)  ->  apply (read x [,res], write y)
+//   backward: reduce (read dy, x [,y]; write dz if a residual consumes it)  ->  finalize  ->
+//             elemt (read dz|dy, x; write dx)
+// Activations are bf16 (16-byte = 8-channel vectors, C % 8 == 0), statistics / parameters fp32,
+// partial sums per block are merged in double by the finalize kernels (no atomics, deterministic).
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace v2f {
+
+constexpr int BN_THREADS = 256;
+
+struct __align__(16) bf16x8 { __nv_bfloat162 a, b, c, d; };
+
+__device__ __forceinline__ void unpack8(const uint4& u, float* f) {
+  const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const float2 t = __bfloat1622float2(p[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  uint4 u;
+  __nv_bfloat162* p = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; i++) p[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return u;
+}
+__device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+
+// Thread geometry shared by all sweeps: CV = C/8 vectors per row.  A block is viewed as
+// [RB rows][CVB vector columns] with CVB = min(CV, 256); when CV > 256 a thread loops over columns
+// (not needed for ResNet, C <= 2048).  Rows are dealt to blocks in an interleaved, grid-strided way.
+struct Geo {
+  int CV, CVB, RB;
+};
+__host__ __device__ inline Geo make_geo(int C) {
+  Geo g;
+  g.CV = C / 8;
+  g.CVB = g.CV < BN_THREADS ? g.CV : BN_THREADS;
+  g.RB = BN_THREADS / g.CVB;
+  return g;
+}
+
+// ---------------------------------------------------------------- forward: statistics
+// part[blk][0][c] = sum x, part[blk][1][c] = sum x^2 over the rows of block blk.
+__global__ void __launch_bounds__(BN_THREADS)
+bn_stats_kernel(long long R, int C, const uint4* __restrict__ x, float* __restrict__ part) {
+  extern __shared__ float sm[];   // [RB][2][CVB*8]
+  const Geo g = make_geo(C);
+  const int vcol = threadIdx.x % g.CVB, roff = threadIdx.x / g.CVB;
+  for (int v0 = 0; v0 < g.CV; v0 += g.CVB) {
+    const int v = v0 + vcol;
+    float s[8], q[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) s[i] = q[i] = 0.f;
+    if (roff < g.RB) {
+      const long long stride = (long long)gridDim.x * g.RB;
+      long long r = (long long)blockIdx.x * g.RB + roff;
+      // 4 independent 16-byte loads in flight per thread
+      for (; r + 3 * stride < R; r += 4 * stride) {
+        uint4 u[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) u[k] = ldg_stream(x + (r + k * stride) * g.CV + v);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          float f[8];
+          unpack8(u[k], f);
+#pragma unroll
+          for (int i = 0; i < 8; i++) {
+            s[i] += f[i];
+            q[i] = fmaf(f[i], f[i], q[i]);
+          }
+        }
+      }
+      for (; r < R; r += stride) {
+        float f[8];
+        unpack8(ldg_stream(x + r * g.CV + v), f);
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          s[i] += f[i];
+          q[i] = fmaf(f[i], f[i], q[i]);
+        }
+      }
+    }
+    const int W8 = g.CVB * 8;
+    if (roff < g.RB) {
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        sm[(roff * 2 + 0) * W8 + vcol * 8 + i] = s[i];
+        sm[(roff * 2 + 1) * W8 + vcol * 8 + i] = q[i];
+      }
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < 2 * W8; j += BN_THREADS) {
+      const int which = j / W8, cc = j - which * W8;
+      float t = 0.f;
+      for (int rr = 0; rr < g.RB; rr++) t += sm[(rr * 2 + which) * W8 + cc];
+      part[((long long)blockIdx.x * 2 + which) * C + v0 * 8 + cc] = t;
+    }
+    __syncthreads();
+  }
+}
+
+// Merge of the block partials of one channel group: block (32 channels, 8 slices of the partial
+// range), double accumulation, fixed order.  Returns the totals to the threads with threadIdx.y == 0.
+__device__ __forceinline__ void merge_partials(int C, int c, int nblk, const float* __restrict__ part,
+                                               double& S, double& Q) {
+  __shared__ double red[2][8][33];
+  double s = 0.0, q = 0.0;
+  if (c < C)
+    for (int b = threadIdx.y; b < nblk; b += 8) {
+      s += (double)part[((long long)b * 2) * C + c];
+      q += (double)part[((long long)b * 2 + 1) * C + c];
+    }
+  red[0][threadIdx.y][threadIdx.x] = s;
+  red[1][threadIdx.y][threadIdx.x] = q;
+  __syncthreads();
+  S = Q = 0.0;
+  if (threadIdx.y == 0)
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      S += red[0][i][threadIdx.x];
+      Q += red[1][i][threadIdx.x];
+    }
+}
+
+// Per channel: merge the block partials, produce scale/shift, the saved mean / rstd and the
+// running-statistics update (momentum, unbiased variance).  grid = ceil(C/32), block (32,8).
+__global__ void bn_fwd_finalize_kernel(long long R, int C, int nblk, const float* __restrict__ part,
+                                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                                       float* __restrict__ run_mean, float* __restrict__ run_var,
+                                       int training, float momentum, float eps, float* __restrict__ scale,
+                                       float* __restrict__ shift, float* __restrict__ save_mean,
+                                       float* __restrict__ save_rstd) {
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  double S = 0.0, Q = 0.0;
+  if (training) merge_partials(C, c, nblk, part, S, Q);
+  if (c >= C || threadIdx.y != 0) return;
+  float mean, var;
+  if (training) {
+    const double m = S / (double)R;
+    double vv = Q / (double)R - m * m;
+    if (vv < 0.0) vv = 0.0;
+    mean = (float)m;
+    var = (float)vv;
+    if (run_mean) {
+      const float unb = R > 1 ? (float)(vv * (double)R / (double)(R - 1)) : var;
+      run_mean[c] = (1.f - momentum) * run_mean[c] + momentum * mean;
+      run_var[c] = (1.f - momentum) * run_var[c] + momentum * unb;
+    }
+  } else {
+    mean = run_mean[c];
+    var = run_var[c];
+  }
+  const float r = 1.0f / sqrtf(var + eps);
+  const float sc = gamma[c] * r;
+  scale[c] = sc;
+  shift[c] = beta[c] - mean * sc;
+  save_mean[c] = mean;
+  save_rstd[c] = r;
+}
+
+// ---------------------------------------------------------------- forward: apply
+// y = act(x * scale + shift (+ res))
+template <bool RES, bool RELU>
+__global__ void __launch_bounds__(BN_THREADS)
+bn_apply_kernel(long long R, int C, const uint4* __restrict__ x, const uint4* __restrict__ res,
+                const float* __restrict__ scale, const float* __restrict__ shift, uint4* __restrict__ y) {
+  const Geo g = make_geo(C);
+  const int vcol = threadIdx.x % g.CVB, roff = threadIdx.x / g.CVB;
+  if (roff >= g.RB) return;
+  for (int v0 = 0; v0 < g.CV; v0 += g.CVB) {
+    const int v = v0 + vcol;
+    float sc[8], sh[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      sc[i] = scale[v * 8 + i];
+      sh[i] = shift[v * 8 + i];
+    }
+    const long long stride = (long long)gridDim.x * g.RB;
+    long long r = (long long)blockIdx.x * g.RB + roff;
+    for (; r + 3 * stride < R; r += 4 * stride) {
+      uint4 u[4], w[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        u[k] = ldg_stream(x + (r + k * stride) * g.CV + v);
+        if (RES) w[k] = ldg_stream(res + (r + k * stride) * g.CV + v);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        float f[8], h[8];
+        unpack8(u[k], f);
+        if (RES) unpack8(w[k], h);
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          float t = fmaf(f[i], sc[i], sh[i]);
+          if (RES) t += h[i];
+          f[i] = RELU ? fmaxf(t, 0.f) : t;
+        }
+        y[(r + k * stride) * g.CV + v] = pack8(f);
+      }
+    }
+    for (; r < R; r += stride) {
+      float f[8], h[8];
+      unpack8(ldg_stream(x + r * g.CV + v), f);
+      if (RES) unpack8(ldg_stream(res + r * g.CV + v), h);
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        float t = fmaf(f[i], sc[i], sh[i]);
+        if (RES) t += h[i];
+        f[i] = RELU ? fmaxf(t, 0.f) : t;
+      }
+      y[r * g.CV + v] = pack8(f);
+    }
+  }
+}
+
+// ---------------------------------------------------------------- backward: reduce
+// dz = dy * [y > 0] (RELU) ; part[blk][0][c] = sum dz, part[blk][1][c] = sum dz * xhat.
+// WRITE_DZ: dz is also stored (the residual branch receives it as its gradient).
+template <bool RELU, bool WRITE_DZ>
+__global__ void __launch_bounds__(BN_THREADS)
+bn_bwd_reduce_kernel(long long R, int C, const uint4* __restrict__ dy, const uint4* __restrict__ x,
+                     const uint4* __restrict__ y, const float* __restrict__ mean,
+                     const float* __restrict__ rstd, uint4* __restrict__ dz, float* __restrict__ part) {
+  extern __shared__ float sm[];
+  const Geo g = make_geo(C);
+  const int vcol = threadIdx.x % g.CVB, roff = threadIdx.x / g.CVB;
+  for (int v0 = 0; v0 < g.CV; v0 += g.CVB) {
+    const int v = v0 + vcol;
+    float s[8], q[8], mu[8], rs[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      s[i] = q[i] = 0.f;
+      mu[i] = mean[v * 8 + i];
+      rs[i] = rstd[v * 8 + i];
+    }
+    if (roff < g.RB) {
+      const long long stride = (long long)gridDim.x * g.RB;
+      long long r = (long long)blockIdx.x * g.RB + roff;
+      for (; r + stride < R; r += 2 * stride) {
+        uint4 ud[2], ux[2], uy[2];
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+          ud[k] = ldg_stream(dy + (r + k * stride) * g.CV + v);
+          ux[k] = ldg_stream(x + (r + k * stride) * g.CV + v);
+          if (RELU) uy[k] = ldg_stream(y + (r + k * stride) * g.CV + v);
+        }
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+          float d[8], xv[8], yv[8];
+          unpack8(ud[k], d);
+          unpack8(ux[k], xv);
+          if (RELU) unpack8(uy[k], yv);
+#pragma unroll
+          for (int i = 0; i < 8; i++) {
+            if (RELU && !(yv[i] > 0.f)) d[i] = 0.f;
+            s[i] += d[i];
+            q[i] = fmaf(d[i], (xv[i] - mu[i]) * rs[i], q[i]);
+          }
+          if (WRITE_DZ) dz[(r + k * stride) * g.CV + v] = pack8(d);
+        }
+      }
+      for (; r < R; r += stride) {
+        float d[8], xv[8], yv[8];
+        unpack8(ldg_stream(dy + r * g.CV + v), d);
+        unpack8(ldg_stream(x + r * g.CV + v), xv);
+        if (RELU) unpack8(ldg_stream(y + r * g.CV + v), yv);
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          if (RELU && !(yv[i] > 0.f)) d[i] = 0.f;
+          s[i] += d[i];
+          q[i] = fmaf(d[i], (xv[i] - mu[i]) * rs[i], q[i]);
+        }
+        if (WRITE_DZ) dz[r * g.CV + v] = pack8(d);
+      }
+    }
+    const int W8 = g.CVB * 8;
+    if (roff < g.RB) {
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        sm[(roff * 2 + 0) * W8 + vcol * 8 + i] = s[i];
+        sm[(roff * 2 + 1) * W8 + vcol * 8 + i] = q[i];
+      }
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < 2 * W8; j += BN_THREADS) {
+      const int which = j / W8, cc = j - which * W8;
+      float t = 0.f;
+      for (int rr = 0; rr < g.RB; rr++) t += sm[(rr * 2 + which) * W8 + cc];
+      part[((long long)blockIdx.x * 2 + which) * C + v0 * 8 + cc] = t;
+    }
+    __syncthreads();
+  }
+}
+
+// dgamma = sum dz*xhat, dbeta = sum dz; coefficients of the elementwise pass:
+//   dx = a * (dz - m1 - xhat * m2),  a = gamma*rstd, m1 = dbeta/R, m2 = dgamma/R   (training)
+//   dx = a * dz                                                                      (eval)
+__global__ void bn_bwd_finalize_kernel(long long R, int C, int nblk, const float* __restrict__ part,
+                                       const float* __restrict__ gamma, const float* __restrict__ rstd,
+                                       int training, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                       float* __restrict__ coef) {
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  double S, Q;
+  merge_partials(C, c, nblk, part, S, Q);
+  if (c >= C || threadIdx.y != 0) return;
+  dbeta[c] = (float)S;
+  dgamma[c] = (float)Q;
+  coef[c] = gamma[c] * rstd[c];
+  coef[C + c] = training ? (float)(S / (double)R) : 0.f;
+  coef[2 * C + c] = training ? (float)(Q / (double)R) : 0.f;
+}
+
+// dx = a * (dz - m1 - xhat*m2); dz either stored by the reduce pass (HAVE_DZ) or rebuilt from dy & y.
+template <bool RELU, bool HAVE_DZ>
+__global__ void __launch_bounds__(BN_THREADS)
+bn_bwd_elemt_kernel(long long R, int C, const uint4* __restrict__ dy, const uint4* __restrict__ x,
+                    const uint4* __restrict__ y, const float* __restrict__ mean,
+                    const float* __restrict__ rstd, const float* __restrict__ coef, uint4* __restrict__ dx) {
+  const Geo g = make_geo(C);
+  const int vcol = threadIdx.x % g.CVB, roff = threadIdx.x / g.CVB;
+  if (roff >= g.RB) return;
+  for (int v0 = 0; v0 < g.CV; v0 += g.CVB) {
+    const int v = v0 + vcol;
+    float mu[8], rs[8], a[8], m1[8], m2[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      const int c = v * 8 + i;
+      mu[i] = mean[c];
+      rs[i] = rstd[c];
+      a[i] = coef[c];
+      m1[i] = coef[C + c];
+      m2[i] = coef[2 * C + c];
+    }
+    const long long stride = (long long)gridDim.x * g.RB;
+    long long r = (long long)blockIdx.x * g.RB + roff;
+    for (; r + stride < R; r += 2 * stride) {
+      uint4 ud[2], ux[2], uy[2];
+#pragma unroll
+      for (int k = 0; k < 2; k++) {
+        ud[k] = ldg_stream(dy + (r + k * stride) * g.CV + v);
+        ux[k] = ldg_stream(x + (r + k * stride) * g.CV + v);
+        if (RELU && !HAVE_DZ) uy[k] = ldg_stream(y + (r + k * stride) * g.CV + v);
+      }
+#pragma unroll
+      for (int k = 0; k < 2; k++) {
+        float d[8], xv[8], yv[8];
+        unpack8(ud[k], d);
+        unpack8(ux[k], xv);
+        if (RELU && !HAVE_DZ) unpack8(uy[k], yv);
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          if (RELU && !HAVE_DZ && !(yv[i] > 0.f)) d[i] = 0.f;
+          d[i] = a[i] * (d[i] - m1[i] - (xv[i] - mu[i]) * rs[i] * m2[i]);
+        }
+        dx[(r + k * stride) * g.CV + v] = pack8(d);
+      }
+    }
+    for (; r < R; r += stride) {
+      float d[8], xv[8], yv[8];
+      unpack8(ldg_stream(dy + r * g.CV + v), d);
+      unpack8(ldg_stream(x + r * g.CV + v), xv);
+      if (RELU && !HAVE_DZ) unpack8(ldg_stream(y + r * g.CV + v), yv);
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        if (RELU && !HAVE_DZ && !(yv[i] > 0.f)) d[i] = 0.f;
+        d[i] = a[i] * (d[i] - m1[i] - (xv[i] - mu[i]) * rs[i] * m2[i]);
+      }
+      dx[r * g.CV + v] = pack8(d);
+    }
+  }
+}
+
+static inline int sweep_blocks(long long R, int C) {
+  const Geo g = make_geo(C);
+  long long need = (R + g.RB - 1) / g.RB;           // one block-iteration per RB rows
+  long long cap = 148 * 4;                          // 4 CTAs of 256 threads per SM, 64 B in flight per thread
+  return (int)(need < cap ? need : cap);
+}
+
+}  // namespace v2f
+
+using namespace v2f;
+
+extern "C" int v2f_bn2d_blocks(long long R, int C) {
+  if (R <= 0 || C <= 0 || (C & 7)) return 0;
+  return sweep_blocks(R, C);
+}
+
+extern "C" int v2f_bn2d_act_fwd(long long R, int C, const void* x, const void* res, const float* gamma,
+                                const float* beta, float* run_mean, float* run_var, int training,
+                                float momentum, float eps, int relu, void* y, float* save_mean,
+                                float* save_rstd, float* scale_shift, float* part, void* st) {
+  V2F_REQUIRE(R > 0 && C > 0 && (C & 7) == 0, V2F_ERR_BAD_ARG);
+  V2F_REQUIRE(x && gamma && beta && y && save_mean && save_rstd && scale_shift && part, V2F_ERR_BAD_ARG);
+  V2F_REQUIRE(training || (run_mean && run_var), V2F_ERR_BAD_ARG);
+  V2F_REQUIRE(aligned16(x) && aligned16(y) && (!res || aligned16(res)), V2F_ERR_ALIGN);
+  cudaStream_t s = (cudaStream_t)st;
+  const Geo g = make_geo(C);
+  const int nblk = sweep_blocks(R, C);
+  const size_t smem = sizeof(float) * (size_t)g.RB * 2 * g.CVB * 8;
+  if (training) {
+    bn_stats_kernel<<<nblk, BN_THREADS, smem, s>>>(R, C, (const uint4*)x, part);
+    V2F_CHECK_LAUNCH();
+  }
+  bn_fwd_finalize_kernel<<<(C + 31) / 32, dim3(32, 8), 0, s>>>(R, C, nblk, part, gamma, beta, run_mean, run_var, training,
+                                                         momentum, eps, scale_shift, scale_shift + C, save_mean,
+                                                         save_rstd);
+  V2F_CHECK_LAUNCH();
+  const uint4 *xp = (const uint4*)x, *rp = (const uint4*)res;
+  uint4* yp = (uint4*)y;
+  const float *sc = scale_shift, *sh = scale_shift + C;
+  if (res && relu) bn_apply_kernel<true, true><<<nblk, BN_THREADS, 0, s>>>(R, C, xp, rp, sc, sh, yp);
+  else if (res) bn_apply_kernel<true, false><<<nblk, BN_THREADS, 0, s>>>(R, C, xp, rp, sc, sh, yp);
+  else if (relu) bn_apply_kernel<false, true><<<nblk, BN_THREADS, 0, s>>>(R, C, xp, rp, sc, sh, yp);
+  else bn_apply_kernel<false, false><<<nblk, BN_THREADS, 0, s>>>(R, C, xp, rp, sc, sh, yp);
+  V2F_CHECK_LAUNCH();
+  return V2F_OK;
+}
+
+extern "C" int v2f_bn2d_act_bwd(long long R, int C, const void* dy, const void* x, const void* y,
+                                const float* gamma, const float* save_mean, const float* save_rstd,
+                                int training, int relu, void* dz, void* dx, float* dgamma, float* dbeta,
+                                float* coef, float* part, void* st) {
+  V2F_REQUIRE(R > 0 && C > 0 && (C & 7) == 0, V2F_ERR_BAD_ARG);
+  V2F_REQUIRE(dy && x && gamma && save_mean && save_rstd && dx && dgamma && dbeta && coef && part, V2F_ERR_BAD_ARG);
+  V2F_REQUIRE(!relu || y, V2F_ERR_BAD_ARG);
+  V2F_REQUIRE(aligned16(dy) && aligned16(x) && aligned16(dx) && (!y || aligned16(y)) && (!dz || aligned16(dz)),
+              V2F_ERR_ALIGN);
+  cudaStream_t s = (cudaStream_t)st;
+  const Geo g = make_geo(C);
+  const int nblk = sweep_blocks(R, C);
+  const size_t smem = sizeof(float) * (size_t)g.RB * 2 * g.CVB * 8;
+  const uint4 *dyp = (const uint4*)dy, *xp = (const uint4*)x, *yp = (const uint4*)y;
+  uint4 *dzp = (uint4*)dz, *dxp = (uint4*)dx;
+  if (relu && dz) bn_bwd_reduce_kernel<true, true><<<nblk, BN_THREADS, smem, s>>>(R, C, dyp, xp, yp, save_mean, save_rstd, dzp, part);
+  else if (relu) bn_bwd_reduce_kernel<true, false><<<nblk, BN_THREADS, smem, s>>>(R, C, dyp, xp, yp, save_mean, save_rstd, dzp, part);
+  else bn_bwd_reduce_kernel<false, false><<<nblk, BN_THREADS, smem, s>>>(R, C, dyp, xp, yp, save_mean, save_rstd, dzp, part);
+  V2F_CHECK_LAUNCH();
+  bn_bwd_finalize_kernel<<<(C + 31) / 32, dim3(32, 8), 0, s>>>(R, C, nblk, part, gamma, save_rstd, training, dgamma, dbeta, coef);
+  V2F_CHECK_LAUNCH();
+  if (relu && dz) bn_bwd_elemt_kernel<true, true><<<nblk, BN_THREADS, 0, s>>>(R, C, (const uint4*)dz, xp, yp, save_mean, save_rstd, coef, dxp);
+  else if (relu) bn_bwd_elemt_kernel<true, false><<<nblk, BN_THREADS, 0, s>>>(R, C, dyp, xp, yp, save_mean, save_rstd, coef, dxp);
+  else bn_bwd_elemt_kernel<false, false><<<nblk, BN_THREADS, 0, s>>>(R, C, dyp, xp, yp, save_mean, save_rstd, coef, dxp);
+  V2F_CHECK_LAUNCH();
+  return V2F_OK;
+}

@@ -18,6 +18,7 @@ import torch.nn.functional as F
 
 from .. import functional as Fv
 from .. import functional_gtm as Fg
+from .. import trunk
 from ._base import LightningBase, make_adafactor, resnet101_trunk
 
 
@@ -197,10 +198,13 @@ class ImageEncoder(nn.Module):
     def use_bf16_backbone(self, on=True):
         self.backbone_dtype = torch.bfloat16 if on else None
         self.cnn.to(memory_format=torch.channels_last if on else torch.contiguous_format)
+        self.fused_trunk = bool(on) and trunk.supported(self.cnn)    # BN/add/ReLU sweeps of csrc/bn_act.cu
         return self
 
     def trunk(self, x):
         if self.backbone_dtype is not None and x.dim() == 4 and x.shape[1] == 3:
+            if getattr(self, "fused_trunk", False):
+                return trunk.forward(self.cnn, x)
             with torch.autocast("cuda", dtype=self.backbone_dtype):
                 return self.cnn(x.contiguous(memory_format=torch.channels_last))
         return self.cnn(x)

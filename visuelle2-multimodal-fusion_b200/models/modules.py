@@ -9,6 +9,7 @@ import torch
 import torch.nn as nn
 
 from .. import functional as Fv
+from .. import trunk
 from ._base import resnet101_trunk
 
 
@@ -89,12 +90,16 @@ class ImageEncoder(nn.Module):
         """bf16 autocast + channels_last for the (unreplaced) torchvision/cuDNN trunk."""
         self.backbone_dtype = torch.bfloat16 if on else None
         self.cnn.to(memory_format=torch.channels_last if on else torch.contiguous_format)
+        self.fused_trunk = bool(on) and trunk.supported(self.cnn)    # BN/add/ReLU sweeps of csrc/bn_act.cu
         return self
 
     def forward(self, x):
         if self.backbone_dtype is not None and x.dim() == 4 and x.shape[1] == 3:
-            with torch.autocast("cuda", dtype=self.backbone_dtype):
-                feat = self.cnn(x.contiguous(memory_format=torch.channels_last))
+            if getattr(self, "fused_trunk", False):
+                feat = trunk.forward(self.cnn, x)
+            else:
+                with torch.autocast("cuda", dtype=self.backbone_dtype):
+                    feat = self.cnn(x.contiguous(memory_format=torch.channels_last))
         else:
             feat = self.cnn(x)
         B, C = feat.shape[0], feat.shape[1]

@@ -1,0 +1,131 @@
+"""bf16 channels_last execution of the torchvision ResNet-101 trunk with the BatchNorm / residual add /
+ReLU between the (cuDNN) convolutions fused into the sweeps of csrc/bn_act.cu.
+
+The trunk's modules, parameters, buffers and state_dict keys are untouched (``image_encoder.cnn.*`` of
+/root/reference/models/CrossAttnRNN210.py:58-72); only the order of evaluation of torchvision's
+``Bottleneck.forward`` is restated here so that ``bn -> relu`` and ``bn -> (+identity) -> relu`` each
+become one statistics pass + one apply pass (and two passes backward) over the activation instead of
+torch's separate batch_norm / add / relu kernels, which were 60 % of the end-to-end step.
+"""
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._lib import check, ptr, stream
+
+_CL = torch.channels_last
+
+
+def _f32(*shape, device):
+    return torch.empty(*shape, device=device, dtype=torch.float32)
+
+
+class _BnAct(torch.autograd.Function):
+    """y = act(BatchNorm2d(x) (+ res)) on bf16 channels_last tensors; ``bn`` is the nn.BatchNorm2d whose
+    parameters / running statistics are used (and updated in train mode)."""
+
+    @staticmethod
+    def forward(ctx, x, res, gamma, beta, bn, relu):
+        if x.dtype != torch.bfloat16 or not x.is_cuda:
+            raise RuntimeError("fused trunk expects bf16 CUDA activations (no CPU / fp32 fallback here)")
+        if not x.is_contiguous(memory_format=_CL):
+            x = x.contiguous(memory_format=_CL)
+        if res is not None and not res.is_contiguous(memory_format=_CL):
+            res = res.contiguous(memory_format=_CL)
+        N, C, H, W = x.shape
+        R = N * H * W
+        dev = x.device
+        use_batch = bn.training or bn.running_mean is None
+        y = torch.empty_like(x)
+        mean, rstd = _f32(C, device=dev), _f32(C, device=dev)
+        ss = _f32(2, C, device=dev)
+        nblk = _lib.lib().v2f_bn2d_blocks(R, C)
+        part = _f32(max(nblk, 1) * 2 * C, device=dev)
+        mom = bn.momentum
+        if use_batch and bn.running_mean is not None and bn.num_batches_tracked is not None:
+            bn.num_batches_tracked.add_(1)
+            if mom is None:
+                mom = 1.0 / float(bn.num_batches_tracked)
+        check(_lib.lib().v2f_bn2d_act_fwd(R, C, x.data_ptr(), res.data_ptr() if res is not None else None,
+                                          ptr(gamma), ptr(beta),
+                                          ptr(bn.running_mean, allow_none=True), ptr(bn.running_var, allow_none=True),
+                                          1 if use_batch else 0, float(mom if mom is not None else 0.0), float(bn.eps),
+                                          1 if relu else 0, y.data_ptr(), ptr(mean), ptr(rstd), ptr(ss), ptr(part),
+                                          stream()), "v2f_bn2d_act_fwd")
+        ctx.save_for_backward(x, y if relu else None, gamma, mean, rstd)
+        ctx.cfg = (R, C, use_batch, relu, res is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, y, gamma, mean, rstd = ctx.saved_tensors
+        R, C, use_batch, relu, has_res = ctx.cfg
+        if dy.dtype != torch.bfloat16:
+            dy = dy.to(torch.bfloat16)
+        if not dy.is_contiguous(memory_format=_CL):
+            dy = dy.contiguous(memory_format=_CL)
+        dev = dy.device
+        need_dz = has_res and relu and ctx.needs_input_grad[1]
+        dz = torch.empty_like(x) if need_dz else None
+        dx = torch.empty_like(x)
+        dgamma, dbeta = _f32(C, device=dev), _f32(C, device=dev)
+        coef = _f32(3, C, device=dev)
+        nblk = _lib.lib().v2f_bn2d_blocks(R, C)
+        part = _f32(nblk * 2 * C, device=dev)
+        check(_lib.lib().v2f_bn2d_act_bwd(R, C, dy.data_ptr(), x.data_ptr(), y.data_ptr() if relu else None,
+                                          ptr(gamma), ptr(mean), ptr(rstd), 1 if use_batch else 0, 1 if relu else 0,
+                                          dz.data_ptr() if need_dz else None, dx.data_ptr(), ptr(dgamma), ptr(dbeta),
+                                          ptr(coef), ptr(part), stream()), "v2f_bn2d_act_bwd")
+        dres = None
+        if has_res and ctx.needs_input_grad[1]:
+            dres = dz if relu else dy
+        return (dx if ctx.needs_input_grad[0] else None, dres,
+                dgamma if ctx.needs_input_grad[2] else None, dbeta if ctx.needs_input_grad[3] else None, None, None)
+
+
+def bn_act(x, bn, relu=True, res=None):
+    return _BnAct.apply(x, res, bn.weight, bn.bias, bn, relu)
+
+
+def _bottleneck(blk, x):
+    """torchvision.models.resnet.Bottleneck.forward with the fused normalisation sweeps."""
+    out = bn_act(blk.conv1(x), blk.bn1, relu=True)
+    out = bn_act(blk.conv2(out), blk.bn2, relu=True)
+    identity = x
+    if blk.downsample is not None:
+        identity = bn_act(blk.downsample[0](x), blk.downsample[1], relu=False)
+    return bn_act(blk.conv3(out), blk.bn3, relu=True, res=identity)
+
+
+def supported(cnn):
+    """True when ``cnn`` is the torchvision ResNet trunk this module knows how to walk."""
+    try:
+        from torchvision.models.resnet import Bottleneck
+    except Exception:
+        return False
+    mods = list(cnn.children())
+    if len(mods) < 5 or not isinstance(mods[0], nn.Conv2d) or not isinstance(mods[1], nn.BatchNorm2d):
+        return False
+    if not isinstance(mods[2], nn.ReLU) or not isinstance(mods[3], nn.MaxPool2d):
+        return False
+    for layer in mods[4:]:
+        if not isinstance(layer, nn.Sequential) or not all(isinstance(b, Bottleneck) for b in layer):
+            return False
+        for b in layer:
+            if b.downsample is not None and not (len(b.downsample) == 2 and isinstance(b.downsample[0], nn.Conv2d)
+                                                 and isinstance(b.downsample[1], nn.BatchNorm2d)):
+                return False
+    return True
+
+
+def forward(cnn, images):
+    """images [B,3,H,W] fp32 (any memory format) -> feature map [B,2048,h,w] bf16 channels_last."""
+    mods = list(cnn.children())
+    x = images.contiguous(memory_format=_CL)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        x = bn_act(mods[0](x), mods[1], relu=True)
+        x = mods[3](x)
+        for layer in mods[4:]:
+            for blk in layer:
+                x = _bottleneck(blk, x)
+    return x
