@@ -48,13 +48,14 @@ def test_bn_act_matches_torch(N, C, H, W, relu, res, training):
         assert _rel(r.grad, rd.grad) < 8e-3
 
 
-def test_fused_trunk_matches_torchvision_forward_backward():
-    """Whole ResNet-101 trunk, same weights, three executions: fp32 torchvision (the truth), torchvision under
-    bf16 autocast, and the fused walk.  A 101-layer random-init network amplifies bf16 rounding, so the fused
-    walk is required to be as close to the fp32 truth as torch's own bf16 execution is (not to match it)."""
+def _cos(a, b):
+    a, b = a.detach().double().flatten(), b.detach().double().flatten()
+    return float(a @ b / (a.norm() * b.norm() + 1e-30))
+
+
+def _trunks():
     import copy
     import warnings
-    from visuelle2_multimodal_fusion_b200 import trunk
     from visuelle2_multimodal_fusion_b200.models._base import resnet101_trunk
     torch.manual_seed(0)
     torch.backends.cudnn.allow_tf32 = False
@@ -62,8 +63,50 @@ def test_fused_trunk_matches_torchvision_forward_backward():
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         truth = resnet101_trunk().cuda().train()
-    cnn = copy.deepcopy(truth).to(memory_format=CL)
-    ref = copy.deepcopy(truth).to(memory_format=CL)
+    return truth, copy.deepcopy(truth).to(memory_format=CL), copy.deepcopy(truth).to(memory_format=CL)
+
+
+def test_every_bottleneck_matches_torchvision_on_identical_inputs():
+    """Each of the 33 Bottleneck blocks, fed the SAME bf16 input: fused walk vs torchvision's forward under
+    autocast -- outputs within bf16 rounding, input / parameter gradients aligned."""
+    from visuelle2_multimodal_fusion_b200 import trunk
+    truth, cnn, ref = _trunks()
+    x = torch.randn(8, 3, 299, 299, device="cuda")
+    mt, mc, mr = list(truth.children()), list(cnn.children()), list(ref.children())
+    with torch.no_grad():
+        a = mt[3](mt[2](mt[1](mt[0](x))))
+    n = 0
+    for li in range(4, 8):
+        for bi in range(len(mt[li])):
+            xin = a.detach().bfloat16().contiguous(memory_format=CL)
+            x1, x2 = xin.clone().requires_grad_(True), xin.clone().requires_grad_(True)
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                y1 = trunk._bottleneck(mc[li][bi], x1)
+                y2 = mr[li][bi](x2)
+            g = torch.randn_like(y2)
+            y1.backward(g)
+            y2.backward(g)
+            assert _rel(y1, y2) < 3e-2 and _cos(y1, y2) > 0.9999, (li, bi, _rel(y1, y2), _cos(y1, y2))
+            assert _cos(x1.grad, x2.grad) > 0.999, (li, bi, _cos(x1.grad, x2.grad))
+            for (k, p), (_, q) in zip(mc[li][bi].named_parameters(), mr[li][bi].named_parameters()):
+                if q.grad is None:
+                    assert p.grad is None, k
+                    continue
+                assert _cos(p.grad, q.grad) > 0.995, (li, bi, k, _cos(p.grad, q.grad))
+                p.grad = q.grad = None
+            with torch.no_grad():
+                a = mt[li][bi](a)
+            n += 1
+    assert n == 33
+
+
+def test_fused_trunk_matches_torchvision_forward_backward():
+    """Whole ResNet-101 trunk, same weights, three executions: fp32 torchvision (the truth), torchvision under
+    bf16 autocast, and the fused walk.  A 101-layer random-init network in train mode amplifies bf16 rounding
+    chaotically (torch's own bf16 run ends at cos 0.63 against fp32), so the whole-trunk criterion is relative:
+    the fused walk must be at least as close to the fp32 truth as torch's bf16 execution is."""
+    from visuelle2_multimodal_fusion_b200 import trunk
+    truth, cnn, ref = _trunks()
     assert trunk.supported(cnn)
     x = torch.randn(8, 3, 299, 299, device="cuda")
     g = torch.randn(8, 2048, 10, 10, device="cuda")
@@ -75,32 +118,21 @@ def test_fused_trunk_matches_torchvision_forward_backward():
         fr = ref(x.contiguous(memory_format=CL))
     fr.backward(g.bfloat16())
     assert f.shape == fr.shape == (8, 2048, 10, 10) and f.dtype == torch.bfloat16
-
-    def cos(a, b):
-        a, b = a.double().flatten(), b.double().flatten()
-        return float(a @ b / (a.norm() * b.norm() + 1e-30))
-
-    c_fused, c_torch = cos(f, ft), cos(fr, ft)
+    c_fused, c_torch = _cos(f, ft), _cos(fr, ft)
     print(f"feature map cos vs fp32: fused {c_fused:.5f}  torch-bf16 {c_torch:.5f}")
-    assert c_fused > 0.99 and c_fused >= c_torch - 5e-3
+    assert c_fused >= c_torch - 5e-3
     st, sd, sr = truth.state_dict(), cnn.state_dict(), ref.state_dict()
     for k in sd:
         if k.endswith("running_mean") or k.endswith("running_var"):
             e_f, e_t = _rel(sd[k], st[k]), _rel(sr[k], st[k])
-            assert e_f <= 2.0 * e_t + 2e-2, (k, e_f, e_t)
+            assert e_f <= 1.5 * e_t + 2e-2, (k, e_f, e_t)
         if k.endswith("num_batches_tracked"):
             assert int(sd[k]) == int(st[k]) == 1
-    pt, pr = dict(truth.named_parameters()), dict(ref.named_parameters())
-    checked, worst = 0, 1.0
+    # gradients of the whole chaotic stack are decorrelated from the fp32 truth for BOTH bf16 executions
+    # (cos ~ 0.03), so they are checked block by block above; here only which parameters receive one
+    pt = dict(truth.named_parameters())
     for n, p in cnn.named_parameters():
         assert (p.grad is None) == (pt[n].grad is None), n
-        if p.grad is None:
-            continue
-        cf, ct = cos(p.grad, pt[n].grad), cos(pr[n].grad, pt[n].grad)
-        worst = min(worst, cf - ct)
-        assert cf >= ct - 0.03 and cf > 0.9, (n, cf, ct)
-        checked += 1
-    print(f"{checked} gradient tensors, worst cos(fused) - cos(torch-bf16) = {worst:.4f}")
-    assert checked > 150
+        assert p.grad is None or bool(torch.isfinite(p.grad).all()), n
     # frozen part (conv1 .. layer2) gets no gradient, as in the reference
     assert all(p.grad is None for n, p in cnn.named_parameters() if n.split(".")[0] in ("0", "1", "4", "5"))
