@@ -273,6 +273,13 @@ int v2f_bn2d_act_bwd(long long R, int C, const void* dy, const void* x, const vo
                      const float* gamma, const float* save_mean, const float* save_rstd, int training,
                      int relu, void* dz, void* dx, float* dgamma, float* dbeta, float* coef, float* part,
                      void* stream);
+/* Stem of the trunk (conv1 -> bn1 -> relu -> maxpool 3x3 stride 2 pad 1, torchvision resnet.py):
+ * y [N,OH,OW,C] = maxpool(relu(BN(x))), x bf16 [N,H,W,C], OH=(H-1)/2+1, OW=(W-1)/2+1.  Forward only:
+ * the stem is frozen in the reference (models/CrossAttnRNN210.py:62-65).  Scratch as v2f_bn2d_act_fwd. */
+int v2f_bn2d_relu_maxpool_fwd(int N, int H, int W, int C, const void* x, const float* gamma,
+                              const float* beta, float* run_mean, float* run_var, int training,
+                              float momentum, float eps, void* y, float* save_mean, float* save_rstd,
+                              float* scale_shift, float* part, void* stream);
 
 #ifdef __cplusplus
 }

@@ -136,3 +136,31 @@ def test_fused_trunk_matches_torchvision_forward_backward():
         assert p.grad is None or bool(torch.isfinite(p.grad).all()), n
     # frozen part (conv1 .. layer2) gets no gradient, as in the reference
     assert all(p.grad is None for n, p in cnn.named_parameters() if n.split(".")[0] in ("0", "1", "4", "5"))
+
+
+@pytest.mark.parametrize("N,H,W", [(3, 150, 150), (2, 9, 7), (4, 16, 16)])
+@pytest.mark.parametrize("training", [True, False])
+def test_fused_stem_matches_torch(N, H, W, training):
+    """conv -> BN -> ReLU -> maxpool(3,2,1) in one sweep (frozen stem) vs torch on the same bf16 conv output."""
+    from visuelle2_multimodal_fusion_b200 import trunk
+    torch.manual_seed(H)
+    conv = nn.Conv2d(3, 64, 7, 2, 3, bias=False).cuda().to(memory_format=CL)
+    bn = nn.BatchNorm2d(64).cuda()
+    pool = nn.MaxPool2d(3, 2, 1)
+    for p in list(conv.parameters()) + list(bn.parameters()):
+        p.requires_grad = False
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5)
+        bn.bias.normal_()
+    bn.train(training)
+    import copy
+    ref = copy.deepcopy(bn).double()
+    x = torch.randn(N, 3, 2 * H, 2 * W, device="cuda").contiguous(memory_format=CL)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        y = trunk.stem(conv, bn, pool, x)
+        c = conv(x)
+    yr = pool(torch.relu(ref(c.double())))
+    assert y.shape == yr.shape and y.dtype == torch.bfloat16
+    assert _rel(y, yr) < 8e-3
+    assert _rel(bn.running_mean, ref.running_mean) < 1e-5 and _rel(bn.running_var, ref.running_var) < 1e-5
+    assert int(bn.num_batches_tracked) == int(ref.num_batches_tracked)

@@ -89,7 +89,9 @@ def _declare(lib):
                                      c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]
     lib.v2f_bn2d_act_bwd.argtypes = [c_ll, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_vp,
                                      c_vp, c_vp, c_vp, c_vp]
-    for name in ("v2f_bn2d_blocks", "v2f_bn2d_act_fwd", "v2f_bn2d_act_bwd"):
+    lib.v2f_bn2d_relu_maxpool_fwd.argtypes = [c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_float,
+                                              c_float, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]
+    for name in ("v2f_bn2d_blocks", "v2f_bn2d_act_fwd", "v2f_bn2d_act_bwd", "v2f_bn2d_relu_maxpool_fwd"):
         getattr(lib, name).restype = c_int
     for name in ("v2f_add_ln_fwd", "v2f_add_ln_bwd_blocks", "v2f_add_ln_bwd", "v2f_bn1d_fwd", "v2f_bn1d_bwd",
                  "v2f_gate_fwd", "v2f_gate_bwd", "v2f_add_f32", "v2f_relu_bwd", "v2f_relu_fwd", "v2f_add_bcast", "v2f_copy2d",

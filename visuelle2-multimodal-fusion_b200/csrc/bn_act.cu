@@ -121,31 +121,43 @@ bn_stats_kernel(long long R, int C, const uint4* __restrict__ x, float* __restri
   }
 }
 
-// Merge of the block partials of one channel group: block (32 channels, 8 slices of the partial
-// range), double accumulation, fixed order.  Returns the totals to the threads with threadIdx.y == 0.
+// Merge of the block partials of one channel group: block (32 channels, 32 slices of the partial
+// range), two independent double accumulators per thread so the loads pipeline, fixed order.
+// Returns the totals to the threads with threadIdx.y == 0.
+constexpr int FIN_Y = 32;
 __device__ __forceinline__ void merge_partials(int C, int c, int nblk, const float* __restrict__ part,
                                                double& S, double& Q) {
-  __shared__ double red[2][8][33];
-  double s = 0.0, q = 0.0;
-  if (c < C)
-    for (int b = threadIdx.y; b < nblk; b += 8) {
-      s += (double)part[((long long)b * 2) * C + c];
-      q += (double)part[((long long)b * 2 + 1) * C + c];
+  __shared__ double red[2][FIN_Y][33];
+  double s0 = 0.0, q0 = 0.0, s1 = 0.0, q1 = 0.0;
+  if (c < C) {
+    int b = threadIdx.y;
+    for (; b + FIN_Y < nblk; b += 2 * FIN_Y) {
+      const float a0 = part[((long long)b * 2) * C + c], a1 = part[((long long)b * 2 + 1) * C + c];
+      const float b0 = part[((long long)(b + FIN_Y) * 2) * C + c], b1 = part[((long long)(b + FIN_Y) * 2 + 1) * C + c];
+      s0 += (double)a0;
+      q0 += (double)a1;
+      s1 += (double)b0;
+      q1 += (double)b1;
     }
-  red[0][threadIdx.y][threadIdx.x] = s;
-  red[1][threadIdx.y][threadIdx.x] = q;
+    if (b < nblk) {
+      s0 += (double)part[((long long)b * 2) * C + c];
+      q0 += (double)part[((long long)b * 2 + 1) * C + c];
+    }
+  }
+  red[0][threadIdx.y][threadIdx.x] = s0 + s1;
+  red[1][threadIdx.y][threadIdx.x] = q0 + q1;
   __syncthreads();
   S = Q = 0.0;
   if (threadIdx.y == 0)
 #pragma unroll
-    for (int i = 0; i < 8; i++) {
+    for (int i = 0; i < FIN_Y; i++) {
       S += red[0][i][threadIdx.x];
       Q += red[1][i][threadIdx.x];
     }
 }
 
 // Per channel: merge the block partials, produce scale/shift, the saved mean / rstd and the
-// running-statistics update (momentum, unbiased variance).  grid = ceil(C/32), block (32,8).
+// running-statistics update (momentum, unbiased variance).  grid = ceil(C/32), block (32,32).
 __global__ void bn_fwd_finalize_kernel(long long R, int C, int nblk, const float* __restrict__ part,
                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                        float* __restrict__ run_mean, float* __restrict__ run_var,
@@ -392,6 +404,46 @@ bn_bwd_elemt_kernel(long long R, int C, const uint4* __restrict__ dy, const uint
   }
 }
 
+// ---------------------------------------------------------------- stem: BN + ReLU + 3x3/2 max-pool (forward only)
+// y[n,oh,ow,:] = max over the valid 3x3 window (stride 2, pad 1) of relu(x*scale+shift).  One thread per
+// (output pixel, 8 channels); the overlapping window reads are served by L1/L2, DRAM sees x once.
+__global__ void __launch_bounds__(BN_THREADS)
+bn_relu_maxpool_kernel(int N, int H, int W, int C, int OH, int OW, const uint4* __restrict__ x,
+                       const float* __restrict__ scale, const float* __restrict__ shift, uint4* __restrict__ y) {
+  const int CV = C / 8;
+  const long long total = (long long)N * OH * OW * CV;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int v = (int)(i % CV);
+  long long p = i / CV;
+  const int ow = (int)(p % OW);
+  p /= OW;
+  const int oh = (int)(p % OH);
+  const int n = (int)(p / OH);
+  float sc[8], sh[8], m[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    sc[k] = scale[v * 8 + k];
+    sh[k] = shift[v * 8 + k];
+    m[k] = 0.f;                       // relu output >= 0 and every window holds a valid pixel
+  }
+#pragma unroll
+  for (int dh = 0; dh < 3; dh++) {
+    const int ih = 2 * oh - 1 + dh;
+    if (ih < 0 || ih >= H) continue;
+#pragma unroll
+    for (int dw = 0; dw < 3; dw++) {
+      const int iw = 2 * ow - 1 + dw;
+      if (iw < 0 || iw >= W) continue;
+      float f[8];
+      unpack8(__ldg(x + (((long long)n * H + ih) * W + iw) * CV + v), f);
+#pragma unroll
+      for (int k = 0; k < 8; k++) m[k] = fmaxf(m[k], fmaf(f[k], sc[k], sh[k]));
+    }
+  }
+  y[i] = pack8(m);
+}
+
 static inline int sweep_blocks(long long R, int C) {
   const Geo g = make_geo(C);
   long long need = (R + g.RB - 1) / g.RB;           // one block-iteration per RB rows
@@ -424,7 +476,7 @@ extern "C" int v2f_bn2d_act_fwd(long long R, int C, const void* x, const void* r
     bn_stats_kernel<<<nblk, BN_THREADS, smem, s>>>(R, C, (const uint4*)x, part);
     V2F_CHECK_LAUNCH();
   }
-  bn_fwd_finalize_kernel<<<(C + 31) / 32, dim3(32, 8), 0, s>>>(R, C, nblk, part, gamma, beta, run_mean, run_var, training,
+  bn_fwd_finalize_kernel<<<(C + 31) / 32, dim3(32, FIN_Y), 0, s>>>(R, C, nblk, part, gamma, beta, run_mean, run_var, training,
                                                          momentum, eps, scale_shift, scale_shift + C, save_mean,
                                                          save_rstd);
   V2F_CHECK_LAUNCH();
@@ -458,11 +510,42 @@ extern "C" int v2f_bn2d_act_bwd(long long R, int C, const void* dy, const void* 
   else if (relu) bn_bwd_reduce_kernel<true, false><<<nblk, BN_THREADS, smem, s>>>(R, C, dyp, xp, yp, save_mean, save_rstd, dzp, part);
   else bn_bwd_reduce_kernel<false, false><<<nblk, BN_THREADS, smem, s>>>(R, C, dyp, xp, yp, save_mean, save_rstd, dzp, part);
   V2F_CHECK_LAUNCH();
-  bn_bwd_finalize_kernel<<<(C + 31) / 32, dim3(32, 8), 0, s>>>(R, C, nblk, part, gamma, save_rstd, training, dgamma, dbeta, coef);
+  bn_bwd_finalize_kernel<<<(C + 31) / 32, dim3(32, FIN_Y), 0, s>>>(R, C, nblk, part, gamma, save_rstd, training, dgamma, dbeta, coef);
   V2F_CHECK_LAUNCH();
   if (relu && dz) bn_bwd_elemt_kernel<true, true><<<nblk, BN_THREADS, 0, s>>>(R, C, (const uint4*)dz, xp, yp, save_mean, save_rstd, coef, dxp);
   else if (relu) bn_bwd_elemt_kernel<true, false><<<nblk, BN_THREADS, 0, s>>>(R, C, dyp, xp, yp, save_mean, save_rstd, coef, dxp);
   else bn_bwd_elemt_kernel<false, false><<<nblk, BN_THREADS, 0, s>>>(R, C, dyp, xp, yp, save_mean, save_rstd, coef, dxp);
+  V2F_CHECK_LAUNCH();
+  return V2F_OK;
+}
+
+// Stem of the trunk: y = maxpool3x3/2(relu(BN(x))), x bf16 [N,H,W,C], y bf16 [N,OH,OW,C] with
+// OH = (H-1)/2+1, OW = (W-1)/2+1.  Forward only (the stem is frozen in the reference).
+extern "C" int v2f_bn2d_relu_maxpool_fwd(int N, int H, int W, int C, const void* x, const float* gamma,
+                                         const float* beta, float* run_mean, float* run_var, int training,
+                                         float momentum, float eps, void* y, float* save_mean,
+                                         float* save_rstd, float* scale_shift, float* part, void* st) {
+  V2F_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && (C & 7) == 0, V2F_ERR_BAD_ARG);
+  V2F_REQUIRE(x && gamma && beta && y && save_mean && save_rstd && scale_shift && part, V2F_ERR_BAD_ARG);
+  V2F_REQUIRE(training || (run_mean && run_var), V2F_ERR_BAD_ARG);
+  V2F_REQUIRE(aligned16(x) && aligned16(y), V2F_ERR_ALIGN);
+  cudaStream_t s = (cudaStream_t)st;
+  const long long R = (long long)N * H * W;
+  const Geo g = make_geo(C);
+  const int nblk = sweep_blocks(R, C);
+  const size_t smem = sizeof(float) * (size_t)g.RB * 2 * g.CVB * 8;
+  if (training) {
+    bn_stats_kernel<<<nblk, BN_THREADS, smem, s>>>(R, C, (const uint4*)x, part);
+    V2F_CHECK_LAUNCH();
+  }
+  bn_fwd_finalize_kernel<<<(C + 31) / 32, dim3(32, FIN_Y), 0, s>>>(R, C, nblk, part, gamma, beta, run_mean, run_var,
+                                                                   training, momentum, eps, scale_shift,
+                                                                   scale_shift + C, save_mean, save_rstd);
+  V2F_CHECK_LAUNCH();
+  const int OH = (H - 1) / 2 + 1, OW = (W - 1) / 2 + 1;
+  const long long total = (long long)N * OH * OW * (C / 8);
+  bn_relu_maxpool_kernel<<<(unsigned)((total + BN_THREADS - 1) / BN_THREADS), BN_THREADS, 0, s>>>(
+      N, H, W, C, OH, OW, (const uint4*)x, scale_shift, scale_shift + C, (uint4*)y);
   V2F_CHECK_LAUNCH();
   return V2F_OK;
 }

@@ -20,6 +20,59 @@ def _f32(*shape, device):
     return torch.empty(*shape, device=device, dtype=torch.float32)
 
 
+_pending_counters = None     # inside forward(): num_batches_tracked buffers to bump with ONE multi-tensor add
+
+
+def _count_batch(bn, use_batch, mom):
+    """nn.BatchNorm bookkeeping: num_batches_tracked += 1 in train mode (deferred to one _foreach_add_ per trunk
+    forward); momentum=None means a cumulative moving average."""
+    if use_batch and bn.running_mean is not None and bn.num_batches_tracked is not None:
+        if mom is None or _pending_counters is None:
+            bn.num_batches_tracked.add_(1)
+            if mom is None:
+                mom = 1.0 / float(bn.num_batches_tracked)
+        else:
+            _pending_counters.append(bn.num_batches_tracked)
+    return mom
+
+
+def _stem_fusable(conv, bn, pool, x):
+    ks = pool.kernel_size if isinstance(pool.kernel_size, tuple) else (pool.kernel_size,) * 2
+    st = pool.stride if isinstance(pool.stride, tuple) else (pool.stride,) * 2
+    pd = pool.padding if isinstance(pool.padding, tuple) else (pool.padding,) * 2
+    dl = pool.dilation if isinstance(pool.dilation, tuple) else (pool.dilation,) * 2
+    frozen = not (x.requires_grad or bn.weight.requires_grad or bn.bias.requires_grad or
+                  any(p.requires_grad for p in conv.parameters()))
+    return (frozen or not torch.is_grad_enabled()) and ks == (3, 3) and st == (2, 2) and pd == (1, 1) and \
+        dl == (1, 1) and not pool.ceil_mode and not pool.return_indices
+
+
+def stem(conv, bn, pool, x):
+    """maxpool(relu(bn(conv(x)))) with BN + ReLU + max-pool in one sweep when no gradient flows through the
+    stem (it is frozen in the reference); otherwise BN+ReLU fused and torch's max-pool."""
+    c = conv(x)
+    if not _stem_fusable(conv, bn, pool, x) or c.dtype != torch.bfloat16:
+        return pool(bn_act(c, bn, relu=True))
+    c = c.detach()
+    if not c.is_contiguous(memory_format=_CL):
+        c = c.contiguous(memory_format=_CL)
+    N, C, H, W = c.shape
+    OH, OW = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    dev = c.device
+    use_batch = bn.training or bn.running_mean is None
+    y = torch.empty((N, C, OH, OW), device=dev, dtype=torch.bfloat16, memory_format=_CL)
+    mean, rstd, ss = _f32(C, device=dev), _f32(C, device=dev), _f32(2, C, device=dev)
+    part = _f32(max(_lib.lib().v2f_bn2d_blocks(N * H * W, C), 1) * 2 * C, device=dev)
+    mom = _count_batch(bn, use_batch, bn.momentum)
+    check(_lib.lib().v2f_bn2d_relu_maxpool_fwd(N, H, W, C, c.data_ptr(), ptr(bn.weight), ptr(bn.bias),
+                                               ptr(bn.running_mean, allow_none=True),
+                                               ptr(bn.running_var, allow_none=True), 1 if use_batch else 0,
+                                               float(mom if mom is not None else 0.0), float(bn.eps), y.data_ptr(),
+                                               ptr(mean), ptr(rstd), ptr(ss), ptr(part), stream()),
+          "v2f_bn2d_relu_maxpool_fwd")
+    return y
+
+
 class _BnAct(torch.autograd.Function):
     """y = act(BatchNorm2d(x) (+ res)) on bf16 channels_last tensors; ``bn`` is the nn.BatchNorm2d whose
     parameters / running statistics are used (and updated in train mode)."""
@@ -42,10 +95,7 @@ class _BnAct(torch.autograd.Function):
         nblk = _lib.lib().v2f_bn2d_blocks(R, C)
         part = _f32(max(nblk, 1) * 2 * C, device=dev)
         mom = bn.momentum
-        if use_batch and bn.running_mean is not None and bn.num_batches_tracked is not None:
-            bn.num_batches_tracked.add_(1)
-            if mom is None:
-                mom = 1.0 / float(bn.num_batches_tracked)
+        mom = _count_batch(bn, use_batch, mom)
         check(_lib.lib().v2f_bn2d_act_fwd(R, C, x.data_ptr(), res.data_ptr() if res is not None else None,
                                           ptr(gamma), ptr(beta),
                                           ptr(bn.running_mean, allow_none=True), ptr(bn.running_var, allow_none=True),
@@ -120,12 +170,18 @@ def supported(cnn):
 
 def forward(cnn, images):
     """images [B,3,H,W] fp32 (any memory format) -> feature map [B,2048,h,w] bf16 channels_last."""
+    global _pending_counters
     mods = list(cnn.children())
     x = images.contiguous(memory_format=_CL)
-    with torch.autocast("cuda", dtype=torch.bfloat16):
-        x = bn_act(mods[0](x), mods[1], relu=True)
-        x = mods[3](x)
-        for layer in mods[4:]:
-            for blk in layer:
-                x = _bottleneck(blk, x)
+    _pending_counters = []
+    try:
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            x = stem(mods[0], mods[1], mods[3], x)
+            for layer in mods[4:]:
+                for blk in layer:
+                    x = _bottleneck(blk, x)
+        if _pending_counters:
+            torch._foreach_add_(_pending_counters, 1)
+    finally:
+        _pending_counters = None
     return x
