@@ -268,7 +268,46 @@ def run_product(args):
     clk = clocks.stop()
     for i in range(2):
         step_e2e(i)
-    ms_e2e = timed(step_e2e, args.steps, "e2e")
+    # end to end through the public pipeline: pinned host batches -> DevicePrefetcher (the copy of batch i+1
+    # overlaps step i on a side stream) -> training_step -> backward -> loss read-back.  Every timed step's
+    # host->device copy is issued inside the timed region.
+    from visuelle2_multimodal_fusion_b200.data import DevicePrefetcher
+
+    class _HostBatches:
+        def __init__(self, n):
+            self.n = n
+
+        def __iter__(self):
+            return ((host[i & 1][0], host[i & 1][1]) for i in range(self.n))
+
+        def __len__(self):
+            return self.n
+
+    def run_e2e(steps, tag=None):
+        barrier()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        ev[0].record()
+        for i, batch in enumerate(DevicePrefetcher(_HostBatches(steps), dev)):
+            torch.manual_seed(1234 + i)
+            loss = model.training_step(batch, i)
+            loss.backward()
+            if reducer:
+                reducer.finish()
+            zero()
+            float(loss.detach())                 # device->host read of the step's result
+            ev[i + 1].record()
+        barrier()
+        ms = ev[0].elapsed_time(ev[steps])
+        if tag:
+            step_ms[tag] = [round(ev[i].elapsed_time(ev[i + 1]), 3) for i in range(steps)]
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms
+
+    run_e2e(2)
+    ms_e2e = run_e2e(args.steps, "e2e")
 
     # ---- head-only figure (precomputed feature maps in), explains the roofline numbers
     head_ms = None

@@ -79,6 +79,13 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
                : "memory");
 }
 
+#ifdef V2F_GEMM_TIMELINE
+__device__ long long g_tl[16];
+#define TL(i) do { if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) { long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); g_tl[i] = t_; } } while (0)
+#else
+#define TL(i) do { } while (0)
+#endif
+
 struct TcArgs {
   int M, N, K;
   float* C;
@@ -94,7 +101,7 @@ struct TcArgs {
 
 // KIND 0: bf16 (64 elements per 128-B span, UMMA_K 16); KIND 1: tf32 (32 elements, UMMA_K 8)
 template <int KIND, int BN, int STAGES>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TC_THREADS, 2)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, TcArgs a) {
   constexpr int ELEM = KIND == 0 ? 2 : 4;
   constexpr int BK = TC_STAGE_BYTES_K / ELEM;       // elements of K per stage
@@ -114,6 +121,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(conv + STAGES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) TL(0);
   const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;
   const int bz = blockIdx.z / a.splits, split = blockIdx.z - bz * a.splits;
   const int kb0 = split * a.k_blocks;
@@ -140,6 +148,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_d = *tmem_ptr;
+  if (threadIdx.x == 0) TL(1);
 
   if (warp == 0) {
     if (lane == 0 && nkb > 0) {
@@ -158,9 +167,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       for (int i = 0; i < nkb; i++) {
         const int s = i % STAGES, r = i / STAGES;
         mbar_wait((KIND == 1 && (a.act & 4)) ? &conv[s] : &full[s], r & 1);
+        if (i == 0) TL(2);
+        if (i == 1) TL(3);
+        if (i == nkb - 1) TL(4);
         tc_fence_after();
         const uint64_t ad = umma_desc_sw128(smem_u32(sA + s * A_BYTES));
         const uint64_t bd = umma_desc_sw128(smem_u32(sB + s * B_BYTES));
+#ifdef V2F_GEMM_TIMELINE
+        if (!(a.act & 8))
+#endif
 #pragma unroll
         for (int k = 0; k < BK / UK; k++) {
           // advance 32 bytes of K inside the swizzle span: +2 in the (address >> 4) field
@@ -169,11 +184,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         umma_commit(&empty[s]);     // frees the smem slot when the MMAs above have read it
       }
       umma_commit(tmem_full);       // accumulator complete
+      TL(5);
     }
   } else {
     // ---- epilogue: warp w reads TMEM lanes 32*(w%4) .. +31  == output rows m0 + 32*(w%4) + lane
     const int q = warp & 3;
-    const int row = m0 + q * 32 + lane;
     if (KIND == 1 && (a.act & 4)) {
       // kind::tf32 ignores the low 13 mantissa bits of each fp32 operand, i.e. truncates: a biased error
       // (every product shrinks by ~7e-4) that survives the cancellations of a backward pass through
@@ -218,6 +233,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       mbar_wait(tmem_full, 0);
       tc_fence_after();
     }
+    if (threadIdx.x == 64) TL(6);
+    // Phase 1: TMEM -> registers -> shared staging tile [128][BN+1] (the operand ring is free: every MMA
+    // that read it has completed).  Thread = accumulator row; the odd pitch makes the writes conflict-free.
+    constexpr int LDS = BN + 1;
+    float* stg = reinterpret_cast<float*>(smem);
+    const int rloc = q * 32 + lane;
 #pragma unroll
     for (int c0 = 0; c0 < BN; c0 += 16) {
       uint32_t v[16];
@@ -233,44 +254,53 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 #pragma unroll
         for (int j = 0; j < 16; j++) v[j] = 0u;
       }
-      if (row < a.M) {
-        if (a.act & 2) {
-          // bf16 output (e.g. the gradient handed back to the bf16 backbone): no beta / atomics
-          __nv_bfloat16* crow = reinterpret_cast<__nv_bfloat16*>(a.C) + (long long)bz * a.sC + (long long)row * a.ldc;
 #pragma unroll
-          for (int j = 0; j < 16; j++) {
-            const int col = n0 + c0 + j;
-            if (col < a.N) {
-              float x = __uint_as_float(v[j]);
-              if (a.bias) x += a.bias[col];
-              if (a.act & 1) x = fmaxf(x, 0.f);
-              crow[col] = __float2bfloat16_rn(x);
-            }
-          }
-        } else {
-          float* crow = a.C + (long long)bz * a.sC + (long long)row * a.ldc;
-#pragma unroll
-          for (int j = 0; j < 16; j++) {
-            const int col = n0 + c0 + j;
-            if (col < a.N) {
-              float x = __uint_as_float(v[j]);
-              if (a.atomic) {
-                if (a.bias && split == 0) x += a.bias[col];
-                atomicAdd(crow + col, x);
-              } else {
-                if (a.bias) x += a.bias[col];
-                if (a.beta != 0.f) x += a.beta * crow[col];
-                if (a.act & 1) x = fmaxf(x, 0.f);
-                crow[col] = x;
-              }
-            }
+      for (int j = 0; j < 16; j++) stg[rloc * LDS + c0 + j] = __uint_as_float(v[j]);
+    }
+    named_bar_sync(1, TC_THREADS - 64);
+    if (threadIdx.x == 64) TL(9);
+    // Phase 2: coalesced write-out.  A warp instruction covers RPI rows x CPR consecutive columns
+    // (one 128-byte line per row when BN >= 32), instead of 32 rows x 4 bytes.
+    constexpr int CPR = BN < 32 ? BN : 32;      // lanes per row
+    constexpr int RPI = 32 / CPR;               // rows per warp instruction
+    const int wq = warp - 2;
+    const int rsub = lane / CPR, cl = lane % CPR;
+    const int ncols = a.N - n0 < BN ? a.N - n0 : BN;
+    for (int r0 = wq * RPI; r0 < TC_BM; r0 += 4 * RPI) {
+      const int r = r0 + rsub;
+      const int grow = m0 + r;
+      if (grow >= a.M) continue;
+      const float* srow = stg + r * LDS;
+      if (a.act & 2) {
+        // bf16 output (e.g. the gradient handed back to the bf16 backbone): no beta / atomics
+        __nv_bfloat16* crow = reinterpret_cast<__nv_bfloat16*>(a.C) + (long long)bz * a.sC + (long long)grow * a.ldc + n0;
+        for (int c = cl; c < ncols; c += CPR) {
+          float x = srow[c];
+          if (a.bias) x += a.bias[n0 + c];
+          if (a.act & 1) x = fmaxf(x, 0.f);
+          crow[c] = __float2bfloat16_rn(x);
+        }
+      } else {
+        float* crow = a.C + (long long)bz * a.sC + (long long)grow * a.ldc + n0;
+        for (int c = cl; c < ncols; c += CPR) {
+          float x = srow[c];
+          if (a.atomic) {
+            if (a.bias && split == 0) x += a.bias[n0 + c];
+            atomicAdd(crow + c, x);
+          } else {
+            if (a.bias) x += a.bias[n0 + c];
+            if (a.beta != 0.f) x += a.beta * crow[c];
+            if (a.act & 1) x = fmaxf(x, 0.f);
+            crow[c] = x;
           }
         }
       }
     }
   }
+  if (threadIdx.x == 64) TL(7);
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) TL(8);
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(TMEM_COLS) : "memory");
@@ -314,7 +344,9 @@ static int make_map(CUtensorMap* map, int kind, const void* ptr, long long rows,
 
 template <int KIND, int BN>
 static int launch_tc(const CUtensorMap& mA, const CUtensorMap& mB, const TcArgs& a, int gz, cudaStream_t s) {
-  constexpr int STAGES = BN >= 128 ? 4 : 6;
+  // two CTAs per SM (<= ~110 KB each) so that one tile's epilogue (a burst of global stores) overlaps the
+  // other tile's main loop
+  constexpr int STAGES = BN >= 128 ? 3 : (BN >= 64 ? 4 : 6);
   constexpr size_t smem = 1024 + (size_t)STAGES * (TC_BM + BN) * 128 + (3 * STAGES + 1) * 8 + 16;
   static bool attr_set = false;
   if (!attr_set) {
@@ -449,3 +481,9 @@ extern "C" int v2f_transpose(int rows, int cols, const void* in, long long ld, i
   V2F_CHECK_LAUNCH();
   return V2F_OK;
 }
+
+#ifdef V2F_GEMM_TIMELINE
+extern "C" int v2f_debug_timeline(long long* out) {
+  return cudaMemcpyFromSymbol(out, v2f::g_tl, sizeof(long long) * 16) == cudaSuccess ? 0 : -3;
+}
+#endif
