@@ -367,6 +367,28 @@ def run_product(args):
                           "timing": "CUDA events on the launching stream around each launch, separate pass"}
         model.image_encoder.cnn = cnn
         model.image_encoder.backbone_dtype = saved_dtype
+        # ---- the BatchNorm / add / ReLU sweeps of the trunk (csrc/bn_act.cu): full-model steps, CUDA events
+        # around every launch, algorithmic bytes summed by the library (they differ per layer)
+        if getattr(model.image_encoder, "fused_trunk", False):
+            _lib.prof_enable(True)
+            for i in range(2):
+                step_resident(i)
+            torch.cuda.synchronize()
+            _lib.prof_enable(False)
+            for name, kid in (("bn_stats_kernel", _lib.K_BN_STATS), ("bn_apply_kernel", _lib.K_BN_APPLY),
+                              ("bn_bwd_reduce_kernel", _lib.K_BN_BWD_REDUCE),
+                              ("bn_bwd_elemt_kernel", _lib.K_BN_BWD_ELEMT)):
+                tot, n, nbytes = _lib.prof_read_bytes(kid)
+                if n == 0:
+                    continue
+                ach = nbytes / (tot * 1e-3) / 1e9
+                roof[name] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                              "traffic": None, "kernel": name, "avg_launch_us": tot / n * 1e3,
+                              "launches_per_step": n / 2, "algorithmic_bytes_per_step": nbytes / 2,
+                              "ms_per_step": tot / 2, "peak_source": peak_src,
+                              "timing": "CUDA events on the launching stream around each launch, full-model pass"}
+            for kid in (_lib.K_ATTN_FWD, _lib.K_ATTN_BWD, _lib.K_TILEGRAD):
+                _lib.prof_read(kid)          # drop the head spans of this pass
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -393,8 +415,9 @@ def run_product(args):
                                    "fwd + mse_loss + bwd + zero_grad, full model incl. ResNet-101 trunk",
                        "per_gpu_batch": B, "global_batch": B * world, "E": E, "A": A, "H": H, "out_len": OUT_LEN,
                        "image": 299, "parallelism": f"dp{world}",
-                       "precision": {"backbone": "bf16 autocast channels_last (torchvision/cuDNN, not replaced)"
-                                     if args.precision == "bf16" else "fp32",
+                       "precision": {"backbone": "bf16 channels_last: torchvision modules, cuDNN convolutions; BatchNorm + residual add + "
+                                                 "ReLU (+ stem max-pool) as fused HBM sweeps of libv2f_b200.so (csrc/bn_act.cu)"
+                                     if args.precision == "bf16" else "fp32 torchvision/cuDNN, untouched",
                                      "head": ("tcgen05 GEMMs: bf16 on backbone features, tf32 elsewhere; fp32 state, softmax and gates"
                                               if args.precision == "bf16" else "fp32 CUDA-core kernels") + " (libv2f_b200.so)"},
                        "l2": "inputs larger than L2: two alternating batches, 137 MB of images each"},

@@ -29,11 +29,15 @@ int v2f_version(void);
 long long v2f_launch_count(void);
 
 /* Kernel ids for the optional event timing below. */
-enum { V2F_K_ATTN_FWD = 0, V2F_K_ATTN_BWD = 1, V2F_K_TILEGRAD = 2, V2F_K_COUNT = 3 };
+enum { V2F_K_ATTN_FWD = 0, V2F_K_ATTN_BWD = 1, V2F_K_TILEGRAD = 2, V2F_K_BN_STATS = 3, V2F_K_BN_APPLY = 4,
+       V2F_K_BN_BWD_REDUCE = 5, V2F_K_BN_BWD_ELEMT = 6, V2F_K_COUNT = 7 };
 /* Per-kernel CUDA-event timing on the launching stream (bench.py roofline leg).  Off by default.
  * v2f_prof_read sums the spans recorded for one kernel id since the previous read.            */
 int v2f_prof_enable(int on);
 int v2f_prof_read(int kernel_id, double* total_ms, long long* launches);
+/* Same, plus the algorithmic bytes the recorded launches moved (kernels whose size varies per launch,
+ * i.e. the BatchNorm sweeps, report them; 0 for the others).                                   */
+int v2f_prof_read_bytes(int kernel_id, double* total_ms, long long* launches, long long* bytes);
 
 /* ------------------------------------------------------------------------------------------
  * Dense projections: C[b] = op(A[b]) op(B[b]) (+bias[n]) (+beta*C[b]), optional ReLU (act=1).

@@ -61,6 +61,9 @@ def _declare(lib):
     lib.v2f_transpose.argtypes = [c_int, c_int, c_vp, c_ll, c_int, c_vp, c_ll, c_int, c_vp]
     lib.v2f_prof_enable.argtypes = [c_int]
     lib.v2f_prof_read.argtypes = [c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(c_ll)]
+    lib.v2f_prof_read_bytes.argtypes = [c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(c_ll),
+                                        ctypes.POINTER(c_ll)]
+    lib.v2f_prof_read_bytes.restype = c_int
     # ---- GTM-family row operators (csrc/gtm_ops.cu)
     lib.v2f_add_ln_fwd.argtypes = [c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_float, c_vp, c_vp, c_vp, c_vp]
     lib.v2f_add_ln_bwd_blocks.argtypes = [c_int]
@@ -148,7 +151,7 @@ def launch_count():
     return int(lib().v2f_launch_count())
 
 
-K_ATTN_FWD, K_ATTN_BWD, K_TILEGRAD = 0, 1, 2
+K_ATTN_FWD, K_ATTN_BWD, K_TILEGRAD, K_BN_STATS, K_BN_APPLY, K_BN_BWD_REDUCE, K_BN_BWD_ELEMT = range(7)
 
 
 def prof_enable(on):
@@ -160,3 +163,11 @@ def prof_read(kernel_id):
     ms, n = ctypes.c_double(0.0), c_ll(0)
     check(lib().v2f_prof_read(kernel_id, ctypes.byref(ms), ctypes.byref(n)), "v2f_prof_read")
     return ms.value, n.value
+
+
+def prof_read_bytes(kernel_id):
+    """(total_ms, launches, algorithmic_bytes) of one kernel id since the previous read."""
+    ms, n, b = ctypes.c_double(0.0), c_ll(0), c_ll(0)
+    check(lib().v2f_prof_read_bytes(kernel_id, ctypes.byref(ms), ctypes.byref(n), ctypes.byref(b)),
+          "v2f_prof_read_bytes")
+    return ms.value, n.value, b.value

@@ -472,14 +472,20 @@ extern "C" int v2f_bn2d_act_fwd(long long R, int C, const void* x, const void* r
   const Geo g = make_geo(C);
   const int nblk = sweep_blocks(R, C);
   const size_t smem = sizeof(float) * (size_t)g.RB * 2 * g.CVB * 8;
+  const long long tb = R * (long long)C * 2;     // bytes of one bf16 [R,C] tensor
   if (training) {
+    prof_begin(V2F_K_BN_STATS, s);
+    prof_bytes(V2F_K_BN_STATS, tb);
     bn_stats_kernel<<<nblk, BN_THREADS, smem, s>>>(R, C, (const uint4*)x, part);
+    prof_end(V2F_K_BN_STATS, s);
     V2F_CHECK_LAUNCH();
   }
   bn_fwd_finalize_kernel<<<(C + 31) / 32, dim3(32, FIN_Y), 0, s>>>(R, C, nblk, part, gamma, beta, run_mean, run_var, training,
                                                          momentum, eps, scale_shift, scale_shift + C, save_mean,
                                                          save_rstd);
   V2F_CHECK_LAUNCH();
+  prof_begin(V2F_K_BN_APPLY, s);
+  prof_bytes(V2F_K_BN_APPLY, tb * (res ? 3 : 2));
   const uint4 *xp = (const uint4*)x, *rp = (const uint4*)res;
   uint4* yp = (uint4*)y;
   const float *sc = scale_shift, *sh = scale_shift + C;
@@ -487,6 +493,7 @@ extern "C" int v2f_bn2d_act_fwd(long long R, int C, const void* x, const void* r
   else if (res) bn_apply_kernel<true, false><<<nblk, BN_THREADS, 0, s>>>(R, C, xp, rp, sc, sh, yp);
   else if (relu) bn_apply_kernel<false, true><<<nblk, BN_THREADS, 0, s>>>(R, C, xp, rp, sc, sh, yp);
   else bn_apply_kernel<false, false><<<nblk, BN_THREADS, 0, s>>>(R, C, xp, rp, sc, sh, yp);
+  prof_end(V2F_K_BN_APPLY, s);
   V2F_CHECK_LAUNCH();
   return V2F_OK;
 }
@@ -506,15 +513,22 @@ extern "C" int v2f_bn2d_act_bwd(long long R, int C, const void* dy, const void* 
   const size_t smem = sizeof(float) * (size_t)g.RB * 2 * g.CVB * 8;
   const uint4 *dyp = (const uint4*)dy, *xp = (const uint4*)x, *yp = (const uint4*)y;
   uint4 *dzp = (uint4*)dz, *dxp = (uint4*)dx;
+  const long long tb = R * (long long)C * 2;
+  prof_begin(V2F_K_BN_BWD_REDUCE, s);
+  prof_bytes(V2F_K_BN_BWD_REDUCE, tb * (2 + (relu ? 1 : 0) + ((relu && dz) ? 1 : 0)));
   if (relu && dz) bn_bwd_reduce_kernel<true, true><<<nblk, BN_THREADS, smem, s>>>(R, C, dyp, xp, yp, save_mean, save_rstd, dzp, part);
   else if (relu) bn_bwd_reduce_kernel<true, false><<<nblk, BN_THREADS, smem, s>>>(R, C, dyp, xp, yp, save_mean, save_rstd, dzp, part);
   else bn_bwd_reduce_kernel<false, false><<<nblk, BN_THREADS, smem, s>>>(R, C, dyp, xp, yp, save_mean, save_rstd, dzp, part);
+  prof_end(V2F_K_BN_BWD_REDUCE, s);
   V2F_CHECK_LAUNCH();
   bn_bwd_finalize_kernel<<<(C + 31) / 32, dim3(32, FIN_Y), 0, s>>>(R, C, nblk, part, gamma, save_rstd, training, dgamma, dbeta, coef);
   V2F_CHECK_LAUNCH();
+  prof_begin(V2F_K_BN_BWD_ELEMT, s);
+  prof_bytes(V2F_K_BN_BWD_ELEMT, tb * (3 + ((relu && !dz) ? 1 : 0)));
   if (relu && dz) bn_bwd_elemt_kernel<true, true><<<nblk, BN_THREADS, 0, s>>>(R, C, (const uint4*)dz, xp, yp, save_mean, save_rstd, coef, dxp);
   else if (relu) bn_bwd_elemt_kernel<true, false><<<nblk, BN_THREADS, 0, s>>>(R, C, dyp, xp, yp, save_mean, save_rstd, coef, dxp);
   else bn_bwd_elemt_kernel<false, false><<<nblk, BN_THREADS, 0, s>>>(R, C, dyp, xp, yp, save_mean, save_rstd, coef, dxp);
+  prof_end(V2F_K_BN_BWD_ELEMT, s);
   V2F_CHECK_LAUNCH();
   return V2F_OK;
 }

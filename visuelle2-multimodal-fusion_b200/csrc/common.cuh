@@ -30,6 +30,7 @@ namespace v2f {
 
 void prof_begin(int id, cudaStream_t st);
 void prof_end(int id, cudaStream_t st);
+void prof_bytes(int id, long long bytes);
 
 constexpr unsigned FULL = 0xffffffffu;
 

@@ -10,6 +10,7 @@ static bool g_prof_on = false;
 struct Span { cudaEvent_t a, b; };
 static std::vector<Span> g_spans[V2F_K_COUNT];
 static std::vector<Span> g_free;
+static long long g_bytes[V2F_K_COUNT];
 
 static Span take() {
   if (!g_free.empty()) {
@@ -28,6 +29,9 @@ void prof_begin(int id, cudaStream_t st) {
   Span s = take();
   cudaEventRecord(s.a, st);
   g_spans[id].push_back(s);
+}
+void prof_bytes(int id, long long bytes) {
+  if (g_prof_on) g_bytes[id] += bytes;
 }
 void prof_end(int id, cudaStream_t st) {
   if (!g_prof_on) return;
@@ -57,4 +61,11 @@ extern "C" int v2f_prof_read(int id, double* total_ms, long long* launches) {
   *launches = (long long)g_spans[id].size();
   g_spans[id].clear();
   return V2F_OK;
+}
+
+extern "C" int v2f_prof_read_bytes(int id, double* total_ms, long long* launches, long long* bytes) {
+  V2F_REQUIRE(id >= 0 && id < V2F_K_COUNT && bytes, V2F_ERR_BAD_ARG);
+  *bytes = v2f::g_bytes[id];
+  v2f::g_bytes[id] = 0;
+  return v2f_prof_read(id, total_ms, launches);
 }

@@ -32,13 +32,25 @@ def _record(obj, stream):
             _record(o, stream)
 
 
+_COPY_STREAMS = {}
+
+
+def _copy_stream(device):
+    """One copy stream per device for the life of the process: the caching allocator keeps a block pool per
+    stream, so a fresh stream per epoch would pay cudaMalloc (and its implicit synchronisation) again."""
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    if key not in _COPY_STREAMS:
+        _COPY_STREAMS[key] = torch.cuda.Stream(device=key)
+    return _COPY_STREAMS[key]
+
+
 class DevicePrefetcher:
     """Iterate ``loader`` yielding batches already on ``device``; the copy of the next batch runs on a side
     stream concurrently with the consumer's work on the current stream."""
 
     def __init__(self, loader, device, pin=True):
         self.loader, self.device, self.pin = loader, torch.device(device), pin
-        self.copy_stream = torch.cuda.Stream(device=self.device)
+        self.copy_stream = _copy_stream(self.device)
 
     def _stage(self, it):
         try:
