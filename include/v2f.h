@@ -153,6 +153,10 @@ int v2f_gru_seq_fwd(int N, int L, int I, int H, const float* x, const float* h0,
 /* dOut [N,L,H] (may be NULL), dhL [N,H] (may be NULL).  Scratch: dh [N,H], DGI [N,L,3H],
  * DGH [L,N,3H], Hprev [L,N,H].  Outputs (any may be NULL): dx [N,L,I], dh0 [N,H], dw_ih, dw_hh,
  * db_ih, db_hh.                                                                              */
+/* Both run the whole recurrence as ONE cooperative launch with W_hh resident in shared memory
+ * (csrc/gru_persist.cu; exact fp32, H % 16 == 0, H <= 512, L >= 2), else one GEMM + gate kernel per
+ * step.  v2f_gru_persistent_enable(0) forces the per-step path (A/B tests).                     */
+int v2f_gru_persistent_enable(int on);
 int v2f_gru_seq_bwd(int N, int L, int I, int H, const float* x, const float* h0,
                     const float* w_ih, const float* w_hh, const float* out, const float* RZN,
                     const float* GHN, const float* dOut, const float* dhL, float* dh, float* DGI,

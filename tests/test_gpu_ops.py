@@ -187,3 +187,31 @@ def test_gemm_tc_splitk_and_transpose():
     torch.cuda.synchronize()
     ref = dyT.double() @ xT.double().t()
     assert _rel(C, ref) < 2e-5
+
+
+@pytest.mark.parametrize("N,L,I,H", [(128, 52, 3, 512), (40, 5, 1, 64), (130, 3, 3, 32), (1280, 2, 1, 512), (300, 9, 2, 256)])
+def test_persistent_gru_equals_per_step_path(N, L, I, H):
+    """The one-launch cooperative GRU (W_hh resident in shared memory, csrc/gru_persist.cu) against the
+    GEMM + gate kernel per step path of the same library: outputs and every gradient."""
+    from visuelle2_multimodal_fusion_b200 import _lib
+    from visuelle2_multimodal_fusion_b200 import functional as Fv
+    g = torch.Generator().manual_seed(N + L + H)
+    k = 1 / math.sqrt(H)
+    mk = lambda *s: ((torch.rand(*s, generator=g) * 2 - 1) * k).cuda().requires_grad_(True)
+    x = torch.randn(N, L, I, generator=g).cuda().requires_grad_(True)
+    h0 = (torch.randn(N, H, generator=g) * 0.3).cuda().requires_grad_(True)
+    P = [mk(3 * H, I), mk(3 * H, H), mk(3 * H), mk(3 * H)]
+    d = torch.randn(N, L, H, generator=g).cuda()
+    res = {}
+    for on in (1, 0):
+        _lib.lib().v2f_gru_persistent_enable(on)
+        try:
+            out = Fv.gru_seq(x, h0, *P)
+            out.backward(d)
+            res[on] = [out.detach().clone()] + [t.grad.clone() for t in [x, h0] + P]
+            for t in [x, h0] + P:
+                t.grad = None
+        finally:
+            _lib.lib().v2f_gru_persistent_enable(1)
+    for a, b in zip(res[1], res[0]):
+        assert _rel(a, b) < 2e-5

@@ -60,6 +60,8 @@ def _declare(lib):
     lib.v2f_cast_bf16.argtypes = [c_ll, c_vp, c_vp, c_vp]
     lib.v2f_transpose.argtypes = [c_int, c_int, c_vp, c_ll, c_int, c_vp, c_ll, c_int, c_vp]
     lib.v2f_prof_enable.argtypes = [c_int]
+    lib.v2f_gru_persistent_enable.argtypes = [c_int]
+    lib.v2f_gru_persistent_enable.restype = c_int
     lib.v2f_prof_read.argtypes = [c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(c_ll)]
     lib.v2f_prof_read_bytes.argtypes = [c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(c_ll),
                                         ctypes.POINTER(c_ll)]
