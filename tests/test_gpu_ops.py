@@ -190,7 +190,8 @@ def test_gemm_tc_splitk_and_transpose():
 
 
 @pytest.mark.parametrize("N,L,I,H", [(128, 52, 3, 512), (40, 5, 1, 64), (130, 3, 3, 32), (1280, 2, 1, 512), (300, 9, 2, 256)])
-def test_persistent_gru_equals_per_step_path(N, L, I, H):
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_persistent_gru_equals_per_step_path(N, L, I, H, prec):
     """The one-launch cooperative GRU (W_hh resident in shared memory, csrc/gru_persist.cu) against the
     GEMM + gate kernel per step path of the same library: outputs and every gradient."""
     from visuelle2_multimodal_fusion_b200 import _lib
@@ -206,7 +207,8 @@ def test_persistent_gru_equals_per_step_path(N, L, I, H):
     for on in (1, 0):
         _lib.lib().v2f_gru_persistent_enable(on)
         try:
-            out = Fv.gru_seq(x, h0, *P)
+            with Fv.precision(prec):
+                out = Fv.gru_seq(x, h0, *P)
             out.backward(d)
             res[on] = [out.detach().clone()] + [t.grad.clone() for t in [x, h0] + P]
             for t in [x, h0] + P:
@@ -214,4 +216,4 @@ def test_persistent_gru_equals_per_step_path(N, L, I, H):
         finally:
             _lib.lib().v2f_gru_persistent_enable(1)
     for a, b in zip(res[1], res[0]):
-        assert _rel(a, b) < 2e-5
+        assert _rel(a, b) < (2e-5 if prec == "fp32" else 5e-3)     # tf32 (rounded vs truncated operands) in bf16 mode

@@ -14,10 +14,10 @@ namespace v2f {
 // gru_persist.cu: one cooperative launch for the whole recurrence, W_hh resident in shared memory
 bool gru_persist_supported(int N, int L, int H);
 int gru_persist_fwd(int N, int L, int H, const float* GI, const float* h0, const float* w_hh, const float* b_hh,
-                    float* out, float* RZN, float* GHN, cudaStream_t s);
+                    float* out, float* RZN, float* GHN, int precision, cudaStream_t s);
 int gru_persist_bwd(int N, int L, int H, const float* h0, const float* w_hh, const float* out, const float* RZN,
                     const float* GHN, const float* dOut, const float* dhL, float* DGI, float* DGH, float* Hprev,
-                    float* dh_out, cudaStream_t s);
+                    float* dh_out, int precision, cudaStream_t s);
 
 __global__ void __launch_bounds__(256)
 gru_gates_fwd_kernel(int N, int L, int H, int t, const float* __restrict__ GI,
@@ -83,7 +83,7 @@ extern "C" int v2f_gru_seq_fwd(int N, int L, int I, int H, const float* x, const
   cudaStream_t s = (cudaStream_t)st;
   const GemmCtx gx{precision, nullptr, 0, st};
   V2F_TRY(gemm_nt(gx, N * L, 3 * H, I, x, I, w_ih, I, GI, 3 * H, b_ih, 0.f));
-  if (gru_persist_supported(N, L, H)) return gru_persist_fwd(N, L, H, GI, h0, w_hh, b_hh, out, RZN, GHN, s);
+  if (gru_persist_supported(N, L, H)) return gru_persist_fwd(N, L, H, GI, h0, w_hh, b_hh, out, RZN, GHN, precision, s);
   for (int t = 0; t < L; t++) {
     const float* hp = t == 0 ? h0 : out + (long long)(t - 1) * H;
     const int ldh = t == 0 ? H : L * H;
@@ -108,7 +108,7 @@ extern "C" int v2f_gru_seq_bwd(int N, int L, int I, int H, const float* x, const
   const bool tc = precision != 0 && w_hhT;
   const bool persist = gru_persist_supported(N, L, H);
   if (persist) {
-    V2F_TRY(gru_persist_bwd(N, L, H, h0, w_hh, out, RZN, GHN, dOut, dhL, DGI, DGH, Hprev, dh, s));
+    V2F_TRY(gru_persist_bwd(N, L, H, h0, w_hh, out, RZN, GHN, dOut, dhL, DGI, DGH, Hprev, dh, precision, s));
   } else {
   if (tc) V2F_TRY(v2f_transpose(3 * H, H, w_hh, H, 1, w_hhT, 3 * H, 1, st));
   if (dhL)

@@ -12,17 +12,16 @@
 //   * CTA (ub, rb) owns hidden units [16 ub, 16 ub+16) of rows [32 rb, 32 rb+32): its 48 rows of
 //     W_hh (forward) or its 16 columns of W_hh (backward) -- 96 KB at H=512 -- are loaded into
 //     shared memory ONCE and reused by every step;
-//   * per step it reads the 32 x H slice of h_{t-1} (forward) / the 32 x 3H slice of dgh_t
-//     (backward) that the other unit blocks of its row block produced, through L2 (ld.global.cg),
-//     does the 32x48xH (32x16x3H) product in exact fp32 FMAs out of shared memory, applies the gate
-//     equations and publishes its slice;
-//   * the 32 CTAs of a row block synchronise once per step on a monotonic global counter
+//   * per step it pulls the 32 x H slice of h_{t-1} (forward) / the 32 x 3H slice of dgh_t
+//     (backward) that the other unit blocks of its row block produced, through L2 with cp.async.cg,
+//     does the 32x48xH (32x16x3H) product out of shared memory -- exact fp32 FMAs (precision 0) or
+//     warp-level tf32 tensor-core MMAs with round-to-nearest operands (precision 1) -- applies the gate
+//     equations and publishes its slice; the step's saved activations are prefetched into registers
+//     before the barrier so their latency hides behind it;
+//   * the unit blocks of a row block synchronise once per step on a monotonic global counter
 //     (release: __syncthreads + __threadfence + atomicAdd; acquire: spin on ld.acquire, bounded --
 //     a protocol bug traps instead of hanging the GPU).  Row blocks never wait for each other.
-// The kernel is launched cooperatively so that all CTAs are co-resident.  Exact fp32 (no tensor
-// cores): it serves both precision modes and removes the tf32 error from the recurrence.
-#include <type_traits>
-
+// The kernel is launched cooperatively so that all CTAs are co-resident.
 #include "common.cuh"
 
 namespace v2f {
@@ -58,6 +57,40 @@ __device__ __forceinline__ float dot4(const float4& a, const float4& b, float ac
   acc = fmaf(a.z, b.z, acc);
   return fmaf(a.w, b.w, acc);
 }
+__device__ __forceinline__ uint32_t tf32_rna(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+// D += A(16x8, row) * B(8x8, col), tf32 inputs, fp32 accumulate
+__device__ __forceinline__ void mma_tf32(float* d, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// Asynchronous copy of a [GP_RB, W] fp32 tile (global row pitch ld floats, shared row pitch P floats)
+// through L2 only (cp.async.cg: the data was written by other SMs).  Rows >= nrows are zero-filled.
+__device__ __forceinline__ void tile_copy_async(float* dst, int P, const float* src, long long ld, int W, int nrows) {
+  const int W4 = W >> 2;
+  for (int i = threadIdx.x; i < GP_RB * W4; i += GP_THREADS) {
+    const int r = i / W4, k4 = i - r * W4;
+    float* d = dst + r * P + 4 * k4;
+    if (r < nrows) {
+      const uint32_t sa = static_cast<uint32_t>(__cvta_generic_to_shared(d));
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(src + (long long)r * ld + 4 * k4)
+                   : "memory");
+    } else {
+      *reinterpret_cast<float4*>(d) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tile_copy_wait() {
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+}
 
 struct GpFwdArgs {
   int N, L, H, rows0;   // rows0: first row of this launch (row blocks are relative to it)
@@ -66,81 +99,130 @@ struct GpFwdArgs {
   unsigned* bar;
 };
 
-// shared: Ws [H/4][48] float4 (k-quad major), hs [32][H/4 + 1] float4, red [2][32][48] float
+// shared (floats): Wn [48][H+4] (row = gate*16 + unit), hs [32][H+4], red [4][32][48]
+template <bool TC>
 __global__ void __launch_bounds__(GP_THREADS, 1)
 gru_persist_fwd_kernel(GpFwdArgs a) {
-  extern __shared__ float4 sm4[];
-  const int H = a.H, H4 = H >> 2, HP = H4 + 1;
-  float4* Ws = sm4;
-  float4* hs = Ws + H4 * 48;
-  float* red = reinterpret_cast<float*>(hs + GP_RB * HP);
-  const int tid = threadIdx.x;
+  extern __shared__ __align__(16) float smf[];
+  const int H = a.H, P = H + 4;
+  float* Wn = smf;
+  float* hs = Wn + 48 * P;
+  float* red = hs + GP_RB * P;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int u0 = blockIdx.x * GP_UN;
   const int r0 = a.rows0 + blockIdx.y * GP_RB;
   const int nrows = min(GP_RB, a.N - r0);
   unsigned* ctr = a.bar + blockIdx.y;
   const unsigned nub = gridDim.x;
 
-  // ---- one-time: this CTA's 48 rows of W_hh -> Ws[k4][g*16+u]
-  for (int i = tid; i < 48 * H4; i += GP_THREADS) {
-    const int col = i / H4, k4 = i - col * H4;
-    const int g = col >> 4, u = col & 15;
-    Ws[k4 * 48 + col] = ld4(a.w_hh + (long long)(g * H + u0 + u) * H + 4 * k4);
+  // ---- one-time: this CTA's 48 rows of W_hh (rounded to tf32 once in tensor-core mode)
+  for (int i = tid; i < 48 * (H >> 2); i += GP_THREADS) {
+    const int col = i / (H >> 2), k4 = i - col * (H >> 2);
+    float4 w = ld4(a.w_hh + (long long)((col >> 4) * H + u0 + (col & 15)) * H + 4 * k4);
+    if (TC) {
+      w.x = __uint_as_float(tf32_rna(w.x));
+      w.y = __uint_as_float(tf32_rna(w.y));
+      w.z = __uint_as_float(tf32_rna(w.z));
+      w.w = __uint_as_float(tf32_rna(w.w));
+    }
+    *reinterpret_cast<float4*>(Wn + col * P + 4 * k4) = w;
   }
-  const int kh = tid >> 7;            // K half
-  const int tr = (tid >> 4) & 7;      // 4-row group
-  const int tu = tid & 15;            // unit
+  // the two (row, unit) pairs this thread owns in the gate phase, and their recurrent biases
+  const int pr[2] = {tid >> 4, (tid >> 4) + 16};
+  const int pu = tid & 15, gu = u0 + pu;
+  float bh[3];
+#pragma unroll
+  for (int g = 0; g < 3; g++) bh[g] = a.b_hh[g * H + gu];
+
   for (int t = 0; t < a.L; t++) {
+    // ---- prefetch the input projections of this step (independent of h): hides behind the barrier
+    float gi[2][3];
+#pragma unroll
+    for (int p = 0; p < 2; p++)
+#pragma unroll
+      for (int g = 0; g < 3; g++)
+        gi[p][g] = pr[p] < nrows ? a.GI[((long long)(r0 + pr[p]) * a.L + t) * 3 * H + g * H + gu] : 0.f;
     if (t > 0) row_block_barrier(ctr, (unsigned)t * nub);
-    // ---- h_{t-1} slice [32, H] through L2 (written by other SMs: bypass L1)
     const float* hp = t == 0 ? a.h0 : a.out + (long long)(t - 1) * H;
     const long long ldh = t == 0 ? H : (long long)a.L * H;
-    for (int i = tid; i < GP_RB * H4; i += GP_THREADS) {
-      const int r = i / H4, k4 = i - r * H4;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (r < nrows) v = __ldcg(reinterpret_cast<const float4*>(hp + (long long)(r0 + r) * ldh) + k4);
-      hs[r * HP + k4] = v;
-    }
-    __syncthreads();
-    // ---- gh[32 x 48] = hs Ws^T, K split in two halves
-    float acc[4][3];
+    tile_copy_async(hs, P, hp + (long long)r0 * ldh, ldh, H, nrows);
+    tile_copy_wait();
+    // ---- gh[32 x 48] = hs Wn^T ; partial sums over K quarters / halves go to red[part][row][col]
+    if (TC) {
+      const int mt = warp & 1, kq = warp >> 1, g = lane >> 2, tt = lane & 3;
+      float acc[6][4];
 #pragma unroll
-    for (int r = 0; r < 4; r++)
+      for (int n = 0; n < 6; n++)
 #pragma unroll
-      for (int g = 0; g < 3; g++) acc[r][g] = 0.f;
-    const int kb = kh * (H4 >> 1), ke = kb + (H4 >> 1);
+        for (int j = 0; j < 4; j++) acc[n][j] = 0.f;
+      const float* ha = hs + (16 * mt + g) * P + tt;
+      const float* wb = Wn + g * P + tt;
+      const int kb = kq * (H >> 2), ke = kb + (H >> 2);
 #pragma unroll 2
-    for (int k4 = kb; k4 < ke; k4++) {
-      float4 w[3], h[4];
+      for (int k0 = kb; k0 < ke; k0 += 8) {
+        uint32_t af[4];
+        af[0] = tf32_rna(ha[k0]);
+        af[1] = tf32_rna(ha[8 * P + k0]);
+        af[2] = tf32_rna(ha[k0 + 4]);
+        af[3] = tf32_rna(ha[8 * P + k0 + 4]);
 #pragma unroll
-      for (int g = 0; g < 3; g++) w[g] = Ws[k4 * 48 + g * 16 + tu];
+        for (int n = 0; n < 6; n++)
+          mma_tf32(acc[n], af, __float_as_uint(wb[n * 8 * P + k0]), __float_as_uint(wb[n * 8 * P + k0 + 4]));
+      }
 #pragma unroll
-      for (int r = 0; r < 4; r++) h[r] = hs[(tr * 4 + r) * HP + k4];
+      for (int n = 0; n < 6; n++) {
+        float* rp = red + (kq * GP_RB + 16 * mt + g) * 48 + n * 8 + 2 * tt;
+        rp[0] = acc[n][0];
+        rp[1] = acc[n][1];
+        rp[8 * 48] = acc[n][2];
+        rp[8 * 48 + 1] = acc[n][3];
+      }
+    } else {
+      const int kh = tid >> 7, tr = (tid >> 4) & 7, tu = tid & 15;
+      float acc[4][3];
 #pragma unroll
       for (int r = 0; r < 4; r++)
 #pragma unroll
-        for (int g = 0; g < 3; g++) acc[r][g] = dot4(h[r], w[g], acc[r][g]);
+        for (int g = 0; g < 3; g++) acc[r][g] = 0.f;
+      const int kb = kh * (H >> 1), ke = kb + (H >> 1);
+#pragma unroll 2
+      for (int k = kb; k < ke; k += 4) {
+        float4 w[3], h[4];
+#pragma unroll
+        for (int g = 0; g < 3; g++) w[g] = *reinterpret_cast<const float4*>(Wn + (g * 16 + tu) * P + k);
+#pragma unroll
+        for (int r = 0; r < 4; r++) h[r] = *reinterpret_cast<const float4*>(hs + (tr * 4 + r) * P + k);
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+#pragma unroll
+          for (int g = 0; g < 3; g++) acc[r][g] = dot4(h[r], w[g], acc[r][g]);
+      }
+#pragma unroll
+      for (int r = 0; r < 4; r++)
+#pragma unroll
+        for (int g = 0; g < 3; g++) {
+          red[(kh * GP_RB + tr * 4 + r) * 48 + g * 16 + tu] = acc[r][g];
+          red[((kh + 2) * GP_RB + tr * 4 + r) * 48 + g * 16 + tu] = 0.f;
+        }
     }
-#pragma unroll
-    for (int r = 0; r < 4; r++)
-#pragma unroll
-      for (int g = 0; g < 3; g++) red[(kh * GP_RB + tr * 4 + r) * 48 + g * 16 + tu] = acc[r][g];
     __syncthreads();
     // ---- gates: 32 rows x 16 units, two per thread
-    for (int i = tid; i < GP_RB * GP_UN; i += GP_THREADS) {
-      const int r = i >> 4, u = i & 15;
+#pragma unroll
+    for (int p = 0; p < 2; p++) {
+      const int r = pr[p];
       if (r >= nrows) continue;
-      const int n = r0 + r, gu = u0 + u;
+      const int n = r0 + r;
       float gh[3];
 #pragma unroll
-      for (int g = 0; g < 3; g++)
-        gh[g] = red[r * 48 + g * 16 + u] + red[(GP_RB + r) * 48 + g * 16 + u] + a.b_hh[g * H + gu];
-      const float* gi = a.GI + ((long long)n * a.L + t) * 3 * H;
-      const float rg = sigmoid_full(gi[gu] + gh[0]);
-      const float zg = sigmoid_full(gi[H + gu] + gh[1]);
-      const float cg = tanh_full(gi[2 * H + gu] + rg * gh[2]);
-      const float4 hq = hs[r * HP + (gu >> 2)];
-      const float hprev = (gu & 3) == 0 ? hq.x : (gu & 3) == 1 ? hq.y : (gu & 3) == 2 ? hq.z : hq.w;
+      for (int g = 0; g < 3; g++) {
+        const int c = g * 16 + pu;
+        gh[g] = red[r * 48 + c] + red[(GP_RB + r) * 48 + c] + red[(2 * GP_RB + r) * 48 + c] +
+                red[(3 * GP_RB + r) * 48 + c] + bh[g];
+      }
+      const float rg = sigmoid_full(gi[p][0] + gh[0]);
+      const float zg = sigmoid_full(gi[p][1] + gh[1]);
+      const float cg = tanh_full(gi[p][2] + rg * gh[2]);
+      const float hprev = hs[r * P + gu];
       float* rzn = a.RZN + ((long long)t * a.N + n) * 3 * H;
       rzn[gu] = rg;
       rzn[H + gu] = zg;
@@ -159,54 +241,69 @@ struct GpBwdArgs {
   unsigned* bar;
 };
 
-// shared: Wc [3H/4][16] float4 (k = gate row, k-quad major), dg [32][H/4 + 1] float4 (one gate chunk),
-//         red [4][32][16] float, dhs [32][16] float (the gradient carried through time)
+struct SavedStep { float rg, zg, cg, ghn, hprev, dout; };
+
+// shared (floats): Wc [16][3H+4] (row = own unit, column = gate row j), dg [32][H+4] (one gate chunk of
+// dgh_t), red [4][32][16], dhs [32][16] (the gradient carried through time)
+template <bool TC>
 __global__ void __launch_bounds__(GP_THREADS, 1)
 gru_persist_bwd_kernel(GpBwdArgs a) {
-  extern __shared__ float4 sm4[];
-  const int H = a.H, H4 = H >> 2, HP = H4 + 1, K4 = 3 * H4;
-  float4* Wc = sm4;
-  float4* dg = Wc + K4 * 16;
-  float* red = reinterpret_cast<float*>(dg + GP_RB * HP);
+  extern __shared__ __align__(16) float smf[];
+  const int H = a.H, P = H + 4, PW = 3 * H + 4;
+  float* Wc = smf;
+  float* dg = Wc + 16 * PW;
+  float* red = dg + GP_RB * P;
   float* dhs = red + 4 * GP_RB * GP_UN;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int u0 = blockIdx.x * GP_UN;
   const int r0 = a.rows0 + blockIdx.y * GP_RB;
   const int nrows = min(GP_RB, a.N - r0);
   unsigned* ctr = a.bar + blockIdx.y;
   const unsigned nub = gridDim.x;
 
-  // ---- one-time: this CTA's 16 columns of W_hh -> Wc[j4][u] = (W[4j4..4j4+3][u0+u])
-  for (int i = tid; i < K4 * 16; i += GP_THREADS) {
-    const int j4 = i >> 4, u = i & 15;
-    const float* p = a.w_hh + (long long)(4 * j4) * H + u0 + u;
-    Wc[i] = make_float4(p[0], p[H], p[2 * (long long)H], p[3 * (long long)H]);
+  // ---- one-time: this CTA's 16 columns of W_hh, transposed: Wc[u][j] = W_hh[j][u0+u]
+  for (int i = tid; i < 3 * H * 16; i += GP_THREADS) {
+    const int j = i >> 4, u = i & 15;
+    float w = a.w_hh[(long long)j * H + u0 + u];
+    if (TC) w = __uint_as_float(tf32_rna(w));
+    Wc[u * PW + j] = w;
   }
-  for (int i = tid; i < GP_RB * GP_UN; i += GP_THREADS) {
-    const int r = i >> 4, u = i & 15;
-    dhs[i] = (a.dhL && r < nrows) ? a.dhL[(long long)(r0 + r) * H + u0 + u] : 0.f;
-  }
-  __syncthreads();
-  const int ks = tid >> 6;            // K quarter within a chunk
-  const int tr = (tid >> 4) & 3;      // 8-row group
-  const int tu = tid & 15;
-  for (int t = a.L - 1; t >= 0; t--) {
-    // ---- gate backward for the own (rows, units); publishes DGH[t, rows, own gate rows]
+  const int pr[2] = {tid >> 4, (tid >> 4) + 16};
+  const int pu = tid & 15, gu = u0 + pu;
+#pragma unroll
+  for (int p = 0; p < 2; p++)
+    dhs[pr[p] * GP_UN + pu] = (a.dhL && pr[p] < nrows) ? a.dhL[(long long)(r0 + pr[p]) * H + gu] : 0.f;
+
+  SavedStep sv[2];
+  auto load_saved = [&](int t) {
     const float* hp = t == 0 ? a.h0 : a.out + (long long)(t - 1) * H;
     const long long ldh = t == 0 ? H : (long long)a.L * H;
-    for (int i = tid; i < GP_RB * GP_UN; i += GP_THREADS) {
-      const int r = i >> 4, u = i & 15;
-      if (r >= nrows) continue;
-      const int n = r0 + r, gu = u0 + u;
+#pragma unroll
+    for (int p = 0; p < 2; p++) {
+      if (pr[p] >= nrows) continue;
+      const int n = r0 + pr[p];
       const float* rzn = a.RZN + ((long long)t * a.N + n) * 3 * H;
-      const float rg = rzn[gu], zg = rzn[H + gu], cg = rzn[2 * H + gu];
-      const float ghn = a.GHN[((long long)t * a.N + n) * H + gu];
-      const float hprev = hp[(long long)n * ldh + gu];
-      float dhp = dhs[i];
-      if (a.dOut) dhp += a.dOut[((long long)n * a.L + t) * H + gu];
+      sv[p].rg = rzn[gu];
+      sv[p].zg = rzn[H + gu];
+      sv[p].cg = rzn[2 * H + gu];
+      sv[p].ghn = a.GHN[((long long)t * a.N + n) * H + gu];
+      sv[p].hprev = hp[(long long)n * ldh + gu];
+      sv[p].dout = a.dOut ? a.dOut[((long long)n * a.L + t) * H + gu] : 0.f;
+    }
+  };
+  load_saved(a.L - 1);
+  __syncthreads();
+  for (int t = a.L - 1; t >= 0; t--) {
+    // ---- gate backward for the own (rows, units); publishes DGH[t, rows, own gate rows]
+#pragma unroll
+    for (int p = 0; p < 2; p++) {
+      if (pr[p] >= nrows) continue;
+      const int n = r0 + pr[p], i = pr[p] * GP_UN + pu;
+      const float rg = sv[p].rg, zg = sv[p].zg, cg = sv[p].cg;
+      const float dhp = dhs[i] + sv[p].dout;
       const float dan = dhp * (1.f - zg) * (1.f - cg * cg);
-      const float daz = dhp * (hprev - cg) * zg * (1.f - zg);
-      const float dar = dan * ghn * rg * (1.f - rg);
+      const float daz = dhp * (sv[p].hprev - cg) * zg * (1.f - zg);
+      const float dar = dan * sv[p].ghn * rg * (1.f - rg);
       float* dgi = a.DGI + ((long long)n * a.L + t) * 3 * H;
       dgi[gu] = dar;
       dgi[H + gu] = daz;
@@ -215,61 +312,93 @@ gru_persist_bwd_kernel(GpBwdArgs a) {
       dgh[gu] = dar;
       dgh[H + gu] = daz;
       dgh[2 * H + gu] = dan * rg;
-      a.Hprev[((long long)t * a.N + n) * H + gu] = hprev;
+      a.Hprev[((long long)t * a.N + n) * H + gu] = sv[p].hprev;
       dhs[i] = dhp * zg;
     }
+    if (t > 0) load_saved(t - 1);          // consumed after this step's product: latency hidden
     row_block_barrier(ctr, (unsigned)(a.L - t) * nub);
     // ---- dh[rows, own units] += DGH[t, rows, :] W_hh[:, own units], three gate chunks of H
-    float acc[8];
+    float accf[8];
+    float acct[2][4];
 #pragma unroll
-    for (int r = 0; r < 8; r++) acc[r] = 0.f;
+    for (int r = 0; r < 8; r++) accf[r] = 0.f;
+#pragma unroll
+    for (int n = 0; n < 2; n++)
+#pragma unroll
+      for (int j = 0; j < 4; j++) acct[n][j] = 0.f;
     for (int c = 0; c < 3; c++) {
       if (c > 0) __syncthreads();     // previous chunk fully consumed
-      for (int i = tid; i < GP_RB * H4; i += GP_THREADS) {
-        const int r = i / H4, k4 = i - r * H4;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (r < nrows)
-          v = __ldcg(reinterpret_cast<const float4*>(a.DGH + ((long long)t * a.N + r0 + r) * 3 * H + c * H) + k4);
-        dg[r * HP + k4] = v;
-      }
-      __syncthreads();
-      const int q = H4 >> 2, kb = ks * q, ke = kb + q;
+      tile_copy_async(dg, P, a.DGH + ((long long)t * a.N + r0) * 3 * H + c * H, 3LL * H, H, nrows);
+      tile_copy_wait();
+      if (TC) {
+        const int mt = warp & 1, kq = warp >> 1, g = lane >> 2, tt = lane & 3;
+        const float* da = dg + (16 * mt + g) * P + tt;
+        const float* wb = Wc + g * PW + c * H + tt;
+        const int kb = kq * (H >> 2), ke = kb + (H >> 2);
 #pragma unroll 2
-      for (int k4 = kb; k4 < ke; k4++) {
-        const float4 w = Wc[(c * H4 + k4) * 16 + tu];
+        for (int k0 = kb; k0 < ke; k0 += 8) {
+          uint32_t af[4];
+          af[0] = tf32_rna(da[k0]);
+          af[1] = tf32_rna(da[8 * P + k0]);
+          af[2] = tf32_rna(da[k0 + 4]);
+          af[3] = tf32_rna(da[8 * P + k0 + 4]);
 #pragma unroll
-        for (int r = 0; r < 8; r++) acc[r] = dot4(dg[(tr * 8 + r) * HP + k4], w, acc[r]);
+          for (int n = 0; n < 2; n++)
+            mma_tf32(acct[n], af, __float_as_uint(wb[n * 8 * PW + k0]), __float_as_uint(wb[n * 8 * PW + k0 + 4]));
+        }
+      } else {
+        const int ks = tid >> 6, tr = (tid >> 4) & 3, tu = tid & 15;
+        const int kb = ks * (H >> 2), ke = kb + (H >> 2);
+#pragma unroll 2
+        for (int k = kb; k < ke; k += 4) {
+          const float4 w = *reinterpret_cast<const float4*>(Wc + tu * PW + c * H + k);
+#pragma unroll
+          for (int r = 0; r < 8; r++)
+            accf[r] = dot4(*reinterpret_cast<const float4*>(dg + (tr * 8 + r) * P + k), w, accf[r]);
+        }
       }
     }
+    if (TC) {
+      const int mt = warp & 1, kq = warp >> 1, g = lane >> 2, tt = lane & 3;
 #pragma unroll
-    for (int r = 0; r < 8; r++) red[(ks * GP_RB + tr * 8 + r) * GP_UN + tu] = acc[r];
+      for (int n = 0; n < 2; n++) {
+        float* rp = red + (kq * GP_RB + 16 * mt + g) * GP_UN + n * 8 + 2 * tt;
+        rp[0] = acct[n][0];
+        rp[1] = acct[n][1];
+        rp[8 * GP_UN] = acct[n][2];
+        rp[8 * GP_UN + 1] = acct[n][3];
+      }
+    } else {
+      const int ks = tid >> 6, tr = (tid >> 4) & 3, tu = tid & 15;
+#pragma unroll
+      for (int r = 0; r < 8; r++) red[(ks * GP_RB + tr * 8 + r) * GP_UN + tu] = accf[r];
+    }
     __syncthreads();
-    for (int i = tid; i < GP_RB * GP_UN; i += GP_THREADS)
+#pragma unroll
+    for (int p = 0; p < 2; p++) {
+      const int i = pr[p] * GP_UN + pu;
       dhs[i] += red[i] + red[GP_RB * GP_UN + i] + red[2 * GP_RB * GP_UN + i] + red[3 * GP_RB * GP_UN + i];
+    }
     __syncthreads();
   }
   if (a.dh_out)
-    for (int i = tid; i < GP_RB * GP_UN; i += GP_THREADS) {
-      const int r = i >> 4, u = i & 15;
-      if (r < nrows) a.dh_out[(long long)(r0 + r) * H + u0 + u] = dhs[i];
-    }
+#pragma unroll
+    for (int p = 0; p < 2; p++)
+      if (pr[p] < nrows) a.dh_out[(long long)(r0 + pr[p]) * H + gu] = dhs[pr[p] * GP_UN + pu];
 }
 
 static int g_gp_slot = 0;
-
-static size_t gp_smem(int H) {
-  // fwd: Ws 48*H/4 + hs 32*(H/4+1) float4 + red 2*32*48 floats ; bwd: Wc 3H/4*16 + dg 32*(H/4+1) float4
-  //      + red 4*32*16 + dhs 32*16 floats.  Same leading terms; take the max of the tails.
-  const size_t f4 = (size_t)48 * (H / 4) + (size_t)GP_RB * (H / 4 + 1);
-  return f4 * 16 + sizeof(float) * (2 * GP_RB * 48 + 4 * GP_RB * GP_UN + GP_RB * GP_UN);
-}
-
 static bool g_gp_enabled = true;
 void gru_persist_enable(bool on) { g_gp_enabled = on; }
 
+static size_t gp_smem(int H, bool fwd) {
+  if (fwd) return sizeof(float) * ((size_t)(48 + GP_RB) * (H + 4) + 4 * GP_RB * 48);
+  return sizeof(float) * ((size_t)16 * (3 * H + 4) + (size_t)GP_RB * (H + 4) + 4 * GP_RB * GP_UN + GP_RB * GP_UN);
+}
+
 bool gru_persist_supported(int N, int L, int H) {
   if (!g_gp_enabled) return false;
-  if (H % 16 != 0 || H < 16 || H > 512 || L < 2 || N < 1) return false;
+  if (H % 32 != 0 || H < 32 || H > 512 || L < 2 || N < 1) return false;
   int dev = 0, coop = 0, sms = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return false;
   cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
@@ -278,14 +407,11 @@ bool gru_persist_supported(int N, int L, int H) {
 }
 
 template <typename Args, typename Kern>
-static int gp_launch(Kern kern, Args a, int N, int H, cudaStream_t s) {
-  static bool attr_done[2] = {false, false};
-  const size_t smem = gp_smem(H);
-  const int which = std::is_same<Args, GpFwdArgs>::value ? 0 : 1;
-  if (!attr_done[which]) {
+static int gp_launch(Kern kern, bool* attr_done, Args a, int N, int H, size_t smem, cudaStream_t s) {
+  if (!*attr_done) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
       return V2F_ERR_LAUNCH;
-    attr_done[which] = true;
+    *attr_done = true;
   }
   int dev = 0, sms = 148, per_sm = 0;
   cudaGetDevice(&dev);
@@ -315,16 +441,20 @@ static int gp_launch(Kern kern, Args a, int N, int H, cudaStream_t s) {
 }
 
 int gru_persist_fwd(int N, int L, int H, const float* GI, const float* h0, const float* w_hh, const float* b_hh,
-                    float* out, float* RZN, float* GHN, cudaStream_t s) {
+                    float* out, float* RZN, float* GHN, int precision, cudaStream_t s) {
+  static bool done[2] = {false, false};
   GpFwdArgs a{N, L, H, 0, GI, h0, w_hh, b_hh, out, RZN, GHN, nullptr};
-  return gp_launch(gru_persist_fwd_kernel, a, N, H, s);
+  if (precision) return gp_launch(gru_persist_fwd_kernel<true>, &done[1], a, N, H, gp_smem(H, true), s);
+  return gp_launch(gru_persist_fwd_kernel<false>, &done[0], a, N, H, gp_smem(H, true), s);
 }
 
 int gru_persist_bwd(int N, int L, int H, const float* h0, const float* w_hh, const float* out, const float* RZN,
                     const float* GHN, const float* dOut, const float* dhL, float* DGI, float* DGH, float* Hprev,
-                    float* dh_out, cudaStream_t s) {
+                    float* dh_out, int precision, cudaStream_t s) {
+  static bool done[2] = {false, false};
   GpBwdArgs a{N, L, H, 0, h0, w_hh, out, RZN, GHN, dOut, dhL, DGI, DGH, Hprev, dh_out, nullptr};
-  return gp_launch(gru_persist_bwd_kernel, a, N, H, s);
+  if (precision) return gp_launch(gru_persist_bwd_kernel<true>, &done[1], a, N, H, gp_smem(H, false), s);
+  return gp_launch(gru_persist_bwd_kernel<false>, &done[0], a, N, H, gp_smem(H, false), s);
 }
 
 }  // namespace v2f
