@@ -77,7 +77,7 @@ def _nbytes(batch):
 
 
 class _Clocks:
-    """SM clock and throttle reasons sampled every 100 ms DURING the timed region through NVML (the
+    """SM clock and throttle reasons sampled every 250 ms DURING the timed region through NVML (the
     source nvidia-smi reads; polling nvidia-smi itself at 200 ms perturbed the step time by 2x)."""
 
     def __init__(self, gpu_index):
@@ -109,7 +109,7 @@ class _Clocks:
                         self.reasons.add(k)
             except Exception:
                 pass
-            self._stop.wait(0.1)
+            self._stop.wait(0.25)
 
     def start(self):
         if self.nv is None:
@@ -129,7 +129,7 @@ class _Clocks:
         self._thr.join()
         sm = sorted(self.sm)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.mx, "reasons": sorted(self.reasons),
-                "samples": len(sm), "source": "NVML (pynvml), 100 ms"}
+                "samples": len(sm), "source": "NVML (pynvml), 250 ms"}
 
 
 def _cpu_reference_step_fn(batch_items, threads):
@@ -260,12 +260,14 @@ def run_product(args):
     import gc
     gc.collect()
     gc.freeze()
+    gc.disable()          # collections happen between the timed regions (gc.collect() below), not inside them
     clocks = _Clocks(local)
     clocks.start()
     l0 = _lib.launch_count()
     ms = timed(step_resident, args.steps, "resident")
     launches = _lib.launch_count() - l0
     clk = clocks.stop()
+    gc.collect()
     for i in range(2):
         step_e2e(i)
     # end to end through the public pipeline: pinned host batches -> DevicePrefetcher (the copy of batch i+1
@@ -307,7 +309,9 @@ def run_product(args):
         return ms
 
     run_e2e(2)
+    gc.collect()
     ms_e2e = run_e2e(args.steps, "e2e")
+    gc.collect()
 
     # ---- head-only figure (precomputed feature maps in), explains the roofline numbers
     head_ms = None
@@ -440,7 +444,7 @@ def run_product(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=128)
