@@ -196,8 +196,11 @@ def run_product(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device(dev))
     B = args.batch
+    if os.environ.get("V2F_NO_PERSISTENT_GRU"):          # A/B knob for experiments
+        _lib.lib().v2f_gru_persistent_enable(0)
     model = _build_model(dev, args.precision)
-    reducer = GradReducer(model) if world > 1 else None
+    use_graph = not args.no_graph
+    reducer = GradReducer(model, hooks=not use_graph) if world > 1 else None
     # two distinct batches per rank, alternated: 137 MB of images each, larger than the 126 MB L2
     host = [_batch(B, seed=21 + 1000 * rank + i, pin=True) for i in range(2)]
     resident = [(tuple(t.to(dev) for t in d), im.to(dev)) for d, im in host]
@@ -242,6 +245,10 @@ def run_product(args):
         for i in range(steps):
             fn(i)
             ev[i + 1].record()
+            # keep the launching thread at most one step ahead of the GPU (what reading the loss every step does
+            # in a trainer): with an unbounded run-ahead the driver's launch queue fills and its back-off when
+            # the thread is finally let through showed up as isolated 100-300 ms steps
+            ev[i].synchronize()
         barrier()
         ms = ev[0].elapsed_time(ev[steps])
         if tag:
@@ -251,6 +258,23 @@ def run_product(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t)
         return ms
+
+    # ---- default: the whole step (forward + loss + backward) replayed from ONE CUDA graph
+    # (graphs.GraphedTrainStep); gradients stay in p.grad (static storage), so there is no zero_grad, and the
+    # DDP all-reduce runs right after the replay.  --no-graph times the eager loop instead.
+    step_eager = step_resident
+    graphed = None
+    if use_graph:
+        from visuelle2_multimodal_fusion_b200.graphs import GraphedTrainStep
+        torch.manual_seed(99)
+        graphed = GraphedTrainStep(model, resident[0])
+
+        def step_resident(i):                                # noqa: F811
+            torch.manual_seed(1234 + i)
+            loss = graphed(resident[i & 1])
+            if reducer:
+                reducer.reduce_now()
+            return loss
 
     for i in range(max(args.warmup, 3)):
         step_resident(i)
@@ -262,14 +286,18 @@ def run_product(args):
     gc.freeze()
     gc.disable()          # collections happen between the timed regions (gc.collect() below), not inside them
     clocks = _Clocks(local)
-    clocks.start()
+    if not os.environ.get("V2F_BENCH_NO_CLOCKS"):        # experiment knob: is the NVML poll what perturbs?
+        clocks.start()
     l0 = _lib.launch_count()
     ms = timed(step_resident, args.steps, "resident")
     launches = _lib.launch_count() - l0
+    if graphed is not None:
+        launches = graphed.launches_per_replay * args.steps   # replays do not pass through the host-side counter
     clk = clocks.stop()
     gc.collect()
-    for i in range(2):
-        step_e2e(i)
+    if graphed is None:
+        for i in range(2):
+            step_e2e(i)
     # end to end through the public pipeline: pinned host batches -> DevicePrefetcher (the copy of batch i+1
     # overlaps step i on a side stream) -> training_step -> backward -> loss read-back.  Every timed step's
     # host->device copy is issued inside the timed region.
@@ -291,11 +319,16 @@ def run_product(args):
         ev[0].record()
         for i, batch in enumerate(DevicePrefetcher(_HostBatches(steps), dev)):
             torch.manual_seed(1234 + i)
-            loss = model.training_step(batch, i)
-            loss.backward()
-            if reducer:
-                reducer.finish()
-            zero()
+            if graphed is not None:
+                loss = graphed(batch)            # staged device batch -> the graph's input buffers -> replay
+                if reducer:
+                    reducer.reduce_now()
+            else:
+                loss = model.training_step(batch, i)
+                loss.backward()
+                if reducer:
+                    reducer.finish()
+                zero()
             float(loss.detach())                 # device->host read of the step's result
             ev[i + 1].record()
         barrier()
@@ -316,6 +349,15 @@ def run_product(args):
     # ---- head-only figure (precomputed feature maps in), explains the roofline numbers
     head_ms = None
     roof = {}
+    default_stream = torch.cuda.current_stream()
+    if graphed is not None:
+        # the explanatory passes below run eagerly (per-launch CUDA events), on the stream the capture warm-up
+        # used: the parameters' AccumulateGrad nodes live there, any other stream would add a sync per gradient
+        graphed.release()
+        torch.cuda.set_stream(graphed.side)
+        for p in params:
+            p.grad = None
+        step_resident = step_eager
     if rank == 0 or world > 1:
         feats = []
         with torch.no_grad():
@@ -394,6 +436,7 @@ def run_product(args):
             for kid in (_lib.K_ATTN_FWD, _lib.K_ATTN_BWD, _lib.K_TILEGRAD):
                 _lib.prof_read(kid)          # drop the head spans of this pass
 
+    torch.cuda.set_stream(default_stream)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
@@ -424,7 +467,9 @@ def run_product(args):
                                      if args.precision == "bf16" else "fp32 torchvision/cuDNN, untouched",
                                      "head": ("tcgen05 GEMMs: bf16 on backbone features, tf32 elsewhere; fp32 state, softmax and gates"
                                               if args.precision == "bf16" else "fp32 CUDA-core kernels") + " (libv2f_b200.so)"},
-                       "l2": "inputs larger than L2: two alternating batches, 137 MB of images each"},
+                       "l2": "inputs larger than L2: two alternating batches, 137 MB of images each",
+                       "execution": ("whole step (fwd + loss + bwd) replayed from one CUDA graph, graphs.GraphedTrainStep"
+                                     if use_graph else "eager launches")},
             "e2e": {"value": total / (ms_e2e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "gpu_launches_per_step": launches / args.steps,
@@ -451,6 +496,7 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--ref-batch", type=int, default=8, help="items per step of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="time the eager loop instead of the CUDA-graph replay")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -134,6 +134,10 @@ typedef struct v2f_decode_params {
   /* optional scratch that enables the streaming (TMA-staged, 148-way balanced) attention kernels:
    * N * (ceil(Li/8)+ceil(Lt/8)) * (2E+2) floats.  NULL selects the simple per-(row,modality) kernels. */
   float *attn_ws;
+  /* optional: the teacher-forcing bits in DEVICE memory (one unsigned, same layout as tf_mask).  When non-NULL
+   * (and y != NULL) the kernels read it at run time instead of the immediate, so a captured CUDA graph of the
+   * step can be replayed with a fresh draw (graphs.GraphedTrainStep).                                        */
+  const unsigned* tf_mask_dev;
 } v2f_decode_params;
 
 int v2f_decode_fwd(const v2f_decode_params* p, void* stream);

@@ -114,3 +114,54 @@ def test_streaming_attention_equals_simple_kernels():
             Fv.STREAM_ATTENTION = True
     for a, b in zip(res[True], res[False]):
         assert float((a - b).abs().max()) <= 2e-5 * float(b.abs().max()) + 1e-9
+
+
+@pytest.mark.parametrize("model", ["CrossAttnRNN210", "CrossAttnRNNDemand"])
+def test_cuda_graph_replay_equals_eager_step(model):
+    """graphs.GraphedTrainStep: captured forward+loss+backward, replayed with fresh batches and fresh
+    teacher-forcing draws, equals the eager training_step/backward (eval-mode dropout, same host RNG state)."""
+    import torch.nn as nn
+    import visuelle2_multimodal_fusion_b200.synth as synth
+    import visuelle2_multimodal_fusion_b200.models.modules as mods
+    from visuelle2_multimodal_fusion_b200.graphs import GraphedTrainStep
+    from visuelle2_multimodal_fusion_b200.models import CrossAttnRNN210, CrossAttnRNNDemand
+    orig = mods.resnet101_trunk
+    mods.resnet101_trunk = lambda: nn.Identity()
+    try:
+        torch.manual_seed(0)
+        cat_d, col_d, fab_d = synth.label_dicts()
+        if model == "CrossAttnRNN210":
+            m = CrossAttnRNN210.CrossAttnRNN(64, 64, 64, cat_d, col_d, fab_d, synth.STORE_N, 3, out_len=10)
+        else:
+            m = CrossAttnRNNDemand.CrossAttnRNN(64, 64, 3, 64, cat_d, col_d, fab_d, synth.STORE_N, True, True, True,
+                                                True, out_len=12, use_teacher_forcing=True)
+    finally:
+        mods.resnet101_trunk = orig
+    m = m.cuda().eval()
+    m.use_teacher_forcing = True
+    demand = model == "CrossAttnRNNDemand"
+
+    def batch(seed):
+        data, feat = synth.make_batch(16, out_len=10, demand=demand, seed=seed, feat_hw=4)
+        return tuple(t.cuda() for t in data), feat.cuda()
+
+    step = GraphedTrainStep(m, batch(1))
+    got = []
+    for seed in (2, 3, 4):
+        torch.manual_seed(100 + seed)
+        loss = step(batch(seed))
+        got.append((loss.detach().clone(), {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None}))
+    step.release()
+    for (gl, gg), seed in zip(got, (2, 3, 4)):
+        torch.manual_seed(100 + seed)
+        for p in m.parameters():
+            p.grad = None
+        loss = m.training_step(batch(seed), 0)
+        loss.backward()
+        assert float((loss - gl).abs()) <= 1e-6 * float(loss.abs()) + 1e-9
+        for k, p in m.named_parameters():
+            if p.grad is None:
+                assert k not in gg
+                continue
+            d = float((p.grad - gg[k]).abs().max())
+            assert d <= 1e-5 * float(p.grad.abs().max()) + 1e-9, (k, d)

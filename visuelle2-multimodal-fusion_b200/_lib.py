@@ -10,7 +10,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libv2f_b200.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 _lib = None
 
@@ -33,7 +33,7 @@ class DecodeParams(ctypes.Structure):
              "dWcat", "dbcat", "dw_att", "db_tl", "dWe_mm", "dW_me", "db_me", "dW_ihc", "dw_x",
              "db_ih", "dw_fc", "db_fc", "WcatT", "W_ihcT", "W_meT", "We_mmT", "ws"]
     _fields_ = ([(n, c_int) for n in _INTS] + [("tf_mask", ctypes.c_uint), ("precision", c_int)] +
-                [(n, c_vp) for n in _PTRS] + [("ws_floats", c_ll), ("attn_ws", c_vp)])
+                [(n, c_vp) for n in _PTRS] + [("ws_floats", c_ll), ("attn_ws", c_vp), ("tf_mask_dev", c_vp)])
 
 
 def _declare(lib):

@@ -377,6 +377,7 @@ mm_bwd_kernel(MmBwdArgs a) {
 // GRU gates + decoder_fc + teacher-forcing select.  Row-local.
 struct GateArgs {
   int N, H, T, t, ldS, goff, forced;
+  const unsigned* mask_dev;   // optional device-resident teacher-forcing mask (overrides ``forced``)
   const float* GI;      // [N,3H] = ctx W_ihc^T + b_ih
   const float* S;       // this step; gh at column goff (includes b_hh)
   const float* hprev;   // [N,H]
@@ -413,12 +414,14 @@ gates_fwd_kernel(GateArgs a) {
   if (tid == 0) {
     const float yh = part[0] + a.b_fc[0];
     a.yhat[(long long)n * a.T + a.t] = yh;
-    a.xnext[n] = (a.forced && a.y) ? a.y[(long long)n * a.T + a.t] : yh;
+    const int forced = a.mask_dev ? (int)((*a.mask_dev >> a.t) & 1u) : a.forced;
+    a.xnext[n] = (forced && a.y) ? a.y[(long long)n * a.T + a.t] : yh;
   }
 }
 
 struct GateBwdArgs {
   int N, H, T, t, ldS, goff, forced;   // forced: x_{t+1} was y[:,t] (yhat_t did not feed forward)
+  const unsigned* mask_dev;            // optional device-resident mask (overrides ``forced`` for t < T-1)
   const float *RZN, *S, *hprev, *w_x, *w_fc, *dY;
   float* dh;      // [N,H] in: dL/dh_{t+1}; out: direct part of dL/dh_t
   float* dxn;     // [N] in: dL/dx_{t+1}; out: dL/dx_t
@@ -431,7 +434,8 @@ __global__ void __launch_bounds__(256)
 gates_bwd_kernel(GateBwdArgs a) {
   __shared__ float red[32];
   const int n = blockIdx.x, H = a.H, tid = threadIdx.x;
-  const float dyh = a.dY[(long long)n * a.T + a.t] + (a.forced ? 0.f : a.dxn[n]);
+  const int forced = (a.mask_dev && a.t < a.T - 1) ? (int)((*a.mask_dev >> a.t) & 1u) : a.forced;
+  const float dyh = a.dY[(long long)n * a.T + a.t] + (forced ? 0.f : a.dxn[n]);
   const float* rzn = a.RZN + (long long)n * 3 * H;
   const float* gh = a.S + (long long)n * a.ldS + a.goff;
   float part[1] = {0.f};
@@ -646,7 +650,7 @@ extern "C" int v2f_decode_fwd(const v2f_decode_params* p, void* st) {
     NT(N, E, E, U, E, p->W_me, E, CTX, E, p->b_me, 0.f);
     if (gru) {
       NT(N, 3 * H, E, CTX, E, p->W_ihc, E, p->GI, 3 * H, p->b_ih, 0.f);
-      GateArgs g{N, H, T, t, ldS, 3 * E, (int)((p->tf_mask >> t) & 1u), p->GI, S, h,
+      GateArgs g{N, H, T, t, ldS, 3 * E, (int)((p->tf_mask >> t) & 1u), p->y ? p->tf_mask_dev : nullptr, p->GI, S, h,
                  p->xin + (long long)t * N, p->w_x, p->w_fc, p->b_fc, p->y,
                  p->RZN + (long long)t * N * 3 * H, p->h_all + (long long)(t + 1) * N * H, p->yhat,
                  p->xin + (long long)(t + 1) * N};
@@ -693,7 +697,8 @@ extern "C" int v2f_decode_bwd(const v2f_decode_params* p, void* st) {
     if (gru) {
       // forced flag of THIS step's output: bit t says x_{t+1} = y[:,t]; the last step feeds nothing
       const int forced = (t == T - 1) ? 1 : (int)((p->tf_mask >> t) & 1u);
-      GateBwdArgs g{N, H, T, t, ldS, 3 * E, forced, p->RZN + (long long)t * N * 3 * H, S, h, p->w_x,
+      GateBwdArgs g{N, H, T, t, ldS, 3 * E, forced, p->y ? p->tf_mask_dev : nullptr,
+                    p->RZN + (long long)t * N * 3 * H, S, h, p->w_x,
                     p->w_fc, p->dY, p->dh, p->dxn, p->DGI + (long long)t * N * 3 * H, DS,
                     p->DYH + (long long)t * N};
       gates_bwd_kernel<<<N, 256, 0, s>>>(g);

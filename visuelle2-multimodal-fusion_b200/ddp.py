@@ -29,7 +29,7 @@ def shard_batch(batch, rank, world):
 
 
 class GradReducer:
-    def __init__(self, module, bucket_bytes=25 << 20, group=None):
+    def __init__(self, module, bucket_bytes=25 << 20, group=None, hooks=True):
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         params = [p for p in module.parameters() if p.requires_grad]
@@ -49,7 +49,9 @@ class GradReducer:
         self.cuda = any(p.is_cuda for p in params)
         self.stream = torch.cuda.Stream() if self.cuda else None
         self._reset()
-        self.hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in params]
+        # hooks=False: no overlap with backward; call reduce_now() after the step (CUDA-graph replay, where the
+        # backward is one opaque launch and the hooks would only fire at capture time)
+        self.hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in params] if hooks else []
 
     def _reset(self):
         self.pending = [len(b) for b in self.buckets]
@@ -102,6 +104,14 @@ class GradReducer:
             if self.cuda:
                 torch.cuda.current_stream().wait_stream(self.stream)
         self._reset()
+
+    def reduce_now(self):
+        """All-reduce every bucket now (gradients already complete), then write the mean back."""
+        if self.world > 1:
+            for i in range(len(self.buckets)):
+                if not self.launched[i]:
+                    self._launch(i)
+        self.finish()
 
     def remove(self):
         for h in self.hooks:

@@ -507,6 +507,9 @@ class _Decode(torch.autograd.Function):
         full = (mod_mask & 0b1010) == 0b1010
         p = DecodeParams()
         p.N, p.B, p.W, p.E, p.H, p.Li, p.Lt, p.T = N, B, W, E, H, Li, Lt, T
+        tf_dev = tf_mask if torch.is_tensor(tf_mask) else None      # device-resident bits (CUDA-graph replay)
+        if tf_dev is not None:
+            tf_mask = 0
         p.variant, p.mod_mask, p.tf_mask = variant, mod_mask, tf_mask if y is not None else 0
         prec = 1 if (_tc() and E % 4 == 0 and H % 4 == 0) else 0
         p.precision = prec
@@ -527,9 +530,10 @@ class _Decode(torch.autograd.Function):
             keep["attn_ws"] = _f32(N * ((Li + 7) // 8 + (Lt + 7) // 8) * (2 * E + 2), device=dev)
         for k, v in keep.items():
             setattr(p, k, ptr(v, allow_none=True))
+        p.tf_mask_dev = ptr(tf_dev, torch.int32, allow_none=True)
         check(_lib.lib().v2f_decode_fwd(ctypes.byref(p), stream()), "v2f_decode_fwd")
         ctx.keep, ctx.dims = keep, (variant, W, T, mod_mask, N, B, E, H, Li, Lt, G)
-        ctx.tf_mask, ctx.prec = p.tf_mask, prec
+        ctx.tf_mask, ctx.prec, ctx.tf_dev = p.tf_mask, prec, tf_dev
         yhat, a_img, a_mm = keep["yhat"], keep["alpha_img"], keep["alpha_mm"]
         ctx.mark_non_differentiable(a_img, a_mm)
         return yhat, a_img, a_mm
@@ -575,6 +579,7 @@ class _Decode(torch.autograd.Function):
             setattr(p, k, ptr(v, allow_none=True))
         for k, v in g.items():
             setattr(p, k, ptr(v, allow_none=True))
+        p.tf_mask_dev = ptr(ctx.tf_dev, torch.int32, allow_none=True)
         check(_lib.lib().v2f_decode_bwd(ctypes.byref(p), stream()), "v2f_decode_bwd")
         dWcat, dw_att = g["dWcat"], g["dw_att"]
         zero1 = dWcat.new_zeros(1)

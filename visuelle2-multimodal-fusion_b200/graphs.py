@@ -1,0 +1,91 @@
+"""Whole-step CUDA graph: forward + loss + backward of a drop-in module's ``training_step`` captured once
+and replayed per batch.
+
+The step is ~2 900 kernel launches (torchvision/cuDNN trunk + libv2f_b200) whose host-side issue time
+(~27 ms) is close to their 33 ms of GPU time, so any hiccup of the launching thread stalls the GPU.
+Captured into one graph the host cost per step is a few copies and one ``cudaGraphLaunch``.
+
+What makes the step capturable:
+  * every kernel of libv2f_b200 is launched on the caller's current stream with caller-owned buffers
+    (include/v2f.h), so torch's capture sees them like its own kernels; the cooperative persistent-GRU
+    launch is a capturable kernel node;
+  * dropout masks come from torch's CUDA generator, which is graph-safe (offset advanced per replay);
+  * the teacher-forcing decision of CrossAttnRNN210/Demand is drawn on the HOST in the reference
+    (models/CrossAttnRNN210.py:216-217); here the T bits live in a device word (``tf_mask_dev`` of
+    ``v2f_decode_params``) that is refreshed before each replay with the same host draws in the same order.
+Gradients are left in ``p.grad`` (static storage): run the optimizer / ``ddp.GradReducer.reduce_now``
+after the call.
+"""
+import torch
+
+
+def _tree_map(fn, obj):
+    if torch.is_tensor(obj):
+        return fn(obj)
+    if isinstance(obj, (list, tuple)):
+        return type(obj)(_tree_map(fn, o) for o in obj)
+    if isinstance(obj, dict):
+        return {k: _tree_map(fn, v) for k, v in obj.items()}
+    return obj
+
+
+def _tree_copy(dst, src):
+    if torch.is_tensor(dst):
+        dst.copy_(src, non_blocking=True)
+    elif isinstance(dst, (list, tuple)):
+        for d, s in zip(dst, src):
+            _tree_copy(d, s)
+    elif isinstance(dst, dict):
+        for k in dst:
+            _tree_copy(dst[k], src[k])
+
+
+class GraphedTrainStep:
+    """``step = GraphedTrainStep(model, example_batch); loss = step(batch)`` -- same arithmetic as
+    ``loss = model.training_step(batch, i); loss.backward()`` with gradients in ``p.grad``."""
+
+    def __init__(self, model, example_batch, warmup=3):
+        self.model = model
+        dev = next(model.parameters()).device
+        self.device = dev
+        self.static_batch = _tree_map(lambda t: t.to(dev, copy=True), example_batch)
+        self.has_tf = hasattr(model, "draw_tf_mask")
+        if self.has_tf:
+            model._tf_mask_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+            self._tf_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self.params = [p for p in model.parameters() if p.requires_grad]
+        side = self.side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for i in range(warmup):                       # lazy initialisations happen outside the capture
+                self._refresh_tf()
+                loss = model.training_step(self.static_batch, i)
+                loss.backward()
+                for p in self.params:
+                    p.grad = None
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        from . import _lib
+        l0 = _lib.launch_count()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph, stream=side):     # same stream as the warm-up: no AccumulateGrad stream mismatch
+            self.static_loss = model.training_step(self.static_batch, 0)
+            self.static_loss.backward()
+        self.launches_per_replay = _lib.launch_count() - l0   # libv2f_b200 kernels inside one replay
+
+    def _refresh_tf(self):
+        if self.has_tf:
+            y = self.static_batch[0][1] if not isinstance(self.static_batch[0], dict) else None
+            self._tf_host[0] = self.model.draw_tf_mask(y is not None) & 0x7FFFFFFF
+            self.model._tf_mask_dev.copy_(self._tf_host, non_blocking=True)
+
+    def __call__(self, batch):
+        _tree_copy(self.static_batch, batch)              # device->device (or pinned host->device) into the graph's inputs
+        self._refresh_tf()
+        self.graph.replay()
+        return self.static_loss
+
+    def release(self):
+        """Back to eager: the module draws its teacher-forcing bits on the host again."""
+        if self.has_tf:
+            self.model._tf_mask_dev = None

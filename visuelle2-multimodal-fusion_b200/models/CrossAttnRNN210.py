@@ -45,6 +45,14 @@ class CrossAttnRNN(LightningBase):
         self.decoder_fc = nn.Linear(hidden_dim, 1)
 
     precision = "fp32"     # "bf16": tcgen05 tensor-core GEMMs (2e-2 contract), see functional.set_precision
+    _tf_mask_dev = None    # int32[1] CUDA tensor when the step is replayed from a CUDA graph
+
+    def draw_tf_mask(self, has_y=True):
+        """The reference's host draws: ``torch.rand(1) < ratio`` once per step, only when teacher forcing is on
+        and targets are given (models/CrossAttnRNN210.py:216-217), packed into a bit mask."""
+        if self.use_teacher_forcing and has_y:
+            return draw_teacher_forcing(self.out_len, self.teacher_forcing_ratio)
+        return 0
 
     def forward(self, X, y, categories, colors, fabrics, stores, temporal_features, gtrends, images):
         with Fv.precision(self.precision):
@@ -56,9 +64,8 @@ class CrossAttnRNN(LightningBase):
                               images, by_proj=False)
         h0 = sales_state(self, X)
         x0 = X[:, -1, 0]
-        tf_mask = 0
-        if self.use_teacher_forcing and y is not None:
-            tf_mask = draw_teacher_forcing(self.out_len, self.teacher_forcing_ratio)
+        # graphs.GraphedTrainStep keeps the bits in device memory (drawn by it, in the same host order)
+        tf_mask = self._tf_mask_dev if self._tf_mask_dev is not None else self.draw_tf_mask(y is not None)
         yhat, _, _ = run_decoder(self, Fv.VARIANT_210, num_windows, self.out_len, tf_mask, 0b1111, tiles,
                                  h0, x0, y, self.decoder_gru, self.decoder_fc)
         return yhat, None

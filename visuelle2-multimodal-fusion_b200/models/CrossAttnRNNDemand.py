@@ -58,6 +58,16 @@ class CrossAttnRNN(LightningBase):
         self.save_hyperparameters()
 
     precision = "fp32"     # "bf16": tcgen05 tensor-core GEMMs (2e-2 contract), see functional.set_precision
+    _tf_mask_dev = None    # int32[1] CUDA tensor when the step is replayed from a CUDA graph
+
+    def draw_tf_mask(self, has_y=True):
+        """One host draw per step, always -- even in eval (reference :343-345); the bits are only honoured when
+        teacher forcing is on."""
+        draws = 0
+        for t in range(self.out_len):
+            if bool(torch.rand(1) < self.teacher_forcing_ratio):
+                draws |= 1 << t
+        return draws if (self.use_teacher_forcing and has_y) else 0
 
     def forward(self, ts, categories, colors, fabrics, stores, temporal_features, gtrends, images):
         with Fv.precision(self.precision):
@@ -68,12 +78,7 @@ class CrossAttnRNN(LightningBase):
         tiles = encode_static(self, categories, colors, fabrics, stores, temporal_features, gtrends,
                               images, by_proj=True, use_trends=bool(self.use_trends))
         T = self.out_len
-        # one host draw per step, always (reference :343-345); only honoured when teacher forcing is on
-        draws = 0
-        for t in range(T):
-            if bool(torch.rand(1) < self.teacher_forcing_ratio):
-                draws |= 1 << t
-        tf_mask = draws if (self.use_teacher_forcing and ts is not None) else 0
+        tf_mask = self._tf_mask_dev if self._tf_mask_dev is not None else self.draw_tf_mask(ts is not None)
         mod_mask = 1 | (2 if self.use_img else 0) | (4 if self.use_att else 0) | (8 if self.use_trends else 0)
         h0 = ts.new_zeros(bs, self.hidden_dim, dtype=torch.float32)
         x0 = ts.new_zeros(bs, dtype=torch.float32)
