@@ -47,6 +47,8 @@ class GradReducer:
             self.buckets.append(cur)
         self.bucket_of = {id(p): i for i, b in enumerate(self.buckets) for p in b}
         self.cuda = any(p.is_cuda for p in params)
+        # NCCL averages inside the collective; gloo (CPU tests) only sums
+        self.avg_in_collective = self.cuda and dist.is_initialized() and dist.get_backend(group) == "nccl"
         self.stream = torch.cuda.Stream() if self.cuda else None
         self._reset()
         # hooks=False: no overlap with backward; call reduce_now() after the step (CUDA-graph replay, where the
@@ -82,7 +84,8 @@ class GradReducer:
             if self.cuda:
                 for p in ps:
                     p.grad.record_stream(self.stream)
-            h = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+            op = dist.ReduceOp.AVG if self.avg_in_collective else dist.ReduceOp.SUM
+            h = dist.all_reduce(flat, op=op, group=self.group, async_op=True)
             self.work.append((h, flat, ps))
 
     def finish(self):
@@ -95,12 +98,14 @@ class GradReducer:
             with (torch.cuda.stream(self.stream) if self.cuda else contextlib.nullcontext()):
                 for h, flat, ps in self.work:
                     h.wait()                      # side stream waits for the collective
-                    flat.div_(self.world)
-                    off = 0
+                    if not self.avg_in_collective:
+                        flat.div_(self.world)
+                    views, off = [], 0
                     for p in ps:
                         n = p.numel()
-                        p.grad.copy_(flat[off:off + n].view_as(p.grad))
+                        views.append(flat[off:off + n].view_as(p.grad))
                         off += n
+                    torch._foreach_copy_([p.grad for p in ps], views)      # one multi-tensor launch per bucket
             if self.cuda:
                 torch.cuda.current_stream().wait_stream(self.stream)
         self._reset()
