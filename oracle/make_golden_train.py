@@ -1,0 +1,97 @@
+"""Training-trajectory fixtures from the UNMODIFIED reference (build container only).  TEST INFRASTRUCTURE ONLY.
+
+BASELINE.json asks for forecast-metric parity: WAPE/MAE of a training run within 0.1 points of the reference's.
+The dataset is not available, so the run is K optimisation steps on a fixed set of seeded synthetic batches:
+the reference module (backbone stripped: the batches carry feature maps), its own ``training_step`` /
+``configure_optimizers`` (Adafactor, relative step) / ``validation_step`` + the metric formulas of
+``validation_epoch_end``; every dropout p = 0 so both sides see the same arithmetic, host teacher-forcing draws
+seeded per step.  The fixture stores the initial state, the batches, the loss of every step and the validation
+MAE / WAPE; tests/test_gpu_training_parity.py replays it on the CUDA path.
+
+Usage:  python -m oracle.make_golden_train
+"""
+import copy
+import os
+import sys
+
+import torch
+import torch.nn.functional as F
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import refshim  # noqa: E402
+from oracle.make_golden import GOLDEN_DIR  # noqa: E402
+
+
+def metrics(gt, pred, abs_den):
+    """val_mae / val_wWAPE as in validation_epoch_end (CrossAttnRNN210.py:262-286; GTM_Visuelle2.py:289-312)."""
+    gt, pred = gt.reshape(-1), pred.reshape(-1)
+    mae = F.l1_loss(gt * 53, pred * 53)
+    den = torch.sum(torch.abs(gt * 53)) if abs_den else torch.sum(gt * 53)
+    return float(mae), float(100 * torch.sum(torch.abs((gt - pred) * 53)) / den)
+
+
+def run_training(model, batches, val_batch, steps, opt=None, log=None):
+    """The loop both sides run (the product test imports this function)."""
+    opt = opt or model.configure_optimizers()[0]
+    losses = []
+    model.train()
+    if hasattr(model, "on_train_epoch_start"):
+        model.on_train_epoch_start()
+    for s in range(steps):
+        torch.manual_seed(1000 + s)                      # host teacher-forcing draws of this step
+        loss = model.training_step(batches[s % len(batches)], s)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        losses.append(float(loss.detach()))
+    model.eval()
+    if hasattr(model, "on_validation_epoch_start"):
+        model.on_validation_epoch_start()
+    torch.manual_seed(5000)
+    with torch.no_grad():
+        y, f = model.validation_step(val_batch, 0)
+    return losses, y.detach().cpu(), f.detach().cpu()
+
+
+def case(kind, steps=60, B=16, nb=4, E=32, H=32, hw=2, seed=51):
+    import visuelle2_multimodal_fusion_b200.synth as synth
+    cat_d, col_d, fab_d = synth.label_dicts()
+    torch.manual_seed(seed)
+    if kind == "rnn210":
+        mod = refshim.load_reference_module("CrossAttnRNN210")
+        m = mod.CrossAttnRNN(E, E, H, cat_d, col_d, fab_d, synth.STORE_N, 3, out_len=10)
+        demand, out_len, abs_den = False, 10, True
+    elif kind == "demand":
+        mod = refshim.load_reference_module("CrossAttnRNNDemand")
+        m = mod.CrossAttnRNN(E, E, 3, H, cat_d, col_d, fab_d, synth.STORE_N, True, True, True, True, out_len=12)
+        demand, out_len, abs_den = True, 10, True
+    else:
+        from oracle.make_golden_gtm import build_reference
+        m = build_reference(kind, E, 2 * H, 12, 4, False, "image")
+        demand, out_len, abs_den = True, 10, False
+    if kind in ("rnn210", "demand"):
+        refshim.strip_backbone(m)
+    refshim.zero_dropout(m)
+
+    def mk(s):
+        data, feat = synth.make_batch(B, out_len=out_len, demand=demand, seed=s, feat_hw=hw)
+        return data, feat
+
+    batches = [mk(seed + 1 + i) for i in range(nb)]
+    val = mk(seed + 100)
+    state0 = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    losses, y, f = run_training(m, batches, val, steps)
+    mae, wape = metrics(y, f, abs_den)
+    final = {k: v.detach().clone() for k, v in m.state_dict().items() if v.is_floating_point() and v.numel() <= 4096}
+    return dict(kind=kind, cfg=dict(E=E, H=H, B=B, steps=steps, seed=seed, hw=hw, abs_den=abs_den), state=state0,
+                batches=batches, val=val, losses=losses, val_y=y, val_forecast=f, mae=mae, wape=wape, final=final)
+
+
+if __name__ == "__main__":
+    os.makedirs(GOLDEN_DIR, exist_ok=True)
+    for kind in (sys.argv[1:] or ["rnn210", "demand", "gtm", "v4"]):
+        blob = case(kind)
+        path = os.path.join(GOLDEN_DIR, f"train_{kind}.pt")
+        torch.save(blob, path)
+        print(f"{path}: loss {blob['losses'][0]:.6f} -> {blob['losses'][-1]:.6f}  MAE {blob['mae']:.4f}  WAPE {blob['wape']:.3f}  "
+              f"({os.path.getsize(path) / 1e6:.1f} MB)")
