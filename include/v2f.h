@@ -273,7 +273,9 @@ int v2f_meanpool_bwd(int B, int L, int C, const float* dout, int layout, int kin
  *   updated with `momentum` (unbiased variance) unless run_mean is NULL; else running statistics.
  * x, res, y, dy, dz, dx: bf16 [R,C].  save_mean/save_rstd [C]; scale_shift [2,C] scratch;
  * part: v2f_bn2d_blocks(R,C)*2*C floats of scratch; coef [3,C] scratch.
- * Backward: dz = dy*[y>0] (relu) is what a residual branch receives; pass dz != NULL to have it
+ * Backward: dy2 (optional) is a second upstream gradient -- the output fed two consumers (the next
+ * block's conv1 and its residual add) -- summed on the fly instead of by a separate kernel (needs dz).
+ * dz = (dy+dy2)*[y>0] (relu) is what a residual branch receives; pass dz != NULL to have it
  * stored (bf16 [R,C]).  dx = gamma*rstd*(dz - mean(dz) - xhat*mean(dz*xhat)) (training) or
  * gamma*rstd*dz (eval); dgamma = sum dz*xhat, dbeta = sum dz.                                   */
 int v2f_bn2d_blocks(long long R, int C);
@@ -281,7 +283,7 @@ int v2f_bn2d_act_fwd(long long R, int C, const void* x, const void* res, const f
                      const float* beta, float* run_mean, float* run_var, int training, float momentum,
                      float eps, int relu, void* y, float* save_mean, float* save_rstd,
                      float* scale_shift, float* part, void* stream);
-int v2f_bn2d_act_bwd(long long R, int C, const void* dy, const void* x, const void* y,
+int v2f_bn2d_act_bwd(long long R, int C, const void* dy, const void* dy2, const void* x, const void* y,
                      const float* gamma, const float* save_mean, const float* save_rstd, int training,
                      int relu, void* dz, void* dx, float* dgamma, float* dbeta, float* coef, float* part,
                      void* stream);

@@ -164,3 +164,38 @@ def test_fused_stem_matches_torch(N, H, W, training):
     assert _rel(y, yr) < 8e-3
     assert _rel(bn.running_mean, ref.running_mean) < 1e-5 and _rel(bn.running_var, ref.running_var) < 1e-5
     assert int(bn.num_batches_tracked) == int(ref.num_batches_tracked)
+
+
+@pytest.mark.parametrize("res", [False, True])
+def test_bn_act_fork_sums_the_two_consumer_gradients(res):
+    """bn_act_fork returns one storage twice; the two upstream gradients are summed inside the backward sweep."""
+    from visuelle2_multimodal_fusion_b200 import trunk
+    torch.manual_seed(3)
+    N, C, H, W = 6, 256, 7, 5
+    bn = nn.BatchNorm2d(C).cuda().train()
+    mk = lambda: torch.randn(N, C, H, W, device="cuda").bfloat16().contiguous(memory_format=CL)
+    x = mk().requires_grad_(True)
+    r = mk().requires_grad_(True) if res else None
+    g1, g2 = mk(), mk()
+    y1, y2 = trunk.bn_act_fork(x, bn, relu=True, res=r)
+    assert y1.data_ptr() == y2.data_ptr()
+    (y1.float() * g1.float()).sum().backward(retain_graph=True)          # only the first edge
+    only_first = x.grad.clone()
+    x.grad = None
+    bn.zero_grad()
+    if res:
+        r.grad = None
+    ((y1.float() * g1.float()).sum() + (y2.float() * g2.float()).sum()).backward()
+    fork = [x.grad.clone(), bn.weight.grad.clone(), bn.bias.grad.clone()] + ([r.grad.clone()] if res else [])
+    x2 = x.detach().clone().requires_grad_(True)
+    r2 = r.detach().clone().requires_grad_(True) if res else None
+    bn.zero_grad()
+    y = trunk.bn_act(x2, bn, relu=True, res=r2)
+    y.backward((g1.float() + g2.float()).bfloat16())
+    plain = [x2.grad, bn.weight.grad, bn.bias.grad] + ([r2.grad] if res else [])
+    for a, b in zip(fork, plain):
+        assert _rel(a, b) < 1.2e-2                     # bf16 rounding of (g1+g2) happens at a different point
+    y.backward(g1, inputs=[x2]) if False else None
+    x3 = x.detach().clone().requires_grad_(True)
+    trunk.bn_act(x3, bn, relu=True, res=r.detach() if res else None).backward(g1)
+    assert _rel(only_first, x3.grad) < 1e-6

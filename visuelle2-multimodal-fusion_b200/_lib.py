@@ -92,8 +92,8 @@ def _declare(lib):
     lib.v2f_bn2d_blocks.argtypes = [c_ll, c_int]
     lib.v2f_bn2d_act_fwd.argtypes = [c_ll, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_float, c_float, c_int,
                                      c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]
-    lib.v2f_bn2d_act_bwd.argtypes = [c_ll, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_vp,
-                                     c_vp, c_vp, c_vp, c_vp]
+    lib.v2f_bn2d_act_bwd.argtypes = [c_ll, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_vp,
+                                     c_vp, c_vp, c_vp, c_vp, c_vp]
     lib.v2f_bn2d_relu_maxpool_fwd.argtypes = [c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_float,
                                               c_float, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]
     for name in ("v2f_bn2d_blocks", "v2f_bn2d_act_fwd", "v2f_bn2d_act_bwd", "v2f_bn2d_relu_maxpool_fwd"):

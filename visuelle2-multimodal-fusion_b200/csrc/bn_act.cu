@@ -250,10 +250,12 @@ bn_apply_kernel(long long R, int C, const uint4* __restrict__ x, const uint4* __
 // ---------------------------------------------------------------- backward: reduce
 // dz = dy * [y > 0] (RELU) ; part[blk][0][c] = sum dz, part[blk][1][c] = sum dz * xhat.
 // WRITE_DZ: dz is also stored (the residual branch receives it as its gradient).
-template <bool RELU, bool WRITE_DZ>
+// ADD2: the output fed two consumers (the next block's conv1 and its residual add); their gradients
+// arrive separately (dy, dy2) and are summed here instead of by a separate elementwise kernel.
+template <bool RELU, bool WRITE_DZ, bool ADD2>
 __global__ void __launch_bounds__(BN_THREADS)
-bn_bwd_reduce_kernel(long long R, int C, const uint4* __restrict__ dy, const uint4* __restrict__ x,
-                     const uint4* __restrict__ y, const float* __restrict__ mean,
+bn_bwd_reduce_kernel(long long R, int C, const uint4* __restrict__ dy, const uint4* __restrict__ dy2,
+                     const uint4* __restrict__ x, const uint4* __restrict__ y, const float* __restrict__ mean,
                      const float* __restrict__ rstd, uint4* __restrict__ dz, float* __restrict__ part) {
   extern __shared__ float sm[];
   const Geo g = make_geo(C);
@@ -271,21 +273,24 @@ bn_bwd_reduce_kernel(long long R, int C, const uint4* __restrict__ dy, const uin
       const long long stride = (long long)gridDim.x * g.RB;
       long long r = (long long)blockIdx.x * g.RB + roff;
       for (; r + stride < R; r += 2 * stride) {
-        uint4 ud[2], ux[2], uy[2];
+        uint4 ud[2], ue[2], ux[2], uy[2];
 #pragma unroll
         for (int k = 0; k < 2; k++) {
           ud[k] = ldg_stream(dy + (r + k * stride) * g.CV + v);
+          if (ADD2) ue[k] = ldg_stream(dy2 + (r + k * stride) * g.CV + v);
           ux[k] = ldg_stream(x + (r + k * stride) * g.CV + v);
           if (RELU) uy[k] = ldg_stream(y + (r + k * stride) * g.CV + v);
         }
 #pragma unroll
         for (int k = 0; k < 2; k++) {
-          float d[8], xv[8], yv[8];
+          float d[8], e[8], xv[8], yv[8];
           unpack8(ud[k], d);
+          if (ADD2) unpack8(ue[k], e);
           unpack8(ux[k], xv);
           if (RELU) unpack8(uy[k], yv);
 #pragma unroll
           for (int i = 0; i < 8; i++) {
+            if (ADD2) d[i] += e[i];
             if (RELU && !(yv[i] > 0.f)) d[i] = 0.f;
             s[i] += d[i];
             q[i] = fmaf(d[i], (xv[i] - mu[i]) * rs[i], q[i]);
@@ -294,12 +299,14 @@ bn_bwd_reduce_kernel(long long R, int C, const uint4* __restrict__ dy, const uin
         }
       }
       for (; r < R; r += stride) {
-        float d[8], xv[8], yv[8];
+        float d[8], e[8], xv[8], yv[8];
         unpack8(ldg_stream(dy + r * g.CV + v), d);
+        if (ADD2) unpack8(ldg_stream(dy2 + r * g.CV + v), e);
         unpack8(ldg_stream(x + r * g.CV + v), xv);
         if (RELU) unpack8(ldg_stream(y + r * g.CV + v), yv);
 #pragma unroll
         for (int i = 0; i < 8; i++) {
+          if (ADD2) d[i] += e[i];
           if (RELU && !(yv[i] > 0.f)) d[i] = 0.f;
           s[i] += d[i];
           q[i] = fmaf(d[i], (xv[i] - mu[i]) * rs[i], q[i]);
@@ -498,34 +505,42 @@ extern "C" int v2f_bn2d_act_fwd(long long R, int C, const void* x, const void* r
   return V2F_OK;
 }
 
-extern "C" int v2f_bn2d_act_bwd(long long R, int C, const void* dy, const void* x, const void* y,
+extern "C" int v2f_bn2d_act_bwd(long long R, int C, const void* dy, const void* dy2, const void* x, const void* y,
                                 const float* gamma, const float* save_mean, const float* save_rstd,
                                 int training, int relu, void* dz, void* dx, float* dgamma, float* dbeta,
                                 float* coef, float* part, void* st) {
   V2F_REQUIRE(R > 0 && C > 0 && (C & 7) == 0, V2F_ERR_BAD_ARG);
   V2F_REQUIRE(dy && x && gamma && save_mean && save_rstd && dx && dgamma && dbeta && coef && part, V2F_ERR_BAD_ARG);
   V2F_REQUIRE(!relu || y, V2F_ERR_BAD_ARG);
+  V2F_REQUIRE(!dy2 || (dz && aligned16(dy2)), V2F_ERR_BAD_ARG);     // the summed gradient has to be stored
   V2F_REQUIRE(aligned16(dy) && aligned16(x) && aligned16(dx) && (!y || aligned16(y)) && (!dz || aligned16(dz)),
               V2F_ERR_ALIGN);
   cudaStream_t s = (cudaStream_t)st;
   const Geo g = make_geo(C);
   const int nblk = sweep_blocks(R, C);
   const size_t smem = sizeof(float) * (size_t)g.RB * 2 * g.CVB * 8;
-  const uint4 *dyp = (const uint4*)dy, *xp = (const uint4*)x, *yp = (const uint4*)y;
+  const uint4 *dyp = (const uint4*)dy, *dy2p = (const uint4*)dy2, *xp = (const uint4*)x, *yp = (const uint4*)y;
   uint4 *dzp = (uint4*)dz, *dxp = (uint4*)dx;
   const long long tb = R * (long long)C * 2;
   prof_begin(V2F_K_BN_BWD_REDUCE, s);
-  prof_bytes(V2F_K_BN_BWD_REDUCE, tb * (2 + (relu ? 1 : 0) + ((relu && dz) ? 1 : 0)));
-  if (relu && dz) bn_bwd_reduce_kernel<true, true><<<nblk, BN_THREADS, smem, s>>>(R, C, dyp, xp, yp, save_mean, save_rstd, dzp, part);
-  else if (relu) bn_bwd_reduce_kernel<true, false><<<nblk, BN_THREADS, smem, s>>>(R, C, dyp, xp, yp, save_mean, save_rstd, dzp, part);
-  else bn_bwd_reduce_kernel<false, false><<<nblk, BN_THREADS, smem, s>>>(R, C, dyp, xp, yp, save_mean, save_rstd, dzp, part);
+  const bool have_dz = dz && (relu || dy2);
+  prof_bytes(V2F_K_BN_BWD_REDUCE, tb * (2 + (relu ? 1 : 0) + (have_dz ? 1 : 0) + (dy2 ? 1 : 0)));
+#define BN_RED(RELU_, WDZ_, ADD2_) \
+  bn_bwd_reduce_kernel<RELU_, WDZ_, ADD2_><<<nblk, BN_THREADS, smem, s>>>(R, C, dyp, dy2p, xp, yp, save_mean, save_rstd, dzp, part)
+  if (dy2 && relu) BN_RED(true, true, true);
+  else if (dy2) BN_RED(false, true, true);
+  else if (relu && dz) BN_RED(true, true, false);
+  else if (relu) BN_RED(true, false, false);
+  else BN_RED(false, false, false);
+#undef BN_RED
   prof_end(V2F_K_BN_BWD_REDUCE, s);
   V2F_CHECK_LAUNCH();
   bn_bwd_finalize_kernel<<<(C + 31) / 32, dim3(32, FIN_Y), 0, s>>>(R, C, nblk, part, gamma, save_rstd, training, dgamma, dbeta, coef);
   V2F_CHECK_LAUNCH();
   prof_begin(V2F_K_BN_BWD_ELEMT, s);
   prof_bytes(V2F_K_BN_BWD_ELEMT, tb * (3 + ((relu && !dz) ? 1 : 0)));
-  if (relu && dz) bn_bwd_elemt_kernel<true, true><<<nblk, BN_THREADS, 0, s>>>(R, C, (const uint4*)dz, xp, yp, save_mean, save_rstd, coef, dxp);
+  if (have_dz && !relu) bn_bwd_elemt_kernel<false, false><<<nblk, BN_THREADS, 0, s>>>(R, C, (const uint4*)dz, xp, yp, save_mean, save_rstd, coef, dxp);
+  else if (relu && dz) bn_bwd_elemt_kernel<true, true><<<nblk, BN_THREADS, 0, s>>>(R, C, (const uint4*)dz, xp, yp, save_mean, save_rstd, coef, dxp);
   else if (relu) bn_bwd_elemt_kernel<true, false><<<nblk, BN_THREADS, 0, s>>>(R, C, dyp, xp, yp, save_mean, save_rstd, coef, dxp);
   else bn_bwd_elemt_kernel<false, false><<<nblk, BN_THREADS, 0, s>>>(R, C, dyp, xp, yp, save_mean, save_rstd, coef, dxp);
   prof_end(V2F_K_BN_BWD_ELEMT, s);

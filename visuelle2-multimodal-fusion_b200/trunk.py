@@ -73,77 +73,120 @@ def stem(conv, bn, pool, x):
     return y
 
 
+def _bn_forward(ctx, x, res, gamma, beta, bn, relu):
+    if x.dtype != torch.bfloat16 or not x.is_cuda:
+        raise RuntimeError("fused trunk expects bf16 CUDA activations (no CPU / fp32 fallback here)")
+    if not x.is_contiguous(memory_format=_CL):
+        x = x.contiguous(memory_format=_CL)
+    if res is not None and not res.is_contiguous(memory_format=_CL):
+        res = res.contiguous(memory_format=_CL)
+    N, C, H, W = x.shape
+    R = N * H * W
+    dev = x.device
+    use_batch = bn.training or bn.running_mean is None
+    y = torch.empty_like(x)
+    mean, rstd = _f32(C, device=dev), _f32(C, device=dev)
+    ss = _f32(2, C, device=dev)
+    nblk = _lib.lib().v2f_bn2d_blocks(R, C)
+    part = _f32(max(nblk, 1) * 2 * C, device=dev)
+    mom = _count_batch(bn, use_batch, bn.momentum)
+    check(_lib.lib().v2f_bn2d_act_fwd(R, C, x.data_ptr(), res.data_ptr() if res is not None else None,
+                                      ptr(gamma), ptr(beta),
+                                      ptr(bn.running_mean, allow_none=True), ptr(bn.running_var, allow_none=True),
+                                      1 if use_batch else 0, float(mom if mom is not None else 0.0), float(bn.eps),
+                                      1 if relu else 0, y.data_ptr(), ptr(mean), ptr(rstd), ptr(ss), ptr(part),
+                                      stream()), "v2f_bn2d_act_fwd")
+    ctx.save_for_backward(x, y if relu else None, gamma, mean, rstd)
+    ctx.cfg = (R, C, use_batch, relu, res is not None)
+    return y
+
+
+def _as_grad(t):
+    if t.dtype != torch.bfloat16:
+        t = t.to(torch.bfloat16)
+    return t if t.is_contiguous(memory_format=_CL) else t.contiguous(memory_format=_CL)
+
+
+def _bn_backward(ctx, dy, dy2):
+    x, y, gamma, mean, rstd = ctx.saved_tensors
+    R, C, use_batch, relu, has_res = ctx.cfg
+    if dy is None:                        # only the second consumer produced a gradient
+        dy, dy2 = dy2, None
+    dy = _as_grad(dy)
+    dy2 = _as_grad(dy2) if dy2 is not None else None
+    dev = dy.device
+    need_res = has_res and ctx.needs_input_grad[1]
+    need_dz = dy2 is not None or (need_res and relu)
+    dz = torch.empty_like(x) if need_dz else None
+    dx = torch.empty_like(x)
+    dgamma, dbeta = _f32(C, device=dev), _f32(C, device=dev)
+    coef = _f32(3, C, device=dev)
+    nblk = _lib.lib().v2f_bn2d_blocks(R, C)
+    part = _f32(nblk * 2 * C, device=dev)
+    check(_lib.lib().v2f_bn2d_act_bwd(R, C, dy.data_ptr(), dy2.data_ptr() if dy2 is not None else None, x.data_ptr(),
+                                      y.data_ptr() if relu else None, ptr(gamma), ptr(mean), ptr(rstd),
+                                      1 if use_batch else 0, 1 if relu else 0,
+                                      dz.data_ptr() if need_dz else None, dx.data_ptr(), ptr(dgamma), ptr(dbeta),
+                                      ptr(coef), ptr(part), stream()), "v2f_bn2d_act_bwd")
+    dres = None
+    if need_res:
+        dres = dz if need_dz else dy
+    return (dx if ctx.needs_input_grad[0] else None, dres,
+            dgamma if ctx.needs_input_grad[2] else None, dbeta if ctx.needs_input_grad[3] else None, None, None)
+
+
 class _BnAct(torch.autograd.Function):
     """y = act(BatchNorm2d(x) (+ res)) on bf16 channels_last tensors; ``bn`` is the nn.BatchNorm2d whose
     parameters / running statistics are used (and updated in train mode)."""
 
     @staticmethod
     def forward(ctx, x, res, gamma, beta, bn, relu):
-        if x.dtype != torch.bfloat16 or not x.is_cuda:
-            raise RuntimeError("fused trunk expects bf16 CUDA activations (no CPU / fp32 fallback here)")
-        if not x.is_contiguous(memory_format=_CL):
-            x = x.contiguous(memory_format=_CL)
-        if res is not None and not res.is_contiguous(memory_format=_CL):
-            res = res.contiguous(memory_format=_CL)
-        N, C, H, W = x.shape
-        R = N * H * W
-        dev = x.device
-        use_batch = bn.training or bn.running_mean is None
-        y = torch.empty_like(x)
-        mean, rstd = _f32(C, device=dev), _f32(C, device=dev)
-        ss = _f32(2, C, device=dev)
-        nblk = _lib.lib().v2f_bn2d_blocks(R, C)
-        part = _f32(max(nblk, 1) * 2 * C, device=dev)
-        mom = bn.momentum
-        mom = _count_batch(bn, use_batch, mom)
-        check(_lib.lib().v2f_bn2d_act_fwd(R, C, x.data_ptr(), res.data_ptr() if res is not None else None,
-                                          ptr(gamma), ptr(beta),
-                                          ptr(bn.running_mean, allow_none=True), ptr(bn.running_var, allow_none=True),
-                                          1 if use_batch else 0, float(mom if mom is not None else 0.0), float(bn.eps),
-                                          1 if relu else 0, y.data_ptr(), ptr(mean), ptr(rstd), ptr(ss), ptr(part),
-                                          stream()), "v2f_bn2d_act_fwd")
-        ctx.save_for_backward(x, y if relu else None, gamma, mean, rstd)
-        ctx.cfg = (R, C, use_batch, relu, res is not None)
-        return y
+        return _bn_forward(ctx, x, res, gamma, beta, bn, relu)
 
     @staticmethod
     def backward(ctx, dy):
-        x, y, gamma, mean, rstd = ctx.saved_tensors
-        R, C, use_batch, relu, has_res = ctx.cfg
-        if dy.dtype != torch.bfloat16:
-            dy = dy.to(torch.bfloat16)
-        if not dy.is_contiguous(memory_format=_CL):
-            dy = dy.contiguous(memory_format=_CL)
-        dev = dy.device
-        need_dz = has_res and relu and ctx.needs_input_grad[1]
-        dz = torch.empty_like(x) if need_dz else None
-        dx = torch.empty_like(x)
-        dgamma, dbeta = _f32(C, device=dev), _f32(C, device=dev)
-        coef = _f32(3, C, device=dev)
-        nblk = _lib.lib().v2f_bn2d_blocks(R, C)
-        part = _f32(nblk * 2 * C, device=dev)
-        check(_lib.lib().v2f_bn2d_act_bwd(R, C, dy.data_ptr(), x.data_ptr(), y.data_ptr() if relu else None,
-                                          ptr(gamma), ptr(mean), ptr(rstd), 1 if use_batch else 0, 1 if relu else 0,
-                                          dz.data_ptr() if need_dz else None, dx.data_ptr(), ptr(dgamma), ptr(dbeta),
-                                          ptr(coef), ptr(part), stream()), "v2f_bn2d_act_bwd")
-        dres = None
-        if has_res and ctx.needs_input_grad[1]:
-            dres = dz if relu else dy
-        return (dx if ctx.needs_input_grad[0] else None, dres,
-                dgamma if ctx.needs_input_grad[2] else None, dbeta if ctx.needs_input_grad[3] else None, None, None)
+        return _bn_backward(ctx, dy, None)
+
+
+class _BnActFork(torch.autograd.Function):
+    """Same, returning the result twice (two tensors on one storage) for an output with two consumers -- the next
+    block's conv1 and its residual add.  Autograd then hands the two gradients over separately and the backward
+    sweep sums them on the fly, instead of a separate elementwise add over the whole activation."""
+
+    @staticmethod
+    def forward(ctx, x, res, gamma, beta, bn, relu):
+        y = _bn_forward(ctx, x, res, gamma, beta, bn, relu)
+        ctx.set_materialize_grads(False)
+        return y, y.detach()
+
+    @staticmethod
+    def backward(ctx, dy, dy2):
+        if dy is None and dy2 is None:
+            return None, None, None, None, None, None
+        return _bn_backward(ctx, dy, dy2)
 
 
 def bn_act(x, bn, relu=True, res=None):
     return _BnAct.apply(x, res, bn.weight, bn.bias, bn, relu)
 
 
-def _bottleneck(blk, x):
-    """torchvision.models.resnet.Bottleneck.forward with the fused normalisation sweeps."""
+def bn_act_fork(x, bn, relu=True, res=None):
+    """(y, y): one storage, two autograd edges (see _BnActFork)."""
+    return _BnActFork.apply(x, res, bn.weight, bn.bias, bn, relu)
+
+
+def _bottleneck(blk, x, x_res=None, fork=False):
+    """torchvision.models.resnet.Bottleneck.forward with the fused normalisation sweeps.  ``x`` feeds conv1,
+    ``x_res`` (same values; defaults to ``x``) the identity / downsample branch; ``fork``: return the output as a
+    pair for the next block."""
+    x_res = x if x_res is None else x_res
     out = bn_act(blk.conv1(x), blk.bn1, relu=True)
     out = bn_act(blk.conv2(out), blk.bn2, relu=True)
-    identity = x
+    identity = x_res
     if blk.downsample is not None:
-        identity = bn_act(blk.downsample[0](x), blk.downsample[1], relu=False)
+        identity = bn_act(blk.downsample[0](x_res), blk.downsample[1], relu=False)
+    if fork:
+        return bn_act_fork(blk.conv3(out), blk.bn3, relu=True, res=identity)
     return bn_act(blk.conv3(out), blk.bn3, relu=True, res=identity)
 
 
@@ -177,9 +220,13 @@ def forward(cnn, images):
     try:
         with torch.autocast("cuda", dtype=torch.bfloat16):
             x = stem(mods[0], mods[1], mods[3], x)
-            for layer in mods[4:]:
-                for blk in layer:
-                    x = _bottleneck(blk, x)
+            blocks = [blk for layer in mods[4:] for blk in layer]
+            x_res = None
+            for i, blk in enumerate(blocks):
+                if i + 1 < len(blocks):
+                    x, x_res = _bottleneck(blk, x, x_res, fork=True)     # two consumers downstream
+                else:
+                    x = _bottleneck(blk, x, x_res)
         if _pending_counters:
             torch._foreach_add_(_pending_counters, 1)
     finally:
