@@ -383,11 +383,26 @@ def run_product(args):
         timed(step_head, args.steps, "head_only")
         hs = sorted(step_ms["head_only"])
         head_ms = hs[len(hs) // 2] * args.steps        # median step: this eager, launch-bound pass is jitter-prone
-        # ---- roofline pass: CUDA events around every launch of the attention kernels
+        # ---- roofline pass: CUDA events around every launch of the attention kernels.  The eager loop is
+        # launch-bound (the GPU waits for the host between kernels), so an event pair around one launch would
+        # also time the host's issue latency (~5 us on a 16 us kernel).  A spin kernel ahead of the forward and of
+        # the backward lets the host run ahead; the bracketed launches then execute back to back from the queue.
+        lag = int(0.03 * 1.9e9)                  # ~30 ms of GPU spin (cycles)
+
+        def step_head_prof(i):
+            torch.manual_seed(1234 + i)
+            d, _ = resident[i & 1]
+            f = feats[i & 1].clone().requires_grad_(True)
+            torch.cuda._sleep(lag)
+            loss = model.training_step((d, f), i)
+            torch.cuda._sleep(lag)
+            loss.backward()
+            zero()
+
         _lib.prof_enable(True)
         nprof = min(args.steps, 5)
         for i in range(nprof):
-            step_head(i)
+            step_head_prof(i)
         torch.cuda.synchronize()
         _lib.prof_enable(False)
         peak, peak_src = _peaks()
@@ -412,7 +427,8 @@ def run_product(args):
                           "traffic": tj.get(name), "kernel": name, "avg_launch_us": avg_ms * 1e3,
                           "launches_per_step": n / nprof, "algorithmic_bytes_per_launch": bytes_per_launch,
                           "peak_source": peak_src,
-                          "timing": "CUDA events on the launching stream around each launch, separate pass"}
+                          "timing": "CUDA events on the launching stream around each launch, separate eager pass with the "
+                                    "host running ahead of the GPU (spin kernel before forward / backward)"}
         model.image_encoder.cnn = cnn
         model.image_encoder.backbone_dtype = saved_dtype
         # ---- the BatchNorm / add / ReLU sweeps of the trunk (csrc/bn_act.cu): full-model steps, CUDA events
@@ -420,7 +436,12 @@ def run_product(args):
         if getattr(model.image_encoder, "fused_trunk", False):
             _lib.prof_enable(True)
             for i in range(2):
-                step_resident(i)
+                torch.manual_seed(1234 + i)
+                torch.cuda._sleep(2 * lag)                    # host runs ahead: launches execute back to back
+                loss = model.training_step(resident[i & 1], i)
+                torch.cuda._sleep(2 * lag)
+                loss.backward()
+                zero()
             torch.cuda.synchronize()
             _lib.prof_enable(False)
             for name, kid in (("bn_stats_kernel", _lib.K_BN_STATS), ("bn_apply_kernel", _lib.K_BN_APPLY),
