@@ -200,7 +200,9 @@ def run_product(args):
         _lib.lib().v2f_gru_persistent_enable(0)
     model = _build_model(dev, args.precision)
     use_graph = not args.no_graph
-    reducer = GradReducer(model, hooks=not use_graph) if world > 1 else None
+    # --graph-nccl: capture the bucketed all-reduces inside the graph (overlap with backward); default: reduce after
+    graph_nccl = use_graph and args.graph_nccl
+    reducer = GradReducer(model, hooks=(not use_graph) or graph_nccl) if world > 1 else None
     # two distinct batches per rank, alternated: 137 MB of images each, larger than the 126 MB L2
     host = [_batch(B, seed=21 + 1000 * rank + i, pin=True) for i in range(2)]
     resident = [(tuple(t.to(dev) for t in d), im.to(dev)) for d, im in host]
@@ -267,12 +269,12 @@ def run_product(args):
     if use_graph:
         from visuelle2_multimodal_fusion_b200.graphs import GraphedTrainStep
         torch.manual_seed(99)
-        graphed = GraphedTrainStep(model, resident[0])
+        graphed = GraphedTrainStep(model, resident[0], reducer=reducer if graph_nccl else None)
 
         def step_resident(i):                                # noqa: F811
             torch.manual_seed(1234 + i)
             loss = graphed(resident[i & 1])
-            if reducer:
+            if reducer and not graph_nccl:
                 reducer.reduce_now()
             return loss
 
@@ -321,7 +323,7 @@ def run_product(args):
             torch.manual_seed(1234 + i)
             if graphed is not None:
                 loss = graphed(batch)            # staged device batch -> the graph's input buffers -> replay
-                if reducer:
+                if reducer and not graph_nccl:
                     reducer.reduce_now()
             else:
                 loss = model.training_step(batch, i)
@@ -519,6 +521,7 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--ref-batch", type=int, default=8, help="items per step of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--graph-nccl", action="store_true", help="capture the gradient all-reduces inside the CUDA graph")
     ap.add_argument("--no-graph", action="store_true", help="time the eager loop instead of the CUDA-graph replay")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -44,8 +44,12 @@ class GraphedTrainStep:
     """``step = GraphedTrainStep(model, example_batch); loss = step(batch)`` -- same arithmetic as
     ``loss = model.training_step(batch, i); loss.backward()`` with gradients in ``p.grad``."""
 
-    def __init__(self, model, example_batch, warmup=3):
+    def __init__(self, model, example_batch, warmup=3, reducer=None):
+        """``reducer``: a ``ddp.GradReducer`` built with hooks: its bucketed NCCL all-reduces are captured INSIDE
+        the graph, on its side stream, so they overlap the rest of the backward exactly as in the eager loop
+        (gradients in ``p.grad`` are already averaged when the replay returns)."""
         self.model = model
+        self.reducer = reducer
         dev = next(model.parameters()).device
         self.device = dev
         self.static_batch = _tree_map(lambda t: t.to(dev, copy=True), example_batch)
@@ -61,6 +65,8 @@ class GraphedTrainStep:
                 self._refresh_tf()
                 loss = model.training_step(self.static_batch, i)
                 loss.backward()
+                if reducer is not None:
+                    reducer.finish()
                 for p in self.params:
                     p.grad = None
         torch.cuda.current_stream(dev).wait_stream(side)
@@ -71,6 +77,8 @@ class GraphedTrainStep:
         with torch.cuda.graph(self.graph, stream=side):     # same stream as the warm-up: no AccumulateGrad stream mismatch
             self.static_loss = model.training_step(self.static_batch, 0)
             self.static_loss.backward()
+            if reducer is not None:
+                reducer.finish()
         self.launches_per_replay = _lib.launch_count() - l0   # libv2f_b200 kernels inside one replay
 
     def _refresh_tf(self):
