@@ -6,6 +6,7 @@ Restates, as written, the forwards of
   * Proposed_model_v2           /root/reference/models/Proposed_model_v2.py:802-847
   * Proposed_model_v3 (TARG)    /root/reference/models/Proposed_model_v3.py:284-327
   * Proposed_model_v4           /root/reference/models/Proposed_model_v4.py:245-289
+  * M4FT_Visuelle2              /root/reference/models/M4FT_Visuelle2.py:252-300
 on a flat dict of tensors keyed by the reference state_dict names.  The torch building blocks the
 reference delegates to (nn.TransformerEncoderLayer / DecoderLayer post-LN with ReLU,
 nn.MultiheadAttention, nn.LayerNorm, nn.BatchNorm1d, nn.GRU, nn.Embedding, 1x1 nn.Conv2d +
@@ -204,6 +205,20 @@ def fusion_v3(e_temp, e_text, e_vis, P, bn_batch, drop, query_modality):
     return lin(x, P, "fusion_network.fusion_final.net.4.")
 
 
+def _fusion_block(x, P, prefix, bn_batch, drop):
+    """FusionBlock, M4FT_Visuelle2.py:161-173 / Proposed_model_v3.py:160-172."""
+    x = batch_norm1d(x, P, prefix + "net.0.", bn_batch)
+    x = F.dropout(F.relu(lin(x, P, prefix + "net.1.")), 0.2, drop)
+    return lin(x, P, prefix + "net.4.")
+
+
+def fusion_m4ft(e_temp, e_text, e_vis, P, bn_batch, drop):
+    """M4FTFusionNetwork, M4FT_Visuelle2.py:175-202."""
+    out_tt = _fusion_block(e_temp + e_text, P, "fusion_network.fusion_temp_text.", bn_batch, drop)
+    out_tv = _fusion_block(e_text + e_vis, P, "fusion_network.fusion_text_vis.", bn_batch, drop)
+    return _fusion_block(out_tt + out_tv + e_temp + e_text + e_vis, P, "fusion_network.fusion_final.", bn_batch, drop)
+
+
 # --------------------------------------------------------------------------- v1 / v2 custom layers
 def decoder_layer_v1(tgt, mem, P, prefix, heads, tgt_mask, p_drop, drop):
     """GatedTransformerDecoderLayer, Proposed_model.py:226-262 (cross-attn output * sigmoid(gate_proj(query)))."""
@@ -250,7 +265,7 @@ def encoder_layer_v2(x, P, prefix, heads, mask, p_drop, drop):
 def gtm_family_forward(variant, P, item_sales, cat, col, fab, store, temporal, gtrends, feat, *, output_len,
                        heads, num_layers=1, use_encoder_mask=1, autoregressive=False, training=False,
                        drop=None, query_modality="image"):
-    """``variant`` in {'gtm','v1','v2','v3','v4'}.  Returns (forecast [N, output_len], None)."""
+    """``variant`` in {'gtm','v1','v2','v3','v4','m4ft'}.  Returns (forecast [N, output_len], None)."""
     drop = training if drop is None else drop
     if item_sales.dim() == 3:
         bs, splits, window = item_sales.shape
@@ -264,7 +279,7 @@ def gtm_family_forward(variant, P, item_sales, cat, col, fab, store, temporal, g
                              layer_fn=encoder_layer_v2)
     else:
         enc = gtrend_encoder(gtrends, P, "gtrend_encoder.", 4, output_len, use_encoder_mask, drop)
-    if variant == "v3":
+    if variant in ("v3", "m4ft"):
         e_text = F.dropout(lin(torch.cat([P["text_encoder.cat_emb.weight"][cat], P["text_encoder.col_emb.weight"][col],
                                           P["text_encoder.fab_emb.weight"][fab],
                                           P["text_encoder.store_emb.weight"][store]], 1), P, "text_encoder.proj."),
@@ -279,7 +294,9 @@ def gtm_family_forward(variant, P, item_sales, cat, col, fab, store, temporal, g
         enc = enc.repeat_interleave(splits, dim=1)
         statics = [s.repeat_interleave(splits, dim=0) for s in statics]
     h_sales = sales_encoder(item_sales.reshape(bs * splits, window, 1), P, drop)
-    if variant == "v3":
+    if variant == "m4ft":
+        ctx = fusion_m4ft(*statics, P, training, drop)
+    elif variant == "v3":
         ctx = fusion_v3(*statics, P, training, drop, query_modality)
     else:
         ctx = {"gtm": fusion_gtm, "v1": fusion_v1, "v2": fusion_v2, "v4": fusion_v4}[variant](*statics, P, training, drop)

@@ -13,7 +13,7 @@ from oracle import refshim
 
 MODELS = {"gtm": ("GTM_Visuelle2", "GTM_Visuelle2"), "v1": ("Proposed_model", "GatedMultimodal_Visuelle2"),
           "v2": ("Proposed_model_v2", "GatedMultimodal_Visuelle2"), "v3": ("Proposed_model_v3", "TARG_M4FT_Visuelle2"),
-          "v4": ("Proposed_model_v4", "GatedMultimodal_Visuelle2")}
+          "v4": ("Proposed_model_v4", "GatedMultimodal_Visuelle2"), "m4ft": ("M4FT_Visuelle2", "M4FT_Visuelle2")}
 
 
 def build_reference(variant, E, H, out_len, heads, autoregressive, query_modality="image"):
@@ -115,4 +115,6 @@ CASES = {
     "v3_demand_train": _mk("v3", mode="train_nodrop", seed=37, query_modality="text"),
     "v1_demand_train": _mk("v1", mode="train_nodrop", seed=39),
     "v2_demand_train": _mk("v2", mode="train_nodrop", seed=40),
+    "m4ft_demand_train": _mk("m4ft", mode="train_nodrop", seed=41),
+    "m4ft_sofore10_eval": _mk("m4ft", seed=42, demand=False, out_len=10),
 }

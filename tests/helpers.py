@@ -90,7 +90,8 @@ def gtm_product_ctor(variant):
     modname, clsname = {"gtm": ("GTM_Visuelle2", "GTM_Visuelle2"), "v1": ("Proposed_model", "GatedMultimodal_Visuelle2"),
                         "v2": ("Proposed_model_v2", "GatedMultimodal_Visuelle2"),
                         "v3": ("Proposed_model_v3", "TARG_M4FT_Visuelle2"),
-                        "v4": ("Proposed_model_v4", "GatedMultimodal_Visuelle2")}[variant]
+                        "v4": ("Proposed_model_v4", "GatedMultimodal_Visuelle2"),
+                        "m4ft": ("M4FT_Visuelle2", "M4FT_Visuelle2")}[variant]
     import visuelle2_multimodal_fusion_b200.models._gtm as g
     v3 = importlib.import_module("visuelle2_multimodal_fusion_b200.models.Proposed_model_v3")
     for holder in (g, v3):

@@ -45,7 +45,8 @@ def test_decode_params_struct_matches_header():
 
 
 @pytest.mark.parametrize("name", ["rnn210_small", "rnn21_small", "demand_small", "gtm_demand_eval", "gtm_ar_eval",
-                                  "v1_demand_train", "v2_demand_train", "v3_demand_train", "v4_demand_train"])
+                                  "v1_demand_train", "v2_demand_train", "v3_demand_train", "v4_demand_train",
+                                  "m4ft_demand_train"])
 def test_state_dict_keys_match_reference(name):
     from helpers import product_model
     blob = load_golden(name)
@@ -93,7 +94,7 @@ def test_same_seed_same_init_as_reference():
         assert torch.equal(rs[k], ms[k]), k
 
 
-@pytest.mark.parametrize("variant", ["gtm", "v1", "v2", "v3", "v4"])
+@pytest.mark.parametrize("variant", ["gtm", "v1", "v2", "v3", "v4", "m4ft"])
 def test_gtm_family_same_seed_same_init_as_reference(variant):
     """GTM family: same constructor arguments + same seed => bit-identical parameters and buffers."""
     from oracle import refshim

@@ -9,7 +9,8 @@ from helpers import (_restore_gtm_trunk, assert_close, compare_blob, gtm_product
 
 pytestmark = pytest.mark.gpu
 GTM_CASES = ["gtm_demand_eval", "gtm_demand_train", "gtm_sofore1_train", "gtm_ar_eval", "v4_demand_train",
-             "v4_sofore10_eval", "v3_demand_train", "v1_demand_train", "v2_demand_train"]
+             "v4_sofore10_eval", "v3_demand_train", "v1_demand_train", "v2_demand_train", "m4ft_demand_train",
+             "m4ft_sofore10_eval"]
 TOL_TC = 2e-2
 
 
@@ -37,7 +38,8 @@ def test_cuda_tensorcore_path_matches_reference_golden(name):
 @pytest.mark.parametrize("variant,demand,T,ar", [("gtm", True, 12, False), ("v4", True, 12, False),
                                                  ("gtm", False, 10, False), ("v4", False, 1, False),
                                                  ("v1", True, 12, False), ("v2", True, 12, False),
-                                                 ("v3", True, 12, False), ("gtm", True, 12, True)])
+                                                 ("v3", True, 12, False), ("gtm", True, 12, True),
+                                                 ("m4ft", True, 12, False)])
 def test_cuda_matches_oracle_default_dims(variant, demand, T, ar, precision, tol):
     import visuelle2_multimodal_fusion_b200.synth as synth
     # the tensor-core leg runs at a batch closer to the reference's 128: with 16 rows a weight gradient is a sum of

@@ -9,7 +9,8 @@ TOL = 1e-5   # fp32 contract, SURVEY.md section 8d
 
 
 GTM_CASES = ["gtm_demand_eval", "gtm_demand_train", "gtm_sofore1_train", "gtm_ar_eval", "v4_demand_train",
-             "v4_sofore10_eval", "v3_demand_train", "v1_demand_train", "v2_demand_train"]
+             "v4_sofore10_eval", "v3_demand_train", "v1_demand_train", "v2_demand_train", "m4ft_demand_train",
+             "m4ft_sofore10_eval"]
 
 
 @pytest.mark.parametrize("name", RNN_CASES + GTM_CASES)
