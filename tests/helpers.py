@@ -36,6 +36,12 @@ def noise_only_grads(blob):
     if blob["model"] == "GTM:gtm" and blob["cfg"]["mode"] != "eval":
         names |= {"image_encoder.projection.bias", "dummy_encoder.dummy_fusion.bias"}
         names |= {f"dummy_encoder.{n}_emb.bias" for n in ("day", "week", "month", "year")}
+    if blob["model"] == "GTM:m4ft" and blob["cfg"]["mode"] != "eval":
+        # every static embedding reaches the decoder only through train-mode BatchNorm1d layers (M4FT fusion blocks)
+        names |= {"text_encoder.proj.bias", "temporal_encoder.proj.bias", "image_encoder.final_proj.bias",
+                  "image_encoder.projection.bias", "fusion_network.fusion_temp_text.net.4.bias",
+                  "fusion_network.fusion_text_vis.net.4.bias"}
+        names |= {f"temporal_encoder.{n}_emb.bias" for n in ("day", "week", "month", "year")}
     names |= {k for k in blob["grads"] if k.endswith("attn_linear.bias")}
     # a key bias shifts every score of a softmax row equally (Proposed_model_v2's separate k_proj)
     names |= {k for k in blob["state"] if k.endswith("k_proj.bias")}

@@ -50,7 +50,9 @@ def full(path):
     h, units = rows[0], rows[1]
     print("metric,unit," + ",".join(r[h.index("Kernel Name")][:60].replace(",", ";") for r in rows[2:]))
     for i, k in enumerate(h):
-        if k in KEYS or k.startswith("smsp__average_warps_issue_stalled"):
+        if k in KEYS or k.startswith("smsp__average_warps_issue_stalled") or k.startswith("sm__pipe_tensor_cycles_active") \
+                or ("utchmma" in k and "sparsity_off" in k and ("pct_of_peak_sustained_elapsed" in k or k.endswith(".sum"))
+                    and rows[2][i] not in ("0", "0.0")):
             print(",".join([k, units[i]] + [r[i] for r in rows[2:]]))
 
 
