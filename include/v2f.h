@@ -30,7 +30,8 @@ long long v2f_launch_count(void);
 
 /* Kernel ids for the optional event timing below. */
 enum { V2F_K_ATTN_FWD = 0, V2F_K_ATTN_BWD = 1, V2F_K_TILEGRAD = 2, V2F_K_BN_STATS = 3, V2F_K_BN_APPLY = 4,
-       V2F_K_BN_BWD_REDUCE = 5, V2F_K_BN_BWD_ELEMT = 6, V2F_K_COUNT = 7 };
+       V2F_K_BN_BWD_REDUCE = 5, V2F_K_BN_BWD_ELEMT = 6, V2F_K_DECODE_PERSIST_FWD = 7,
+       V2F_K_DECODE_PERSIST_BWD = 8, V2F_K_COUNT = 9 };
 /* Per-kernel CUDA-event timing on the launching stream (bench.py roofline leg).  Off by default.
  * v2f_prof_read sums the spans recorded for one kernel id since the previous read.            */
 int v2f_prof_enable(int on);
@@ -138,10 +139,25 @@ typedef struct v2f_decode_params {
    * (and y != NULL) the kernels read it at run time instead of the immediate, so a captured CUDA graph of the
    * step can be replayed with a fresh draw (graphs.GraphedTrainStep).                                        */
   const unsigned* tf_mask_dev;
+  /* optional scratch of v2f_decode_persist_ws_floats(N,E,H,T) floats: enables the persistent decoder
+   * (csrc/decode_persist.cu): the whole T-step loop as ONE cooperative launch with the recurrent and
+   * fusion weights resident in shared memory.  Taken when E is 256 or 512, H % 64 == 0, H <= 512, image and
+   * trend attention are both on, variant != 1 and attn_ws is given; otherwise (or when NULL) the
+   * step-per-launch path runs.  Both paths fill the same saved activations.                         */
+  float *persist_ws;
 } v2f_decode_params;
 
 int v2f_decode_fwd(const v2f_decode_params* p, void* stream);
 int v2f_decode_bwd(const v2f_decode_params* p, void* stream);
+long long v2f_decode_persist_ws_floats(int N, int E, int H, int T);
+/* A/B switch (default 1): 0 forces the step-per-launch path even when persist_ws is given. */
+int v2f_decode_persistent_enable(int on);
+/* Profiling: CTA 0 of the persistent decoder stamps %globaltimer (ns) at its phase boundaries,
+ * [T][8] unsigned long long at byte offset v2f_decode_persist_stamps_offset(N,E,H) of persist_ws:
+ * 0 step start, 1 after P1 (S product), 2 after P2 (attention sweep), 3 after the combine, 4 after P3 (HC),
+ * 5 after P4 (multimodal attention), 6 after P5/P6 (embedder + GRU gates).                          */
+int v2f_decode_persist_stamps_enable(int on);
+long long v2f_decode_persist_stamps_offset(int N, int E, int H);
 
 /* ------------------------------------------------------------------------------------------
  * Single-layer batch-first GRU over a sequence (nn.GRU, gate order r,z,n):

@@ -165,3 +165,64 @@ def test_cuda_graph_replay_equals_eager_step(model):
                 continue
             d = float((p.grad - gg[k]).abs().max())
             assert d <= 1e-5 * float(p.grad.abs().max()) + 1e-9, (k, d)
+
+
+def _head_model(model, E=512, T=None):
+    import torch.nn as nn
+    import visuelle2_multimodal_fusion_b200.synth as synth
+    import visuelle2_multimodal_fusion_b200.models.modules as mods
+    from visuelle2_multimodal_fusion_b200.models import CrossAttnRNN210, CrossAttnRNNDemand
+    orig = mods.resnet101_trunk
+    mods.resnet101_trunk = lambda: nn.Identity()
+    try:
+        torch.manual_seed(0)
+        cat_d, col_d, fab_d = synth.label_dicts()
+        if model == "CrossAttnRNN210":
+            m = CrossAttnRNN210.CrossAttnRNN(E, E, E, cat_d, col_d, fab_d, synth.STORE_N, 3, out_len=T or 10)
+        else:
+            m = CrossAttnRNNDemand.CrossAttnRNN(E, E, 3, E, cat_d, col_d, fab_d, synth.STORE_N, True, True, True,
+                                                True, out_len=T or 12, use_teacher_forcing=True)
+    finally:
+        mods.resnet101_trunk = orig
+    return m.cuda().eval()
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 2e-5), ("bf16", 2e-2)])
+@pytest.mark.parametrize("model,B,E", [("CrossAttnRNN210", 128, 512), ("CrossAttnRNNDemand", 128, 512),
+                                       ("CrossAttnRNN210", 40, 512), ("CrossAttnRNN210", 150, 512),
+                                       ("CrossAttnRNN210", 24, 256)])
+def test_persistent_decoder_equals_step_per_launch_path(model, B, E, precision, tol):
+    """csrc/decode_persist.cu (one cooperative launch for the whole horizon, weights resident in shared memory)
+    against the step-per-launch path of rnn_decode.cu on the same inputs: forecasts, attention maps and every
+    gradient (the backward consumes the activations the forward path saved)."""
+    import visuelle2_multimodal_fusion_b200.functional as Fv
+    import visuelle2_multimodal_fusion_b200.synth as synth
+    from visuelle2_multimodal_fusion_b200 import _lib
+    demand = model == "CrossAttnRNNDemand"
+    m = _head_model(model, E)
+    m.precision = precision
+    m.use_teacher_forcing = True
+    data, feat = synth.make_batch(B, out_len=10, demand=demand, seed=5, feat_hw=10)
+    data = tuple(t.cuda() for t in data)
+    res = {}
+    launches = {}
+    for flag in (True, False):
+        Fv.PERSISTENT_DECODE = flag
+        try:
+            f = feat.cuda().clone().requires_grad_(True)
+            torch.manual_seed(9)
+            n0 = _lib.launch_count()
+            out = m(*data, f)[0]
+            launches[flag] = _lib.launch_count() - n0
+            out.square().mean().backward()
+            res[flag] = [out.detach().clone(), f.grad.clone()] + \
+                [p.grad.clone() for _, p in sorted(m.named_parameters()) if p.grad is not None]
+            names = ["out", "grad_feat"] + [k for k, p in sorted(m.named_parameters()) if p.grad is not None]
+            m.zero_grad(set_to_none=True)
+        finally:
+            Fv.PERSISTENT_DECODE = True
+    assert launches[True] < launches[False] - 50, launches      # the loop really collapsed into one launch
+    for k, a, b in zip(names, res[True], res[False]):
+        floor = 1e-6 if k.endswith("attn_linear.bias") else 1e-9
+        assert float((a - b).abs().max()) <= tol * float(b.abs().max()) + floor, (k, float((a - b).abs().max()),
+                                                                                 float(b.abs().max()))

@@ -10,7 +10,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libv2f_b200.so")
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 _lib = None
 
@@ -33,7 +33,7 @@ class DecodeParams(ctypes.Structure):
              "dWcat", "dbcat", "dw_att", "db_tl", "dWe_mm", "dW_me", "db_me", "dW_ihc", "dw_x",
              "db_ih", "dw_fc", "db_fc", "WcatT", "W_ihcT", "W_meT", "We_mmT", "ws"]
     _fields_ = ([(n, c_int) for n in _INTS] + [("tf_mask", ctypes.c_uint), ("precision", c_int)] +
-                [(n, c_vp) for n in _PTRS] + [("ws_floats", c_ll), ("attn_ws", c_vp), ("tf_mask_dev", c_vp)])
+                [(n, c_vp) for n in _PTRS] + [("ws_floats", c_ll), ("attn_ws", c_vp), ("tf_mask_dev", c_vp), ("persist_ws", c_vp)])
 
 
 def _declare(lib):
@@ -62,6 +62,14 @@ def _declare(lib):
     lib.v2f_prof_enable.argtypes = [c_int]
     lib.v2f_gru_persistent_enable.argtypes = [c_int]
     lib.v2f_gru_persistent_enable.restype = c_int
+    lib.v2f_decode_persistent_enable.argtypes = [c_int]
+    lib.v2f_decode_persistent_enable.restype = c_int
+    lib.v2f_decode_persist_stamps_enable.argtypes = [c_int]
+    lib.v2f_decode_persist_stamps_enable.restype = c_int
+    lib.v2f_decode_persist_ws_floats.argtypes = [c_int, c_int, c_int, c_int]
+    lib.v2f_decode_persist_ws_floats.restype = c_ll
+    lib.v2f_decode_persist_stamps_offset.argtypes = [c_int, c_int, c_int]
+    lib.v2f_decode_persist_stamps_offset.restype = c_ll
     lib.v2f_prof_read.argtypes = [c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(c_ll)]
     lib.v2f_prof_read_bytes.argtypes = [c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(c_ll),
                                         ctypes.POINTER(c_ll)]
@@ -153,7 +161,8 @@ def launch_count():
     return int(lib().v2f_launch_count())
 
 
-K_ATTN_FWD, K_ATTN_BWD, K_TILEGRAD, K_BN_STATS, K_BN_APPLY, K_BN_BWD_REDUCE, K_BN_BWD_ELEMT = range(7)
+(K_ATTN_FWD, K_ATTN_BWD, K_TILEGRAD, K_BN_STATS, K_BN_APPLY, K_BN_BWD_REDUCE, K_BN_BWD_ELEMT, K_DECODE_PERSIST_FWD,
+ K_DECODE_PERSIST_BWD) = range(9)
 
 
 def prof_enable(on):

@@ -1,0 +1,826 @@
+// Persistent recurrent-attention decoder: ONE cooperative launch for the whole T-step horizon of the
+// CrossAttnRNN210 / CrossAttnRNNDemand decode loop, the recurrent and fusion weights resident in
+// shared memory from the first step to the last.  sm_100a.
+//
+// Reference arithmetic: /root/reference/models/CrossAttnRNN210.py:191-225 (loop), :83-89
+// (AdditiveAttention), :135-140,210-211 (decoder nn.GRU cell), :141,212-225 (decoder_fc + teacher
+// forcing); /root/reference/models/CrossAttnRNNDemand.py:285-347,134-149.  Same equations, same saved
+// activations as the step-per-launch path of rnn_decode.cu (whose backward consumes them unchanged).
+//
+// Why: at N = 128 rows a decode step is four [128 x 512] x [512 x (512..3072)] products, two row-local
+// kernels and one HBM-bound attention sweep -- ~9 launches of 5-20 us each, 10-12 steps, i.e. the loop
+// was launch- and ramp-bound (1 ms for 0.15 ms of memory time).  Here one CTA per SM (576 threads)
+// walks all steps; a step is six phases separated by a grid barrier (monotonic counter, bounded spin):
+//
+//   P1  S = h_t [Wd_img;Wd_tr;Wd_mm;W_hh]^T + b      each CTA owns ~1/148 of the output columns: its
+//   P3  HC = C We_mm^T                               rows of the weight matrices (48 rows x K, 97 KB,
+//   P5  [CTX | GI] = U [W_me ; W_ihc W_me]^T + b     tf32-rounded once in tensor-core mode) stay in
+//                                                    shared memory for the whole horizon; the [128 x K]
+//                                                    activations stream through L2 in 64-wide K chunks
+//                                                    (cp.async double buffer); products on warp-level
+//                                                    tf32 MMAs (precision 1) or exact fp32 FMAs (0)
+//   P2  additive cross-attention over the image map and the trend sequence: the HBM-bound sweep.  The
+//       (row, modality, 8-position chunk) list is split evenly over 2 x 148 consumer groups (8 warps
+//       each); one producer warp per group feeds a 4-slot ring with bulk copies (TMA, mbarrier
+//       completion) of the H and V rows of a chunk as separate slots; warp-per-position energies,
+//       online softmax, thread-per-column context; a segment cut by a group boundary leaves partials
+//   P2b combine of the partials (per segment), softmax weights for the backward pass
+//   P4  row-local multimodal attention -> U; also closes the previous step's decoder_fc
+//       (yhat_{t-1} = sum of the per-CTA partial dot products) and the teacher-forcing select
+//   P6  (fused behind P5, no barrier) GRU gates for the CTA's own hidden units: GI never leaves the SM
+//
+// GI = CTX W_ihc^T is re-associated to U (W_ihc W_me)^T (one product per forward, exact identity) so the
+// embedder and the GRU input projection read U once, in one phase.
+#include "async.cuh"
+#include "attn.cuh"
+#include "gemm_dispatch.cuh"
+
+namespace v2f {
+
+constexpr int DP_CONS = 512;                // 16 consumer warps = 2 groups of 8
+constexpr int DP_GRP = 256;                 // threads per consumer group
+constexpr int DP_THREADS = DP_CONS + 64;    // + one producer warp per group
+constexpr int DP_CH = 8;                    // positions per chunk
+constexpr int DP_SLOTS = 4;                 // ring slots per group; a slot holds one operand (H or V) of one chunk
+constexpr int DP_MB = 128;                  // rows per product row block
+constexpr int DP_KC = 32;                   // K chunk of the streamed activations
+constexpr int DP_XP = DP_KC + 4;            // its shared-memory pitch (conflict-free fragment loads)
+constexpr int DP_KALIGN = 64;               // K (= E, H) must be a multiple of this
+constexpr int DP_NT1 = 3, DP_NT3 = 1, DP_NT5 = 2;   // 8-column MMA tiles owned per CTA in P1 / P3 / P5
+constexpr int DP_MAXG = 192;                // upper bound on the grid (ypart rows, barrier slots)
+constexpr int DP_MAXU = 4;                  // hidden units per CTA (gate phase: 4 lanes per row)
+__host__ __device__ constexpr int dp_stages(bool tc) { return tc ? 5 : 4; }   // activation chunks in the cp.async ring
+constexpr int DP_STAMPS = 8;                // globaltimer stamps per step (profiling)
+constexpr int DP_BAR = 256;                 // barrier region of the workspace (unsigned words)
+
+struct DpArgs {
+  v2f_decode_params p;
+  const float* Wp;        // [3H,E] = W_ihc W_me
+  const float* bp;        // [3H]   = W_ihc b_me + b_ih
+  float* ypart;           // [G,N] per-CTA partial decoder_fc dot products of the current step
+  unsigned* bar;          // grid-barrier slots [DP_MAXG], monotonic epochs (zeroed before launch)
+  float *PM, *PL, *PC;    // attention partials [N,cpr], [N,cpr] (zeroed before launch), [N,cpr,E]
+  unsigned long long* stamps;   // optional [T, DP_STAMPS] globaltimer stamps written by CTA 0
+};
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+// Grid barrier without atomics: CTA c publishes the epoch in its own slot (release), thread i of every CTA
+// spins on slot i (acquire).  Slots are monotonic, zeroed before the launch; every spin is bounded.
+__device__ __forceinline__ void grid_barrier(unsigned* slots, unsigned& epoch) {
+  __syncthreads();
+  ++epoch;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(slots + blockIdx.x), "r"(epoch) : "memory");
+  }
+  if (threadIdx.x < gridDim.x) {
+    const unsigned* sp = slots + threadIdx.x;
+    unsigned v;
+    const long long t0 = clock64();
+    for (;;) {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(sp) : "memory");
+      if (v >= epoch) break;
+      if (clock64() - t0 > (1LL << 31)) __trap();   // ~1 s: a protocol bug must not hang the device
+    }
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ uint32_t dp_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void dp_mma(float* d, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ float dp_dot4(const float4& a, const float4& b, float acc) {
+  acc = fmaf(a.x, b.x, acc);
+  acc = fmaf(a.y, b.y, acc);
+  acc = fmaf(a.z, b.z, acc);
+  return fmaf(a.w, b.w, acc);
+}
+
+// Column ownership of CTA c of G (proportional split; contiguous ranges).
+struct DpOwn {
+  int a_lo, na;     // attention-query columns of S: [a_lo, a_lo+na) of [0,3E)
+  int u_lo, nu;     // hidden units [u_lo, u_lo+nu) of [0,H): gh columns in P1, gate columns in P5
+  int n1;           // na + 3 nu
+  int m3, e_lo3, n3;   // P3: modality row set (0 image contexts, 1 trend contexts) and columns of HC
+  int x_lo, nx, n5;    // P5: columns of CTX, then 3 nu gate columns
+};
+__host__ __device__ inline DpOwn dp_own(int c, int G, int E, int H) {
+  DpOwn o;
+  o.a_lo = (int)((long long)3 * E * c / G);
+  o.na = (int)((long long)3 * E * (c + 1) / G) - o.a_lo;
+  o.u_lo = (int)((long long)H * c / G);
+  o.nu = (int)((long long)H * (c + 1) / G) - o.u_lo;
+  o.n1 = o.na + 3 * o.nu;
+  o.m3 = c & 1;
+  const int Gm = (G - o.m3 + 1) / 2, idx = c >> 1;
+  o.e_lo3 = (int)((long long)E * idx / Gm);
+  o.n3 = (int)((long long)E * (idx + 1) / Gm) - o.e_lo3;
+  o.x_lo = (int)((long long)E * c / G);
+  o.nx = (int)((long long)E * (c + 1) / G) - o.x_lo;
+  o.n5 = o.nx + 3 * o.nu;
+  return o;
+}
+
+// One row block (<= 128 rows) of  OUT[rows, NT*8] = X[rows, K] Wsm[NT*8, K]^T : X streamed from global
+// through L2 (written by other SMs) in DP_KC-wide chunks, Wsm resident.  Leaves NPART partial sums in
+// Rp[part][128][NT*8] (NPART = 2 K-halves in tensor-core mode, 4 K-quarters in exact mode); the caller's
+// epilogue adds them.  All threads of the CTA must call it.
+template <bool TC, int NT>
+__device__ __forceinline__ void dp_product(const float* __restrict__ X, long long ldx, int rows, int K,
+                                           const float* Wsm, int P, float* Xb, float* Rp) {
+  constexpr int NW = NT * 8;
+  constexpr int NST = dp_stages(TC);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nch = K / DP_KC;
+  auto load_chunk = [&](int ch) {
+    float* dst = Xb + (ch % NST) * DP_MB * DP_XP;
+    for (int i = tid; i < DP_MB * (DP_KC / 4); i += DP_THREADS) {
+      const int r = i / (DP_KC / 4), k4 = i - r * (DP_KC / 4);
+      float* d = dst + r * DP_XP + 4 * k4;
+      if (r < rows) {
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(d)),
+                     "l"(X + (long long)r * ldx + ch * DP_KC + 4 * k4)
+                     : "memory");
+      } else {
+        *reinterpret_cast<float4*>(d) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+  };
+  float acc[TC ? NT * 4 : NW];
+#pragma unroll
+  for (int i = 0; i < (TC ? NT * 4 : NW); i++) acc[i] = 0.f;
+#pragma unroll
+  for (int st = 0; st < NST - 1; st++) {
+    if (st < nch) load_chunk(st);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  for (int ch = 0; ch < nch; ch++) {
+    asm volatile("cp.async.wait_group %0;" ::"n"(NST - 2) : "memory");
+    __syncthreads();                  // chunk ch has landed; everybody is done with the buffer of chunk ch-1
+    if (ch + NST - 1 < nch) load_chunk(ch + NST - 1);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    const float* cur = Xb + (ch % NST) * DP_MB * DP_XP;
+    if (warp < DP_CONS / 32) {
+      if (TC) {
+        const int mt = warp & 7, kh = warp >> 3, g = lane >> 2, tt = lane & 3;
+        const float* xa = cur + (16 * mt + g) * DP_XP + tt;
+        const float* wb = Wsm + g * P + ch * DP_KC + tt;
+#pragma unroll
+        for (int ks = 0; ks < DP_KC / 16; ks++) {
+          const int k0 = (kh * (DP_KC / 16) + ks) * 8;
+          uint32_t af[4];
+          af[0] = dp_tf32(xa[k0]);
+          af[1] = dp_tf32(xa[8 * DP_XP + k0]);
+          af[2] = dp_tf32(xa[k0 + 4]);
+          af[3] = dp_tf32(xa[8 * DP_XP + k0 + 4]);
+#pragma unroll
+          for (int n = 0; n < NT; n++)
+            dp_mma(acc + 4 * n, af, __float_as_uint(wb[n * 8 * P + k0]), __float_as_uint(wb[n * 8 * P + k0 + 4]));
+        }
+      } else {
+        const int row = tid & 127, kq = tid >> 7;
+        const float* xr = cur + row * DP_XP + kq * (DP_KC / 4);
+        const float* wr = Wsm + ch * DP_KC + kq * (DP_KC / 4);
+#pragma unroll
+        for (int k = 0; k < DP_KC / 4; k += 4) {
+          const float4 x4 = *reinterpret_cast<const float4*>(xr + k);
+#pragma unroll
+          for (int j = 0; j < NW; j++) acc[j] = dp_dot4(x4, *reinterpret_cast<const float4*>(wr + j * P + k), acc[j]);
+        }
+      }
+    }
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  if (warp < DP_CONS / 32) {
+    if (TC) {
+      const int mt = warp & 7, kh = warp >> 3, g = lane >> 2, tt = lane & 3;
+#pragma unroll
+      for (int n = 0; n < NT; n++) {
+        float* rp = Rp + (kh * DP_MB + 16 * mt + g) * NW + n * 8 + 2 * tt;
+        rp[0] = acc[4 * n];
+        rp[1] = acc[4 * n + 1];
+        rp[8 * NW] = acc[4 * n + 2];
+        rp[8 * NW + 1] = acc[4 * n + 3];
+      }
+    } else {
+      const int row = tid & 127, kq = tid >> 7;
+#pragma unroll
+      for (int j = 0; j < NW; j++) Rp[(kq * DP_MB + row) * NW + j] = acc[j];
+    }
+  }
+  __syncthreads();
+}
+
+template <bool TC, int NW>
+__device__ __forceinline__ float dp_rsum(const float* Rp, int row, int col) {
+  float v = Rp[row * NW + col] + Rp[(DP_MB + row) * NW + col];
+  if (!TC) v += Rp[(2 * DP_MB + row) * NW + col] + Rp[(3 * DP_MB + row) * NW + col];
+  return v;
+}
+
+__device__ __forceinline__ const float* dp_mm_row(const float* st, const float* dyn, int b, int n, int k, int E) {
+  // k: 0 date (static 0), 1 image ctx (dynamic 0), 2 attributes (static 1), 3 trend ctx (dynamic 1)
+  return (k & 1) ? dyn + ((long long)n * 2 + (k >> 1)) * E : st + ((long long)b * 2 + (k >> 1)) * E;
+}
+
+struct DpGeom {
+  int cpi, cpt, cpr;
+  long long total;
+};
+__host__ __device__ inline DpGeom dp_geom(int N, int Li, int Lt) {
+  DpGeom g;
+  g.cpi = (Li + DP_CH - 1) / DP_CH;
+  g.cpt = (Lt + DP_CH - 1) / DP_CH;
+  g.cpr = g.cpi + g.cpt;
+  g.total = (long long)N * g.cpr;
+  return g;
+}
+
+template <int CPT, bool TC>
+__global__ void __launch_bounds__(DP_THREADS, 1)
+decode_persist_fwd_kernel(const __grid_constant__ DpArgs a) {
+  constexpr int E = 256 * CPT, KV = 2 * CPT;
+  constexpr int SLOT = DP_CH * E;             // floats per ring slot
+  constexpr int PE = E + 4;
+  extern __shared__ uint8_t raw[];
+  const v2f_decode_params& p = a.p;
+  const int N = p.N, H = p.H, T = p.T, Li = p.Li, Lt = p.Lt, Wn = p.W;
+  const int PH = H + 4, ldS = 3 * E + 3 * H;
+  const int G = gridDim.x, c = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  float* W1 = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(raw) + 127) & ~uintptr_t(127));
+  float* W3 = W1 + DP_NT1 * 8 * PH;
+  float* W5 = W3 + DP_NT3 * 8 * PE;
+  float* ring = W5 + DP_NT5 * 8 * PE;                       // 2 groups x DP_SLOTS x SLOT floats; product scratch
+  ring = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ring) + 127) & ~uintptr_t(127));
+  constexpr int SCRATCH = dp_stages(TC) * DP_MB * DP_XP + (TC ? 2 : 4) * DP_MB * DP_NT1 * 8;   // product staging + partials
+  constexpr int AREA = 2 * DP_SLOTS * SLOT > SCRATCH ? 2 * DP_SLOTS * SLOT : SCRATCH;
+  uint64_t* full = reinterpret_cast<uint64_t*>(ring + AREA);                 // [2][DP_SLOTS]
+  uint64_t* empty = full + 2 * DP_SLOTS;
+  float* e_sh = reinterpret_cast<float*>(empty + 2 * DP_SLOTS);              // [2 groups][2][DP_CH]
+  float* red = e_sh + 4 * DP_CH;                                             // [64]
+  int* cmap1 = reinterpret_cast<int*>(red + 64);                             // [24]: row of Wcat / column of S
+  int* cmap5 = cmap1 + DP_NT1 * 8;                                           // [16]: row of [W_me ; W']
+  float* Xb = ring;                                                          // product staging (aliases the ring)
+  float* Rp = ring + dp_stages(TC) * DP_MB * DP_XP;
+
+  const DpOwn o = dp_own(c, G, E, H);
+
+  // ------------------------------------------------------------------ one-time set-up
+  if (tid == 0) {
+    for (int s = 0; s < 2 * DP_SLOTS; s++) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], DP_GRP / 32);
+    }
+    mbar_fence_init();
+  }
+  if (tid < DP_NT1 * 8) {
+    int r = -1;
+    if (tid < o.na) r = o.a_lo + tid;
+    else if (tid < o.n1) {
+      const int jj = tid - o.na, gate = jj / o.nu, u = jj - gate * o.nu;
+      r = 3 * E + gate * H + o.u_lo + u;
+    }
+    cmap1[tid] = r;
+  }
+  if (tid < DP_NT5 * 8) {
+    int r = -1;
+    if (tid < o.nx) r = o.x_lo + tid;
+    else if (tid < o.n5) {
+      const int jj = tid - o.nx, gate = jj / o.nu, u = jj - gate * o.nu;
+      r = E + gate * H + o.u_lo + u;          // rows >= E index W'
+    }
+    cmap5[tid] = r;
+  }
+  __syncthreads();
+  auto put = [&](float* dst, const float* src, int K4) {   // one weight row -> shared (rounded once in TC mode)
+    for (int k4 = lane; k4 < K4; k4 += 32) {
+      float4 w = src ? ld4(src + 4 * k4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (TC) {
+        w.x = __uint_as_float(dp_tf32(w.x));
+        w.y = __uint_as_float(dp_tf32(w.y));
+        w.z = __uint_as_float(dp_tf32(w.z));
+        w.w = __uint_as_float(dp_tf32(w.w));
+      }
+      *reinterpret_cast<float4*>(dst + 4 * k4) = w;
+    }
+  };
+  for (int j = warp; j < DP_NT1 * 8 + DP_NT3 * 8 + DP_NT5 * 8; j += DP_THREADS / 32) {
+    if (j < DP_NT1 * 8) {
+      const int r = cmap1[j];
+      put(W1 + j * PH, r >= 0 ? p.Wcat + (long long)r * H : nullptr, H / 4);
+    } else if (j < DP_NT1 * 8 + DP_NT3 * 8) {
+      const int jj = j - DP_NT1 * 8;
+      put(W3 + jj * PE, jj < o.n3 ? p.We_mm + (long long)(o.e_lo3 + jj) * E : nullptr, E / 4);
+    } else {
+      const int jj = j - DP_NT1 * 8 - DP_NT3 * 8, r = cmap5[jj];
+      put(W5 + jj * PE, r < 0 ? nullptr : (r < E ? p.W_me + (long long)r * E : a.Wp + (long long)(r - E) * E), E / 4);
+    }
+  }
+  __syncthreads();
+
+  const DpGeom gm = dp_geom(N, Li, Lt);
+  const int grp = warp < 8 ? 0 : (warp < 16 ? 1 : warp - 16);          // consumer group / producer of group
+  const int gt = tid & (DP_GRP - 1), gw = (tid >> 5) & 7;               // thread / warp index inside the group
+  const long long vb = 2LL * c + grp, nvb = 2LL * G;
+  const long long g_lo = gm.total * vb / nvb, g_hi = gm.total * (vb + 1) / nvb;
+  float* gring = ring + grp * DP_SLOTS * SLOT;
+  uint64_t* gfull = full + grp * DP_SLOTS;
+  uint64_t* gempty = empty + grp * DP_SLOTS;
+  float* ge = e_sh + grp * 2 * DP_CH;
+  unsigned it = 0;                 // chunks this group has streamed so far (all steps)
+  unsigned epoch = 0;
+  const bool byproj = p.variant == 2;
+  const int mod_mask = p.mod_mask;
+  const unsigned* mask_dev = p.y ? p.tf_mask_dev : nullptr;
+  auto stamp = [&](int t, int k) {
+    if (a.stamps && c == 0 && tid == 0) a.stamps[t * DP_STAMPS + k] = globaltimer_ns();
+  };
+
+  for (int t = 0; t < T; t++) {
+    const float* h = p.h_all + (long long)t * N * H;
+    float* S = p.S_all + (long long)t * N * ldS;
+    float* C = p.C + (long long)t * N * 2 * E;
+    float* HC = p.HC + (long long)t * N * 2 * E;
+    float* U = p.U + (long long)t * N * E;
+    float* CTX = p.CTX + (long long)t * N * E;
+    float* al_img = p.alpha_img + (long long)t * N * Li;
+    float* al_tr = p.alpha_tr + (long long)t * N * Lt;
+    stamp(t, 0);
+    // ================================================================ P1: S = h Wcat^T + bcat (own columns)
+    for (int r0 = 0; r0 < N; r0 += DP_MB) {
+      const int rows = min(DP_MB, N - r0);
+      dp_product<TC, DP_NT1>(h + (long long)r0 * H, H, rows, H, W1, PH, Xb, Rp);
+      for (int i = tid; i < rows * o.n1; i += DP_THREADS) {
+        const int r = i / o.n1, j = i - r * o.n1, col = cmap1[j];
+        S[(long long)(r0 + r) * ldS + col] = dp_rsum<TC, DP_NT1 * 8>(Rp, r, j) + p.bcat[col];
+      }
+      __syncthreads();
+    }
+    // the ring area was just used through the generic proxy; the bulk copies of P2 write it through the async proxy
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    grid_barrier(a.bar, epoch);
+    stamp(t, 1);
+    // ================================================================ P2: streaming additive attention
+    if (warp >= 16) {
+      if (lane == 0) {
+        unsigned q = 2 * it;
+        for (long long g = g_lo; g < g_hi; g++, q += 2) {
+          const int n = (int)(g / gm.cpr), cc0 = (int)(g - (long long)n * gm.cpr);
+          const int mod = cc0 >= gm.cpi, cc = mod ? cc0 - gm.cpi : cc0;
+          const int L = mod ? Lt : Li, j0 = cc * DP_CH, nj = min(DP_CH, L - j0);
+          const long long off = ((long long)(n / Wn) * L + j0) * E;
+          const uint32_t bytes = (uint32_t)nj * E * 4u;
+          const unsigned sH = q & (DP_SLOTS - 1), rH = q / DP_SLOTS;
+          mbar_wait(&gempty[sH], (rH & 1) ^ 1);
+          mbar_expect_tx(&gfull[sH], bytes);
+          bulk_g2s(gring + sH * SLOT, (mod ? p.Htr : p.Himg) + off, bytes, &gfull[sH]);
+          const unsigned sV = (q + 1) & (DP_SLOTS - 1), rV = (q + 1) / DP_SLOTS;
+          mbar_wait(&gempty[sV], (rV & 1) ^ 1);
+          mbar_expect_tx(&gfull[sV], bytes);
+          bulk_g2s(gring + sV * SLOT, (mod ? p.Ptr : p.Vimg) + off, bytes, &gfull[sV]);
+        }
+      }
+      __syncwarp();
+    } else {
+      float4 sreg[KV], wreg[KV];
+      float cacc[CPT];
+      float m_run = -INFINITY, l_run = 0.f, beta = 0.f;
+      int cur_n = -1, cur_mod = 0, slot0 = 0;
+#pragma unroll
+      for (int i = 0; i < CPT; i++) cacc[i] = 0.f;
+      auto flush = [&]() {
+        const long long slot = (long long)cur_n * gm.cpr + (cur_mod ? gm.cpi : 0) + slot0;
+        if (gt == 0) {
+          a.PM[slot] = m_run;
+          a.PL[slot] = l_run;
+        }
+#pragma unroll
+        for (int i = 0; i < CPT; i++) a.PC[slot * E + gt + 256 * i] = cacc[i];
+      };
+      unsigned q = 2 * it;
+      int par = 0;
+      for (long long g = g_lo; g < g_hi; g++, q += 2, par ^= 1) {
+        const int n = (int)(g / gm.cpr), cc0 = (int)(g - (long long)n * gm.cpr);
+        const int mod = cc0 >= gm.cpi, cc = mod ? cc0 - gm.cpi : cc0;
+        const int L = mod ? Lt : Li, j0 = cc * DP_CH, nj = min(DP_CH, L - j0);
+        if (n != cur_n || mod != cur_mod) {
+          if (cur_n >= 0) flush();
+          cur_n = n;
+          cur_mod = mod;
+          slot0 = cc;
+          m_run = -INFINITY;
+          l_run = 0.f;
+#pragma unroll
+          for (int i = 0; i < CPT; i++) cacc[i] = 0.f;
+          const float* sp = S + (long long)n * ldS + mod * E;
+          const float* wp = p.w_att + mod * E;
+#pragma unroll
+          for (int k = 0; k < KV; k++) {
+            sreg[k] = __ldcg(reinterpret_cast<const float4*>(sp + lane * 4 + 128 * k));
+            wreg[k] = ld4(wp + lane * 4 + 128 * k);
+          }
+          beta = p.beta_att[mod];
+        }
+        const unsigned sH = q & (DP_SLOTS - 1), rH = q / DP_SLOTS;
+        const unsigned sV = (q + 1) & (DP_SLOTS - 1), rV = (q + 1) / DP_SLOTS;
+        const float* Hs = gring + sH * SLOT;
+        const float* Vs = gring + sV * SLOT;
+        mbar_wait(&gfull[sH], rH & 1);
+        float* eb = ge + par * DP_CH;
+        if (gw < nj) {
+          const float* hp = Hs + gw * E;
+          float acc = 0.f;
+#pragma unroll
+          for (int k = 0; k < KV; k++) {
+            const float4 hv = ld4(hp + lane * 4 + 128 * k);
+            acc = fmaf(wreg[k].x, tanh_fast<TC>(hv.x + sreg[k].x), acc);
+            acc = fmaf(wreg[k].y, tanh_fast<TC>(hv.y + sreg[k].y), acc);
+            acc = fmaf(wreg[k].z, tanh_fast<TC>(hv.z + sreg[k].z), acc);
+            acc = fmaf(wreg[k].w, tanh_fast<TC>(hv.w + sreg[k].w), acc);
+          }
+          acc = warp_sum(acc) + beta;
+          if (lane == 0) {
+            eb[gw] = acc;
+            (mod ? al_tr : al_img)[(long long)n * L + j0 + gw] = acc;   // raw energy; P2b normalises
+          }
+        } else if (lane == 0) {
+          eb[gw] = -INFINITY;
+        }
+        named_bar_sync(1 + grp, DP_GRP);
+        if (lane == 0) mbar_arrive(&gempty[sH]);        // every warp of the group is past its H reads
+        const float ej = lane < DP_CH ? eb[lane] : -INFINITY;
+        const float m_new = fmaxf(m_run, warp_max(ej));
+        const float scale = expf(m_run - m_new);
+        const float pj = expf(ej - m_new);
+        l_run = l_run * scale + warp_sum(pj);
+        m_run = m_new;
+#pragma unroll
+        for (int i = 0; i < CPT; i++) cacc[i] *= scale;
+        mbar_wait(&gfull[sV], rV & 1);
+        if (nj == DP_CH) {
+#pragma unroll
+          for (int j = 0; j < DP_CH; j++) {
+            const float pr = __shfl_sync(FULL, pj, j);
+#pragma unroll
+            for (int i = 0; i < CPT; i++) cacc[i] = fmaf(pr, Vs[j * E + gt + 256 * i], cacc[i]);
+          }
+        } else {
+          for (int j = 0; j < nj; j++) {
+            const float pr = __shfl_sync(FULL, pj, j);
+#pragma unroll
+            for (int i = 0; i < CPT; i++) cacc[i] = fmaf(pr, Vs[j * E + gt + 256 * i], cacc[i]);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&gempty[sV]);
+      }
+      if (cur_n >= 0) flush();
+    }
+    it += (unsigned)(g_hi - g_lo);
+    grid_barrier(a.bar, epoch);
+    stamp(t, 2);
+    // ================================================================ P2b: combine partials per (row, modality)
+    for (int seg = c; seg < 2 * N; seg += G) {
+      const int n = seg >> 1, mod = seg & 1;
+      const int L = mod ? Lt : Li, cnt = mod ? gm.cpt : gm.cpi;      // cnt <= 16 (L <= 128)
+      const long long base = (long long)n * gm.cpr + (mod ? gm.cpi : 0);
+      // lane i holds partial i: every warp computes the same (M, weights) redundantly, loads in parallel
+      const float pl = lane < cnt ? __ldcg(a.PL + base + lane) : 0.f;
+      const float pm = (lane < cnt && pl > 0.f) ? __ldcg(a.PM + base + lane) : -INFINITY;
+      const float M = warp_max(pm);
+      const float wgt = pl > 0.f ? expf(pm - M) : 0.f;
+      const float inv = 1.0f / warp_sum(pl * wgt);
+      const unsigned valid = __ballot_sync(FULL, pl > 0.f);
+      float wv[16];
+#pragma unroll
+      for (int i = 0; i < 16; i++) wv[i] = __shfl_sync(FULL, wgt, i);
+      for (int x = tid; x < E; x += DP_THREADS) {
+        float pc[16];
+#pragma unroll
+        for (int i = 0; i < 16; i++) pc[i] = ((valid >> i) & 1u) ? __ldcg(a.PC + (base + i) * E + x) : 0.f;
+        float cv = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; i++) cv = fmaf(wv[i], pc[i], cv);
+        cv *= inv;
+        if (mod) cv += p.b_tl[x];
+        C[((long long)n * 2 + mod) * E + x] = cv;
+      }
+      float* al = (mod ? al_tr : al_img) + (long long)n * L;
+      for (int j = tid; j < L; j += DP_THREADS) al[j] = expf(__ldcg(al + j) - M) * inv;
+    }
+    grid_barrier(a.bar, epoch);
+    stamp(t, 3);
+    // ================================================================ P3: HC = C We_mm^T (own modality rows, own columns)
+    for (int r0 = 0; r0 < N; r0 += DP_MB) {
+      const int rows = min(DP_MB, N - r0);
+      dp_product<TC, DP_NT3>(C + ((long long)r0 * 2 + o.m3) * E, 2 * E, rows, E, W3, PE, Xb, Rp);
+      for (int i = tid; i < rows * o.n3; i += DP_THREADS) {
+        const int r = i / o.n3, j = i - r * o.n3;
+        HC[((long long)(r0 + r) * 2 + o.m3) * E + o.e_lo3 + j] = dp_rsum<TC, DP_NT3 * 8>(Rp, r, j);
+      }
+      __syncthreads();
+    }
+    grid_barrier(a.bar, epoch);
+    stamp(t, 4);
+    // ================================================================ P4: multimodal attention -> U ; closes step t-1
+    for (int n = c; n < N; n += G) {
+      const int b = n / Wn;
+      const float* Mk[4];
+      const float* HMk[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        Mk[k] = dp_mm_row(p.Mst, C, b, n, k, E);
+        HMk[k] = dp_mm_row(p.HMst, HC, b, n, k, E);
+      }
+      float e[4] = {0.f, 0.f, 0.f, 0.f};
+      float mv[CPT][4], hv[CPT][4];      // M rows and their projections of this thread's columns
+      if (tid < DP_GRP) {
+#pragma unroll
+        for (int i = 0; i < CPT; i++) {
+          const int x = tid + 256 * i;
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            const bool on = (mod_mask >> k) & 1;
+            hv[i][k] = on ? __ldcg(HMk[k] + x) : 0.f;
+            mv[i][k] = on ? __ldcg(Mk[k] + x) : 0.f;
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < CPT; i++) {
+          const int x = tid + 256 * i;
+          const float sx = __ldcg(S + (long long)n * ldS + 2 * E + x), wx = p.w_att[2 * E + x];
+#pragma unroll
+          for (int k = 0; k < 4; k++)
+            if ((mod_mask >> k) & 1) e[k] = fmaf(wx, tanh_acc(hv[i][k] + sx), e[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) e[k] = warp_sum(e[k]);
+        if (lane == 0)
+#pragma unroll
+          for (int k = 0; k < 4; k++) red[warp * 4 + k] = e[k];
+      } else if (warp == 8 && t > 0) {
+        float yp = 0.f;
+        for (int i = lane; i < G; i += 32) yp += __ldcg(a.ypart + (long long)i * N + n);
+        yp = warp_sum(yp);
+        if (lane == 0) {
+          const float yh = yp + p.b_fc[0];
+          p.yhat[(long long)n * T + t - 1] = yh;
+          const int forced = mask_dev ? (int)((*mask_dev >> (t - 1)) & 1u) : (int)((p.tf_mask >> (t - 1)) & 1u);
+          p.xin[(long long)t * N + n] = (forced && p.y) ? p.y[(long long)n * T + t - 1] : yh;
+        }
+      }
+      __syncthreads();
+      if (tid < DP_GRP) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          float v = 0.f;
+#pragma unroll
+          for (int w = 0; w < 8; w++) v += red[w * 4 + k];
+          e[k] = v;
+        }
+        const float beta = p.beta_att[2];
+        float m = -INFINITY;
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+          if ((mod_mask >> k) & 1) {
+            e[k] += beta;
+            m = fmaxf(m, e[k]);
+          }
+        float sum = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          e[k] = ((mod_mask >> k) & 1) ? expf(e[k] - m) : 0.f;
+          sum += e[k];
+        }
+        const float inv = 1.0f / sum;
+#pragma unroll
+        for (int k = 0; k < 4; k++) e[k] *= inv;
+        if (tid == 0)
+#pragma unroll
+          for (int k = 0; k < 4; k++) p.alpha_mm[((long long)t * N + n) * 4 + k] = e[k];
+#pragma unroll
+        for (int i = 0; i < CPT; i++) {
+          const int x = tid + 256 * i;
+          float u = 0.f;
+#pragma unroll
+          for (int k = 0; k < 4; k++)
+            if ((mod_mask >> k) & 1) u += mv[i][k] + e[k] * (byproj ? hv[i][k] : mv[i][k]);
+          U[(long long)n * E + x] = u;
+        }
+      }
+      __syncthreads();
+    }
+    grid_barrier(a.bar, epoch);
+    stamp(t, 5);
+    // ================================================================ P5: [CTX | GI] = U [W_me ; W']^T ; P6: gates
+    for (int r0 = 0; r0 < N; r0 += DP_MB) {
+      const int rows = min(DP_MB, N - r0);
+      dp_product<TC, DP_NT5>(U + (long long)r0 * E, E, rows, E, W5, PE, Xb, Rp);
+      for (int i = tid; i < rows * o.nx; i += DP_THREADS) {
+        const int r = i / o.nx, j = i - r * o.nx;
+        CTX[(long long)(r0 + r) * E + o.x_lo + j] = dp_rsum<TC, DP_NT5 * 8>(Rp, r, j) + p.b_me[o.x_lo + j];
+      }
+      {   // gates: 4 lanes per row, one hidden unit each (nu <= DP_MAXU = 4)
+        const int r = tid >> 2, u = tid & 3;
+        const bool act = tid < DP_CONS && r < rows && u < o.nu;
+        float yp = 0.f;
+        if (act) {
+          const int n = r0 + r, uu = o.u_lo + u;
+          const float x = __ldcg(p.xin + (long long)t * N + n);
+          const float* gh = S + (long long)n * ldS + 3 * E;
+          const float ghr = __ldcg(gh + uu), ghz = __ldcg(gh + H + uu), ghn = __ldcg(gh + 2 * H + uu);
+          const float hp = __ldcg(h + (long long)n * H + uu);
+          float gi[3];
+#pragma unroll
+          for (int g3 = 0; g3 < 3; g3++)
+            gi[g3] = dp_rsum<TC, DP_NT5 * 8>(Rp, r, o.nx + g3 * o.nu + u) + a.bp[g3 * H + uu] + x * p.w_x[g3 * H + uu];
+          const float rg = sigmoid_full(gi[0] + ghr);
+          const float zg = sigmoid_full(gi[1] + ghz);
+          const float cg = tanh_full(gi[2] + rg * ghn);
+          const float hn = (1.f - zg) * cg + zg * hp;
+          float* rzn = p.RZN + ((long long)t * N + n) * 3 * H;
+          rzn[uu] = rg;
+          rzn[H + uu] = zg;
+          rzn[2 * H + uu] = cg;
+          p.h_all[((long long)(t + 1) * N + n) * H + uu] = hn;
+          yp = p.w_fc[uu] * hn;
+        }
+        if (tid < DP_CONS) {
+          yp += __shfl_xor_sync(FULL, yp, 1);
+          yp += __shfl_xor_sync(FULL, yp, 2);
+          if (u == 0 && r < rows) a.ypart[(long long)c * N + r0 + r] = yp;
+        }
+      }
+      __syncthreads();
+    }
+    grid_barrier(a.bar, epoch);
+    stamp(t, 6);
+  }
+  // ------------------------------------------------------------------ close the last step: yhat_{T-1}
+  for (int n = c; n < N; n += G) {
+    if (warp == 0) {
+      float yp = 0.f;
+      for (int i = lane; i < G; i += 32) yp += __ldcg(a.ypart + (long long)i * N + n);
+      yp = warp_sum(yp);
+      if (lane == 0) {
+        const float yh = yp + p.b_fc[0];
+        p.yhat[(long long)n * T + T - 1] = yh;
+        const int forced = mask_dev ? (int)((*mask_dev >> (T - 1)) & 1u) : (int)((p.tf_mask >> (T - 1)) & 1u);
+        p.xin[(long long)T * N + n] = (forced && p.y) ? p.y[(long long)n * T + T - 1] : yh;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host side
+static bool g_dp_enabled = true;
+
+static size_t dp_scratch(bool tc) {   // product staging inside the ring area
+  return sizeof(float) * ((size_t)dp_stages(tc) * DP_MB * DP_XP + (size_t)(tc ? 2 : 4) * DP_MB * DP_NT1 * 8);
+}
+static size_t dp_smem(int E, int H, bool tc) {
+  const size_t w = sizeof(float) * ((size_t)DP_NT1 * 8 * (H + 4) + (size_t)(DP_NT3 + DP_NT5) * 8 * (E + 4));
+  size_t ring = sizeof(float) * (size_t)2 * DP_SLOTS * DP_CH * E;
+  if (dp_scratch(tc) > ring) ring = dp_scratch(tc);
+  return 128 + w + 128 + ring + 2 * 2 * DP_SLOTS * 8 + sizeof(float) * (4 * DP_CH + 64) + sizeof(int) * (DP_NT1 + DP_NT5) * 8;
+}
+static int dp_grid() {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  return sms < DP_MAXG ? sms : DP_MAXG;
+}
+
+static bool dp_supported(const v2f_decode_params* p) {
+  if (!g_dp_enabled || !p->persist_ws) return false;
+  if (p->variant == 1 || p->T < 1) return false;
+  if ((p->mod_mask & 0b1010) != 0b1010) return false;                 // image and trend attention both on
+  if (p->E != 256 && p->E != 512) return false;
+  if (p->H % DP_KALIGN != 0 || p->H < DP_KALIGN || p->H > 512) return false;
+  if (!p->attn_ws) return false;
+  int dev = 0, coop = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return false;
+  cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+  if (!coop) return false;
+  const int G = dp_grid();
+  if (G < 2) return false;
+  for (int c = 0; c < G; c++) {
+    const DpOwn o = dp_own(c, G, p->E, p->H);
+    if (o.n1 > DP_NT1 * 8 || o.n3 > DP_NT3 * 8 || o.n5 > DP_NT5 * 8 || o.nu < 1 || o.nu > DP_MAXU || o.na < 1 || o.nx < 1 || o.n3 < 1)
+      return false;
+  }
+  if (dp_smem(p->E, p->H, p->precision != 0) > 227 * 1024) return false;
+  return true;
+}
+
+long long decode_persist_ws_floats(int N, int E, int H, int T) {
+  // W' [3H,E] | b' [3H] | W_me^T [E,E] (tensor-core mode staging) | ypart [G,N] | barrier slots | stamps (2 per u64)
+  return (long long)3 * H * E + 3 * H + (long long)E * E + (long long)DP_MAXG * N + DP_BAR + 2LL * T * DP_STAMPS + 64;
+}
+
+static int g_dp_stamps = 0;
+
+template <int CPT, bool TC>
+static int dp_launch(const DpArgs& a, int G, size_t smem, cudaStream_t s) {
+  static bool attr = false;
+  auto kern = decode_persist_fwd_kernel<CPT, TC>;
+  if (!attr) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+      return V2F_ERR_LAUNCH;
+    attr = true;
+  }
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, DP_THREADS, smem) != cudaSuccess || per_sm < 1)
+    return V2F_ERR_UNSUPPORTED;
+  void* params[] = {(void*)&a};
+  prof_begin(V2F_K_DECODE_PERSIST_FWD, s);
+  const cudaError_t e = cudaLaunchCooperativeKernel((void*)kern, dim3(G), dim3(DP_THREADS), params, smem, s);
+  prof_end(V2F_K_DECODE_PERSIST_FWD, s);
+  if (e != cudaSuccess) return V2F_ERR_LAUNCH;
+  ++g_v2f_launches;
+  return V2F_OK;
+}
+
+// Returns V2F_ERR_UNSUPPORTED (and launches nothing) when the configuration is outside the persistent
+// kernel's envelope: the caller then takes the step-per-launch path.
+int decode_persist_fwd(const v2f_decode_params* p, cudaStream_t s) {
+  if (!dp_supported(p)) return V2F_ERR_UNSUPPORTED;
+  const int N = p->N, E = p->E, H = p->H, T = p->T;
+  const int G = dp_grid();
+  float* ws = p->persist_ws;
+  float* Wp = ws;
+  float* bp = Wp + (long long)3 * H * E;
+  float* WmeT = bp + 3 * H;
+  float* ypart = WmeT + (long long)E * E;
+  unsigned* bar = reinterpret_cast<unsigned*>(ypart + (long long)DP_MAXG * N);
+  unsigned long long* stamps = reinterpret_cast<unsigned long long*>(bar + DP_BAR);
+  // W' = W_ihc W_me, b' = W_ihc b_me + b_ih
+  if (p->precision != 0) {
+    V2F_TRY(v2f_transpose(E, E, p->W_me, E, 1, WmeT, E, 1, (void*)s));
+    V2F_TRY(v2f_gemm_tc(1, 3 * H, E, E, p->W_ihc, E, WmeT, E, Wp, E, nullptr, 0.f, 4, 1, (void*)s));
+  } else {
+    V2F_TRY(v2f_gemm_f32(0, 0, 3 * H, E, E, p->W_ihc, E, 0, p->W_me, E, 0, Wp, E, 0, 1, nullptr, 0.f, 0, (void*)s));
+  }
+  V2F_TRY(v2f_gemm_f32(0, 1, 1, 3 * H, E, p->b_me, E, 0, p->W_ihc, E, 0, bp, 3 * H, 0, 1, p->b_ih, 0.f, 0, (void*)s));
+  const DpGeom gm = dp_geom(N, p->Li, p->Lt);
+  DpArgs a;
+  a.p = *p;
+  a.Wp = Wp;
+  a.bp = bp;
+  a.ypart = ypart;
+  a.bar = bar;
+  a.PM = p->attn_ws;
+  a.PL = a.PM + gm.total;
+  a.PC = a.PL + gm.total;
+  a.stamps = g_dp_stamps ? stamps : nullptr;
+  cudaMemsetAsync(bar, 0, DP_BAR * sizeof(unsigned), s);
+  cudaMemsetAsync(a.PL, 0, sizeof(float) * (size_t)gm.total, s);
+  const size_t smem = dp_smem(E, H, p->precision != 0);
+  if (E == 512) {
+    if (p->precision != 0) return dp_launch<2, true>(a, G, smem, s);
+    return dp_launch<2, false>(a, G, smem, s);
+  }
+  if (p->precision != 0) return dp_launch<1, true>(a, G, smem, s);
+  return dp_launch<1, false>(a, G, smem, s);
+}
+
+}  // namespace v2f
+
+// A/B switch: 0 routes v2f_decode_fwd through the step-per-launch path again (default 1).
+extern "C" int v2f_decode_persistent_enable(int on) {
+  v2f::g_dp_enabled = on != 0;
+  return V2F_OK;
+}
+// 1: CTA 0 records globaltimer stamps at the phase boundaries of every step into the workspace
+// (read back with v2f_decode_persist_stamps); profiling only.
+extern "C" int v2f_decode_persist_stamps_enable(int on) {
+  v2f::g_dp_stamps = on != 0;
+  return V2F_OK;
+}
+extern "C" long long v2f_decode_persist_ws_floats(int N, int E, int H, int T) {
+  if (N <= 0 || E <= 0 || H <= 0 || T <= 0) return 0;
+  return v2f::decode_persist_ws_floats(N, E, H, T);
+}
+// Byte offset of the stamp table [T, 8] (unsigned long long, ns) inside persist_ws.
+extern "C" long long v2f_decode_persist_stamps_offset(int N, int E, int H) {
+  return (long long)sizeof(float) * ((long long)3 * H * E + 3 * H + (long long)E * E + (long long)v2f::DP_MAXG * N + v2f::DP_BAR);
+}

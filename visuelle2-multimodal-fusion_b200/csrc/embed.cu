@@ -10,7 +10,7 @@
 #include "common.cuh"
 
 long long g_v2f_launches = 0;
-extern "C" int v2f_version(void) { return 2; }
+extern "C" int v2f_version(void) { return 3; }
 extern "C" long long v2f_launch_count(void) { return g_v2f_launches; }
 
 namespace v2f {

@@ -596,6 +596,10 @@ static size_t attn_smem(int E, bool bwd) {
 
 using namespace v2f;
 
+namespace v2f {
+int decode_persist_fwd(const v2f_decode_params* p, cudaStream_t s);   // decode_persist.cu
+}
+
 #define NT(M, N, K, A, lda, B, ldb, C, ldc, bias, beta) V2F_TRY(gemm_nt(gx, M, N, K, A, lda, B, ldb, C, ldc, bias, beta))
 #define NN(M, N, K, A, lda, B, ldb, BT, ldbt, C, ldc, beta) \
   V2F_TRY(gemm_nn(gx, M, N, K, A, lda, B, ldb, BT, ldbt, C, ldc, beta))
@@ -618,6 +622,10 @@ extern "C" int v2f_decode_fwd(const v2f_decode_params* p, void* st) {
   if (gru) {
     copy_kernel<<<(N + 255) / 256, 256, 0, s>>>(N, p->x0, p->xin);
     V2F_CHECK_LAUNCH();
+  }
+  {   // the whole loop as one persistent cooperative launch when the configuration allows
+    const int rc = decode_persist_fwd(p, s);
+    if (rc != V2F_ERR_UNSUPPORTED) return rc;
   }
   for (int t = 0; t < T; t++) {
     const float* h = p->h_all + (long long)t * N * H;

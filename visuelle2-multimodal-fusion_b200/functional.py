@@ -471,6 +471,7 @@ def embed(temporal, Wt, bt, tables, idx, drop=None):
 # --------------------------------------------------------------------------- fused decoder
 VARIANT_210, VARIANT_21, VARIANT_DEMAND = 0, 1, 2
 STREAM_ATTENTION = True      # TMA-staged streaming attention kernels when the dims allow (E % 256 == 0)
+PERSISTENT_DECODE = True     # whole decode loop as one cooperative launch (csrc/decode_persist.cu) when the dims allow
 
 
 class _Decode(torch.autograd.Function):
@@ -528,6 +529,8 @@ class _Decode(torch.autograd.Function):
             xin=_f32(T + 1, N, device=dev, zero=True))
         if STREAM_ATTENTION and E % 256 == 0 and E <= 1024:
             keep["attn_ws"] = _f32(N * ((Li + 7) // 8 + (Lt + 7) // 8) * (2 * E + 2), device=dev)
+            if PERSISTENT_DECODE and gru and E in (256, 512):
+                keep["persist_ws"] = _f32(_lib.lib().v2f_decode_persist_ws_floats(N, E, H, T), device=dev)
         for k, v in keep.items():
             setattr(p, k, ptr(v, allow_none=True))
         p.tf_mask_dev = ptr(tf_dev, torch.int32, allow_none=True)
