@@ -152,11 +152,15 @@ int v2f_decode_bwd(const v2f_decode_params* p, void* stream);
 long long v2f_decode_persist_ws_floats(int N, int E, int H, int T);
 /* A/B switch (default 1): 0 forces the step-per-launch path even when persist_ws is given. */
 int v2f_decode_persistent_enable(int on);
-/* Profiling: CTA 0 of the persistent decoder stamps %globaltimer (ns) at its phase boundaries,
- * [T][8] unsigned long long at byte offset v2f_decode_persist_stamps_offset(N,E,H) of persist_ws:
- * 0 step start, 1 after P1 (S product), 2 after P2 (attention sweep), 3 after the combine, 4 after P3 (HC),
- * 5 after P4 (multimodal attention), 6 after P5/P6 (embedder + GRU gates).                          */
+/* Profiling: CTA 0 of the persistent decoder stamps %globaltimer (ns) around its phases,
+ * [T][16] unsigned long long at byte offset v2f_decode_persist_stamps_offset(N,E,H) of persist_ws:
+ * stamp 2k = phase k starts (after the previous grid barrier), 2k+1 = CTA 0 finished phase k's work (before the
+ * barrier), k = 0 P1 (S product), 1 P2 (attention sweep), 2 combine, 3 P3 (HC), 4 P4 (multimodal attention),
+ * 5 P5/P6 (embedder + GRU gates); stamp 12 = step end.                                              */
 int v2f_decode_persist_stamps_enable(int on);
+/* Timing experiments only (results become invalid): bit 0 skips the activation loads of the products,
+ * bit 1 their MMAs.  Default 0.                                                                   */
+int v2f_decode_persist_debug(int bits);
 long long v2f_decode_persist_stamps_offset(int N, int E, int H);
 
 /* ------------------------------------------------------------------------------------------

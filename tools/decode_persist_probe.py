@@ -26,6 +26,9 @@ def main():
     data = tuple(t.cuda() for t in data)
     feat = feat.cuda()
     lib = _lib.lib()
+    dbg = int(os.environ.get("DP_DBG", "0"))
+    if dbg:
+        lib.v2f_decode_persist_debug(dbg)
     # capture the persist workspace of the last forward to read the stamps
     holder = {}
     orig = Fv._f32
@@ -77,14 +80,19 @@ def main():
     want = lib.v2f_decode_persist_ws_floats(N, E, H, T)
     ws = [t for t in holder["last"] if t.numel() == want][-1]
     off = lib.v2f_decode_persist_stamps_offset(N, E, H) // 4
-    st = ws[off:off + 2 * T * 8].cpu().view(torch.int64).view(T, 8)
+    st = ws[off:off + 2 * T * 16].cpu().view(torch.int64).view(T, 16)
     names = ["P1 S-product", "P2 attention", "P2b combine", "P3 HC-product", "P4 mm-attn", "P5/6 embed+gates"]
-    tot = [0.0] * 6
+    work, wait = [0.0] * 6, [0.0] * 6
     for t in range(T):
-        d = [(int(st[t, k + 1]) - int(st[t, k])) / 1e3 for k in range(6)]
-        tot = [x + y for x, y in zip(tot, d)]
-        print(f"step {t}: " + "  ".join(f"{n}={v:.1f}us" for n, v in zip(names, d)))
-    print("mean per step: " + "  ".join(f"{n}={v / T:.1f}us" for n, v in zip(names, tot)),
+        w = [(int(st[t, 2 * k + 1]) - int(st[t, 2 * k])) / 1e3 for k in range(6)]
+        b = [(int(st[t, 2 * k + 2]) - int(st[t, 2 * k + 1])) / 1e3 for k in range(6)]
+        work = [x + y for x, y in zip(work, w)]
+        wait = [x + y for x, y in zip(wait, b)]
+        if t in (0, T - 1):
+            print(f"step {t}: " + "  ".join(f"{n}={x:.1f}+{y:.1f}us" for n, x, y in zip(names, w, b)))
+    tot = [x + y for x, y in zip(work, wait)]
+    print("mean per step (CTA 0: work + barrier wait): " +
+          "  ".join(f"{n}={x / T:.1f}+{y / T:.1f}us" for n, x, y in zip(names, work, wait)),
           f" | step total {sum(tot) / T:.1f} us")
     bytes_step = N * 4 * (2 * 100 + 2 * 52) * 512 + N * 4 * (5 * 512 + 100 + 52 + 4)
     print(f"attention phase: {bytes_step / 1e6:.2f} MB per step -> {bytes_step / (tot[1] / T * 1e-6) / 1e9:.0f} GB/s")

@@ -130,7 +130,24 @@ __device__ __forceinline__ void merge_partials(int C, int c, int nblk, const flo
   __shared__ double red[2][FIN_Y][33];
   double s0 = 0.0, q0 = 0.0, s1 = 0.0, q1 = 0.0;
   if (c < C) {
+    // partials b = y, y+32, y+64, ...: eight of them (16 independent loads) are issued before the first add, so the
+    // merge is not a chain of dependent L2 round trips (it was 19 of them for 592 blocks)
     int b = threadIdx.y;
+    for (; b + 7 * FIN_Y < nblk; b += 8 * FIN_Y) {
+      float vs[8], vq[8];
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        vs[k] = part[((long long)(b + k * FIN_Y) * 2) * C + c];
+        vq[k] = part[((long long)(b + k * FIN_Y) * 2 + 1) * C + c];
+      }
+#pragma unroll
+      for (int k = 0; k < 8; k += 2) {
+        s0 += (double)vs[k];
+        q0 += (double)vq[k];
+        s1 += (double)vs[k + 1];
+        q1 += (double)vq[k + 1];
+      }
+    }
     for (; b + FIN_Y < nblk; b += 2 * FIN_Y) {
       const float a0 = part[((long long)b * 2) * C + c], a1 = part[((long long)b * 2 + 1) * C + c];
       const float b0 = part[((long long)(b + FIN_Y) * 2) * C + c], b1 = part[((long long)(b + FIN_Y) * 2 + 1) * C + c];
@@ -335,9 +352,11 @@ bn_bwd_reduce_kernel(long long R, int C, const uint4* __restrict__ dy, const uin
 
 // dgamma = sum dz*xhat, dbeta = sum dz; coefficients of the elementwise pass:
 //   dx = a * (dz - m1 - xhat * m2),  a = gamma*rstd, m1 = dbeta/R, m2 = dgamma/R   (training)
-//   dx = a * dz                                                                      (eval)
+//      = a * dz + k1 * x + k0,       k1 = -a*rstd*m2, k0 = -a*m1 - k1*mean        (three coefficients per channel)
+//   dx = a * dz                                                                      (eval: k1 = k0 = 0)
 __global__ void bn_bwd_finalize_kernel(long long R, int C, int nblk, const float* __restrict__ part,
-                                       const float* __restrict__ gamma, const float* __restrict__ rstd,
+                                       const float* __restrict__ gamma, const float* __restrict__ mean,
+                                       const float* __restrict__ rstd,
                                        int training, float* __restrict__ dgamma, float* __restrict__ dbeta,
                                        float* __restrict__ coef) {
   const int c = blockIdx.x * 32 + threadIdx.x;
@@ -346,44 +365,45 @@ __global__ void bn_bwd_finalize_kernel(long long R, int C, int nblk, const float
   if (c >= C || threadIdx.y != 0) return;
   dbeta[c] = (float)S;
   dgamma[c] = (float)Q;
-  coef[c] = gamma[c] * rstd[c];
-  coef[C + c] = training ? (float)(S / (double)R) : 0.f;
-  coef[2 * C + c] = training ? (float)(Q / (double)R) : 0.f;
+  const float a = gamma[c] * rstd[c];
+  const float m1 = training ? (float)(S / (double)R) : 0.f, m2 = training ? (float)(Q / (double)R) : 0.f;
+  const float k1 = -a * rstd[c] * m2;
+  coef[c] = a;
+  coef[C + c] = k1;
+  coef[2 * C + c] = -a * m1 - k1 * mean[c];
 }
 
-// dx = a * (dz - m1 - xhat*m2); dz either stored by the reduce pass (HAVE_DZ) or rebuilt from dy & y.
+// dx = a * dz + k1 * x + k0; dz either stored by the reduce pass (HAVE_DZ) or rebuilt from dy & y.
 template <bool RELU, bool HAVE_DZ>
-__global__ void __launch_bounds__(BN_THREADS)
+__global__ void __launch_bounds__(BN_THREADS, 4)
 bn_bwd_elemt_kernel(long long R, int C, const uint4* __restrict__ dy, const uint4* __restrict__ x,
-                    const uint4* __restrict__ y, const float* __restrict__ mean,
-                    const float* __restrict__ rstd, const float* __restrict__ coef, uint4* __restrict__ dx) {
+                    const uint4* __restrict__ y, const float* __restrict__ coef, uint4* __restrict__ dx) {
   const Geo g = make_geo(C);
   const int vcol = threadIdx.x % g.CVB, roff = threadIdx.x / g.CVB;
   if (roff >= g.RB) return;
+  constexpr int UN = (RELU && !HAVE_DZ) ? 2 : 3;      // 16-byte loads in flight per thread: 6
   for (int v0 = 0; v0 < g.CV; v0 += g.CVB) {
     const int v = v0 + vcol;
-    float mu[8], rs[8], a[8], m1[8], m2[8];
+    float a[8], k1[8], k0[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) {
       const int c = v * 8 + i;
-      mu[i] = mean[c];
-      rs[i] = rstd[c];
       a[i] = coef[c];
-      m1[i] = coef[C + c];
-      m2[i] = coef[2 * C + c];
+      k1[i] = coef[C + c];
+      k0[i] = coef[2 * C + c];
     }
     const long long stride = (long long)gridDim.x * g.RB;
     long long r = (long long)blockIdx.x * g.RB + roff;
-    for (; r + stride < R; r += 2 * stride) {
-      uint4 ud[2], ux[2], uy[2];
+    for (; r + (UN - 1) * stride < R; r += UN * stride) {
+      uint4 ud[UN], ux[UN], uy[UN];
 #pragma unroll
-      for (int k = 0; k < 2; k++) {
+      for (int k = 0; k < UN; k++) {
         ud[k] = ldg_stream(dy + (r + k * stride) * g.CV + v);
         ux[k] = ldg_stream(x + (r + k * stride) * g.CV + v);
         if (RELU && !HAVE_DZ) uy[k] = ldg_stream(y + (r + k * stride) * g.CV + v);
       }
 #pragma unroll
-      for (int k = 0; k < 2; k++) {
+      for (int k = 0; k < UN; k++) {
         float d[8], xv[8], yv[8];
         unpack8(ud[k], d);
         unpack8(ux[k], xv);
@@ -391,7 +411,7 @@ bn_bwd_elemt_kernel(long long R, int C, const uint4* __restrict__ dy, const uint
 #pragma unroll
         for (int i = 0; i < 8; i++) {
           if (RELU && !HAVE_DZ && !(yv[i] > 0.f)) d[i] = 0.f;
-          d[i] = a[i] * (d[i] - m1[i] - (xv[i] - mu[i]) * rs[i] * m2[i]);
+          d[i] = fmaf(a[i], d[i], fmaf(k1[i], xv[i], k0[i]));
         }
         dx[(r + k * stride) * g.CV + v] = pack8(d);
       }
@@ -404,7 +424,7 @@ bn_bwd_elemt_kernel(long long R, int C, const uint4* __restrict__ dy, const uint
 #pragma unroll
       for (int i = 0; i < 8; i++) {
         if (RELU && !HAVE_DZ && !(yv[i] > 0.f)) d[i] = 0.f;
-        d[i] = a[i] * (d[i] - m1[i] - (xv[i] - mu[i]) * rs[i] * m2[i]);
+        d[i] = fmaf(a[i], d[i], fmaf(k1[i], xv[i], k0[i]));
       }
       dx[r * g.CV + v] = pack8(d);
     }
@@ -535,14 +555,14 @@ extern "C" int v2f_bn2d_act_bwd(long long R, int C, const void* dy, const void* 
 #undef BN_RED
   prof_end(V2F_K_BN_BWD_REDUCE, s);
   V2F_CHECK_LAUNCH();
-  bn_bwd_finalize_kernel<<<(C + 31) / 32, dim3(32, FIN_Y), 0, s>>>(R, C, nblk, part, gamma, save_rstd, training, dgamma, dbeta, coef);
+  bn_bwd_finalize_kernel<<<(C + 31) / 32, dim3(32, FIN_Y), 0, s>>>(R, C, nblk, part, gamma, save_mean, save_rstd, training, dgamma, dbeta, coef);
   V2F_CHECK_LAUNCH();
   prof_begin(V2F_K_BN_BWD_ELEMT, s);
   prof_bytes(V2F_K_BN_BWD_ELEMT, tb * (3 + ((relu && !dz) ? 1 : 0)));
-  if (have_dz && !relu) bn_bwd_elemt_kernel<false, false><<<nblk, BN_THREADS, 0, s>>>(R, C, (const uint4*)dz, xp, yp, save_mean, save_rstd, coef, dxp);
-  else if (relu && dz) bn_bwd_elemt_kernel<true, true><<<nblk, BN_THREADS, 0, s>>>(R, C, (const uint4*)dz, xp, yp, save_mean, save_rstd, coef, dxp);
-  else if (relu) bn_bwd_elemt_kernel<true, false><<<nblk, BN_THREADS, 0, s>>>(R, C, dyp, xp, yp, save_mean, save_rstd, coef, dxp);
-  else bn_bwd_elemt_kernel<false, false><<<nblk, BN_THREADS, 0, s>>>(R, C, dyp, xp, yp, save_mean, save_rstd, coef, dxp);
+  if (have_dz && !relu) bn_bwd_elemt_kernel<false, false><<<nblk, BN_THREADS, 0, s>>>(R, C, (const uint4*)dz, xp, yp, coef, dxp);
+  else if (relu && dz) bn_bwd_elemt_kernel<true, true><<<nblk, BN_THREADS, 0, s>>>(R, C, (const uint4*)dz, xp, yp, coef, dxp);
+  else if (relu) bn_bwd_elemt_kernel<true, false><<<nblk, BN_THREADS, 0, s>>>(R, C, dyp, xp, yp, coef, dxp);
+  else bn_bwd_elemt_kernel<false, false><<<nblk, BN_THREADS, 0, s>>>(R, C, dyp, xp, yp, coef, dxp);
   prof_end(V2F_K_BN_BWD_ELEMT, s);
   V2F_CHECK_LAUNCH();
   return V2F_OK;

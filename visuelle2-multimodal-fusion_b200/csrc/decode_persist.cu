@@ -43,24 +43,26 @@ constexpr int DP_THREADS = DP_CONS + 64;    // + one producer warp per group
 constexpr int DP_CH = 8;                    // positions per chunk
 constexpr int DP_SLOTS = 4;                 // ring slots per group; a slot holds one operand (H or V) of one chunk
 constexpr int DP_MB = 128;                  // rows per product row block
-constexpr int DP_KC = 32;                   // K chunk of the streamed activations
+constexpr int DP_KC = 64;                   // K chunk of the streamed activations
 constexpr int DP_XP = DP_KC + 4;            // its shared-memory pitch (conflict-free fragment loads)
 constexpr int DP_KALIGN = 64;               // K (= E, H) must be a multiple of this
 constexpr int DP_NT1 = 3, DP_NT3 = 1, DP_NT5 = 2;   // 8-column MMA tiles owned per CTA in P1 / P3 / P5
 constexpr int DP_MAXG = 192;                // upper bound on the grid (ypart rows, barrier slots)
 constexpr int DP_MAXU = 4;                  // hidden units per CTA (gate phase: 4 lanes per row)
-__host__ __device__ constexpr int dp_stages(bool tc) { return tc ? 5 : 4; }   // activation chunks in the cp.async ring
-constexpr int DP_STAMPS = 8;                // globaltimer stamps per step (profiling)
-constexpr int DP_BAR = 256;                 // barrier region of the workspace (unsigned words)
+__host__ __device__ constexpr int dp_stages(bool tc) { return tc ? 3 : 2; }   // activation chunks in the cp.async ring
+constexpr int DP_STAMPS = 16;               // globaltimer stamps per step (profiling): phase k end-of-work 2k+1, after barrier 2k+2
+constexpr int DP_NCTR = 8;                  // arrival counters of the grid barrier (one 128-byte line each)
+constexpr int DP_BAR = DP_NCTR * 32;        // barrier region of the workspace (unsigned words)
 
 struct DpArgs {
   v2f_decode_params p;
   const float* Wp;        // [3H,E] = W_ihc W_me
   const float* bp;        // [3H]   = W_ihc b_me + b_ih
   float* ypart;           // [G,N] per-CTA partial decoder_fc dot products of the current step
-  unsigned* bar;          // grid-barrier slots [DP_MAXG], monotonic epochs (zeroed before launch)
+  unsigned* bar;          // grid-barrier counters (zeroed before launch)
   float *PM, *PL, *PC;    // attention partials [N,cpr], [N,cpr] (zeroed before launch), [N,cpr,E]
   unsigned long long* stamps;   // optional [T, DP_STAMPS] globaltimer stamps written by CTA 0
+  int dbg;                      // timing experiments only (results invalid): bit 0 skip the activation loads, bit 1 skip the MMAs
 };
 
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
@@ -69,22 +71,26 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
   return t;
 }
 
-// Grid barrier without atomics: CTA c publishes the epoch in its own slot (release), thread i of every CTA
-// spins on slot i (acquire).  Slots are monotonic, zeroed before the launch; every spin is bounded.
-__device__ __forceinline__ void grid_barrier(unsigned* slots, unsigned& epoch) {
+// Grid barrier: arrivals are spread over DP_NCTR monotonic counters on separate 128-byte lines (same-address
+// atomics serialise at ~14 ns each: 148 arrivals on one word cost 2 us, 19 per word 0.26 us); lanes 0..7 of
+// warp 0 poll one counter each and add them up -- a sum of monotonic counters read one by one is a lower
+// bound of the arrivals, so ">= epoch * G" is safe.  Zeroed before the launch; every spin is bounded.
+__device__ __forceinline__ void grid_barrier(unsigned* ctr, unsigned& epoch) {
   __syncthreads();
   ++epoch;
-  if (threadIdx.x == 0) {
-    __threadfence();
-    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(slots + blockIdx.x), "r"(epoch) : "memory");
-  }
-  if (threadIdx.x < gridDim.x) {
-    const unsigned* sp = slots + threadIdx.x;
-    unsigned v;
+  if (threadIdx.x < 32) {
+    if (threadIdx.x == 0)
+      asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr + (blockIdx.x % DP_NCTR) * 32) : "memory");
+    const unsigned target = epoch * gridDim.x;
+    const unsigned* cp = ctr + (threadIdx.x % DP_NCTR) * 32;
     const long long t0 = clock64();
     for (;;) {
-      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(sp) : "memory");
-      if (v >= epoch) break;
+      unsigned v = 0;
+      if (threadIdx.x < DP_NCTR) asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(cp) : "memory");
+#pragma unroll
+      for (int o = DP_NCTR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+      v = __shfl_sync(FULL, v, 0);
+      if (v >= target) break;
       if (clock64() - t0 > (1LL << 31)) __trap();   // ~1 s: a protocol bug must not hang the device
     }
   }
@@ -101,6 +107,16 @@ __device__ __forceinline__ void dp_mma(float* d, const uint32_t* a, uint32_t b0,
       "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// ldmatrix on 32-bit data: an "8x8 b16" matrix is 8 rows of 16 bytes = an 8x4 tile of tf32 words; thread i
+// receives the word (row i/4, column i%4), i.e. exactly the m16n8k8 A / B fragment element it owns.
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const float* addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(smem_u32(addr)));
+}
+__device__ __forceinline__ void ldsm_x2(uint32_t& r0, uint32_t& r1, const float* addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(smem_u32(addr)));
 }
 __device__ __forceinline__ float dp_dot4(const float4& a, const float4& b, float acc) {
   acc = fmaf(a.x, b.x, acc);
@@ -140,19 +156,25 @@ __host__ __device__ inline DpOwn dp_own(int c, int G, int E, int H) {
 // epilogue adds them.  All threads of the CTA must call it.
 template <bool TC, int NT>
 __device__ __forceinline__ void dp_product(const float* __restrict__ X, long long ldx, int rows, int K,
-                                           const float* Wsm, int P, float* Xb, float* Rp) {
+                                           const float* Wsm, int P, float* Xb, float* Rp, int dbg = 0) {
   constexpr int NW = NT * 8;
   constexpr int NST = dp_stages(TC);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nch = K / DP_KC;
+  // every CTA reads the same X: start each CTA at a different K chunk so that the 148 SMs do not all ask the
+  // same few L2 lines at the same time (K chunks can be accumulated in any order)
+  const int rot = blockIdx.x % nch;
+  auto kchunk = [&](int ch) { const int k = ch + rot; return k >= nch ? k - nch : k; };
   auto load_chunk = [&](int ch) {
+    if (dbg & 1) return;
     float* dst = Xb + (ch % NST) * DP_MB * DP_XP;
+    const int kc = kchunk(ch);
     for (int i = tid; i < DP_MB * (DP_KC / 4); i += DP_THREADS) {
       const int r = i / (DP_KC / 4), k4 = i - r * (DP_KC / 4);
       float* d = dst + r * DP_XP + 4 * k4;
       if (r < rows) {
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(d)),
-                     "l"(X + (long long)r * ldx + ch * DP_KC + 4 * k4)
+                     "l"(X + (long long)r * ldx + kc * DP_KC + 4 * k4)
                      : "memory");
       } else {
         *reinterpret_cast<float4*>(d) = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -173,27 +195,38 @@ __device__ __forceinline__ void dp_product(const float* __restrict__ X, long lon
     if (ch + NST - 1 < nch) load_chunk(ch + NST - 1);
     asm volatile("cp.async.commit_group;" ::: "memory");
     const float* cur = Xb + (ch % NST) * DP_MB * DP_XP;
-    if (warp < DP_CONS / 32) {
+    const int kc = kchunk(ch);
+    if (warp < DP_CONS / 32 && !(dbg & 2)) {
       if (TC) {
-        const int mt = warp & 7, kh = warp >> 3, g = lane >> 2, tt = lane & 3;
-        const float* xa = cur + (16 * mt + g) * DP_XP + tt;
-        const float* wb = Wsm + g * P + ch * DP_KC + tt;
+        // warp = (16-row tile mt, K half kh of the chunk).  Fragments come in with ldmatrix: A (activations,
+        // consumed as tf32 = the hardware drops the low mantissa bits) x4 per k-step, B (weights, rounded to
+        // nearest tf32 when they were staged) x4 per pair of 8-column tiles.
+        const int mt = warp & 7, kh = warp >> 3, mi = lane >> 3, rr = lane & 7;
+        const float* xa = cur + (16 * mt + rr + (mi & 1) * 8) * DP_XP + (mi >> 1) * 4;
+        const float* wb = Wsm + ((mi >> 1) * 8 + rr) * P + kc * DP_KC + (mi & 1) * 4;
 #pragma unroll
         for (int ks = 0; ks < DP_KC / 16; ks++) {
           const int k0 = (kh * (DP_KC / 16) + ks) * 8;
           uint32_t af[4];
-          af[0] = dp_tf32(xa[k0]);
-          af[1] = dp_tf32(xa[8 * DP_XP + k0]);
-          af[2] = dp_tf32(xa[k0 + 4]);
-          af[3] = dp_tf32(xa[8 * DP_XP + k0 + 4]);
+          ldsm_x4(af, xa + k0);
+          uint32_t bf[NT + (NT & 1)][2];
 #pragma unroll
-          for (int n = 0; n < NT; n++)
-            dp_mma(acc + 4 * n, af, __float_as_uint(wb[n * 8 * P + k0]), __float_as_uint(wb[n * 8 * P + k0 + 4]));
+          for (int n = 0; n + 1 < NT; n += 2) {
+            uint32_t t4[4];
+            ldsm_x4(t4, wb + n * 8 * P + k0);
+            bf[n][0] = t4[0];
+            bf[n][1] = t4[1];
+            bf[n + 1][0] = t4[2];
+            bf[n + 1][1] = t4[3];
+          }
+          if (NT & 1) ldsm_x2(bf[NT - 1][0], bf[NT - 1][1], wb + (NT - 1) * 8 * P + k0);
+#pragma unroll
+          for (int n = 0; n < NT; n++) dp_mma(acc + 4 * n, af, bf[n][0], bf[n][1]);
         }
       } else {
         const int row = tid & 127, kq = tid >> 7;
         const float* xr = cur + row * DP_XP + kq * (DP_KC / 4);
-        const float* wr = Wsm + ch * DP_KC + kq * (DP_KC / 4);
+        const float* wr = Wsm + kc * DP_KC + kq * (DP_KC / 4);
 #pragma unroll
         for (int k = 0; k < DP_KC / 4; k += 4) {
           const float4 x4 = *reinterpret_cast<const float4*>(xr + k);
@@ -364,7 +397,7 @@ decode_persist_fwd_kernel(const __grid_constant__ DpArgs a) {
     // ================================================================ P1: S = h Wcat^T + bcat (own columns)
     for (int r0 = 0; r0 < N; r0 += DP_MB) {
       const int rows = min(DP_MB, N - r0);
-      dp_product<TC, DP_NT1>(h + (long long)r0 * H, H, rows, H, W1, PH, Xb, Rp);
+      dp_product<TC, DP_NT1>(h + (long long)r0 * H, H, rows, H, W1, PH, Xb, Rp, a.dbg);
       for (int i = tid; i < rows * o.n1; i += DP_THREADS) {
         const int r = i / o.n1, j = i - r * o.n1, col = cmap1[j];
         S[(long long)(r0 + r) * ldS + col] = dp_rsum<TC, DP_NT1 * 8>(Rp, r, j) + p.bcat[col];
@@ -373,8 +406,9 @@ decode_persist_fwd_kernel(const __grid_constant__ DpArgs a) {
     }
     // the ring area was just used through the generic proxy; the bulk copies of P2 write it through the async proxy
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    grid_barrier(a.bar, epoch);
     stamp(t, 1);
+    grid_barrier(a.bar, epoch);
+    stamp(t, 2);
     // ================================================================ P2: streaming additive attention
     if (warp >= 16) {
       if (lane == 0) {
@@ -492,8 +526,9 @@ decode_persist_fwd_kernel(const __grid_constant__ DpArgs a) {
       if (cur_n >= 0) flush();
     }
     it += (unsigned)(g_hi - g_lo);
+    stamp(t, 3);
     grid_barrier(a.bar, epoch);
-    stamp(t, 2);
+    stamp(t, 4);
     // ================================================================ P2b: combine partials per (row, modality)
     for (int seg = c; seg < 2 * N; seg += G) {
       const int n = seg >> 1, mod = seg & 1;
@@ -523,20 +558,22 @@ decode_persist_fwd_kernel(const __grid_constant__ DpArgs a) {
       float* al = (mod ? al_tr : al_img) + (long long)n * L;
       for (int j = tid; j < L; j += DP_THREADS) al[j] = expf(__ldcg(al + j) - M) * inv;
     }
+    stamp(t, 5);
     grid_barrier(a.bar, epoch);
-    stamp(t, 3);
+    stamp(t, 6);
     // ================================================================ P3: HC = C We_mm^T (own modality rows, own columns)
     for (int r0 = 0; r0 < N; r0 += DP_MB) {
       const int rows = min(DP_MB, N - r0);
-      dp_product<TC, DP_NT3>(C + ((long long)r0 * 2 + o.m3) * E, 2 * E, rows, E, W3, PE, Xb, Rp);
+      dp_product<TC, DP_NT3>(C + ((long long)r0 * 2 + o.m3) * E, 2 * E, rows, E, W3, PE, Xb, Rp, a.dbg);
       for (int i = tid; i < rows * o.n3; i += DP_THREADS) {
         const int r = i / o.n3, j = i - r * o.n3;
         HC[((long long)(r0 + r) * 2 + o.m3) * E + o.e_lo3 + j] = dp_rsum<TC, DP_NT3 * 8>(Rp, r, j);
       }
       __syncthreads();
     }
+    stamp(t, 7);
     grid_barrier(a.bar, epoch);
-    stamp(t, 4);
+    stamp(t, 8);
     // ================================================================ P4: multimodal attention -> U ; closes step t-1
     for (int n = c; n < N; n += G) {
       const int b = n / Wn;
@@ -625,12 +662,13 @@ decode_persist_fwd_kernel(const __grid_constant__ DpArgs a) {
       }
       __syncthreads();
     }
+    stamp(t, 9);
     grid_barrier(a.bar, epoch);
-    stamp(t, 5);
+    stamp(t, 10);
     // ================================================================ P5: [CTX | GI] = U [W_me ; W']^T ; P6: gates
     for (int r0 = 0; r0 < N; r0 += DP_MB) {
       const int rows = min(DP_MB, N - r0);
-      dp_product<TC, DP_NT5>(U + (long long)r0 * E, E, rows, E, W5, PE, Xb, Rp);
+      dp_product<TC, DP_NT5>(U + (long long)r0 * E, E, rows, E, W5, PE, Xb, Rp, a.dbg);
       for (int i = tid; i < rows * o.nx; i += DP_THREADS) {
         const int r = i / o.nx, j = i - r * o.nx;
         CTX[(long long)(r0 + r) * E + o.x_lo + j] = dp_rsum<TC, DP_NT5 * 8>(Rp, r, j) + p.b_me[o.x_lo + j];
@@ -668,8 +706,9 @@ decode_persist_fwd_kernel(const __grid_constant__ DpArgs a) {
       }
       __syncthreads();
     }
+    stamp(t, 11);
     grid_barrier(a.bar, epoch);
-    stamp(t, 6);
+    stamp(t, 12);
   }
   // ------------------------------------------------------------------ close the last step: yhat_{T-1}
   for (int n = c; n < N; n += G) {
@@ -738,6 +777,7 @@ long long decode_persist_ws_floats(int N, int E, int H, int T) {
 }
 
 static int g_dp_stamps = 0;
+static int g_dp_dbg = 0;
 
 template <int CPT, bool TC>
 static int dp_launch(const DpArgs& a, int G, size_t smem, cudaStream_t s) {
@@ -792,6 +832,7 @@ int decode_persist_fwd(const v2f_decode_params* p, cudaStream_t s) {
   a.PL = a.PM + gm.total;
   a.PC = a.PL + gm.total;
   a.stamps = g_dp_stamps ? stamps : nullptr;
+  a.dbg = g_dp_dbg;
   cudaMemsetAsync(bar, 0, DP_BAR * sizeof(unsigned), s);
   cudaMemsetAsync(a.PL, 0, sizeof(float) * (size_t)gm.total, s);
   const size_t smem = dp_smem(E, H, p->precision != 0);
@@ -814,6 +855,10 @@ extern "C" int v2f_decode_persistent_enable(int on) {
 // (read back with v2f_decode_persist_stamps); profiling only.
 extern "C" int v2f_decode_persist_stamps_enable(int on) {
   v2f::g_dp_stamps = on != 0;
+  return V2F_OK;
+}
+extern "C" int v2f_decode_persist_debug(int bits) {   // timing experiments only, see DpArgs::dbg
+  v2f::g_dp_dbg = bits;
   return V2F_OK;
 }
 extern "C" long long v2f_decode_persist_ws_floats(int N, int E, int H, int T) {

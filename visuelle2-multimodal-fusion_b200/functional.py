@@ -4,6 +4,7 @@ PyTorch is plumbing here: it owns device memory (caller-allocated workspaces), t
 the autograd graph between fused regions.  All arithmetic runs in libv2f_b200.so.
 """
 import ctypes
+import os
 
 import torch
 
@@ -471,7 +472,9 @@ def embed(temporal, Wt, bt, tables, idx, drop=None):
 # --------------------------------------------------------------------------- fused decoder
 VARIANT_210, VARIANT_21, VARIANT_DEMAND = 0, 1, 2
 STREAM_ATTENTION = True      # TMA-staged streaming attention kernels when the dims allow (E % 256 == 0)
-PERSISTENT_DECODE = True     # whole decode loop as one cooperative launch (csrc/decode_persist.cu) when the dims allow
+# whole decode loop as one cooperative launch (csrc/decode_persist.cu) when the dims allow; V2F_PERSISTENT_DECODE=0 is
+# the A/B switch of bench.py / tools
+PERSISTENT_DECODE = os.environ.get("V2F_PERSISTENT_DECODE", "1") != "0"
 
 
 class _Decode(torch.autograd.Function):
