@@ -186,6 +186,7 @@ def run_reference(args):
 def run_product(args):
     import torch.distributed as dist
     from visuelle2_multimodal_fusion_b200 import _lib
+    import visuelle2_multimodal_fusion_b200.functional as Fv
     from visuelle2_multimodal_fusion_b200.ddp import GradReducer
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -407,6 +408,18 @@ def run_product(args):
             step_head_prof(i)
         torch.cuda.synchronize()
         _lib.prof_enable(False)
+        # phase times inside the persistent decoder (a phase of a persistent kernel has no launch to bracket with CUDA
+        # events): CTA 0 stamps %globaltimer at its phase boundaries during one extra forward
+        phases = None
+        if Fv.PERSISTENT_DECODE:
+            _lib.lib().v2f_decode_persist_stamps_enable(1)
+            Fv.KEEP_LAST_PERSIST_WS = True
+            try:
+                step_head_prof(0)
+                phases = Fv.persist_phase_times()
+            finally:
+                Fv.KEEP_LAST_PERSIST_WS = False
+                _lib.lib().v2f_decode_persist_stamps_enable(0)
         peak, peak_src = _peaks()
         N = B
         tile_bytes = N * 4 * (2 * LI + 2 * LT) * E
@@ -414,7 +427,9 @@ def run_product(args):
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
         tj = json.load(open(tpath)) if os.path.isfile(tpath) else {}
-        for name, kid, bytes_per_launch in (("attn_fwd_kernel", _lib.K_ATTN_FWD, tile_bytes + small),
+        for name, kid, bytes_per_launch in (("decode_persist_fwd_kernel", _lib.K_DECODE_PERSIST_FWD,
+                                             OUT_LEN * (tile_bytes + small)),
+                                            ("attn_fwd_kernel", _lib.K_ATTN_FWD, tile_bytes + small),
                                             ("attn_bwd_kernel", _lib.K_ATTN_BWD, tile_bytes + small),
                                             ("tilegrad_kernel", _lib.K_TILEGRAD, None)):
             tot, n = _lib.prof_read(kid)
@@ -431,6 +446,19 @@ def run_product(args):
                           "peak_source": peak_src,
                           "timing": "CUDA events on the launching stream around each launch, separate eager pass with the "
                                     "host running ahead of the GPU (spin kernel before forward / backward)"}
+        if "decode_persist_fwd_kernel" in roof and phases:
+            r = roof["decode_persist_fwd_kernel"]
+            r["note"] = ("one cooperative launch = all %d decode steps: per step six phases (three weight-stationary "
+                         "products out of shared memory, the HBM/L2-bound attention sweep, two row-local phases) "
+                         "separated by grid barriers; achieved/frac are the by-the-book whole-launch figures "
+                         "(algorithmic tile bytes of all steps / launch duration), attention_phase is the sweep alone" % OUT_LEN)
+            r["phases_us_per_step"] = {k: {"work": round(w, 2), "barrier_wait": round(b, 2)} for k, (w, b) in phases.items()}
+            w, b = phases["P2 attention sweep"]
+            pa = (tile_bytes + small) / ((w + b) * 1e-6) / 1e9
+            r["attention_phase"] = {"algorithmic_bytes_per_step": tile_bytes + small, "us_per_step": round(w + b, 2),
+                                    "achieved": pa, "frac": pa / peak, "unit": "GB/s",
+                                    "timing": "%globaltimer stamps of CTA 0 around the phase including its closing grid "
+                                              "barrier, mean over the steps of one launch"}
         model.image_encoder.cnn = cnn
         model.image_encoder.backbone_dtype = saved_dtype
         # ---- the BatchNorm / add / ReLU sweeps of the trunk (csrc/bn_act.cu): full-model steps, CUDA events
@@ -462,6 +490,7 @@ def run_product(args):
                 _lib.prof_read(kid)          # drop the head spans of this pass
 
     torch.cuda.set_stream(default_stream)
+    roof_main = "decode_persist_fwd_kernel" if "decode_persist_fwd_kernel" in roof else "attn_fwd_kernel"
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
@@ -502,8 +531,8 @@ def run_product(args):
             "head_only": {"value": (B * world * args.steps / (head_ms * 1e-3)) if head_ms else None,
                           "unit": "samples/s", "ms_per_step": head_ms / args.steps if head_ms else None,
                           "note": "feature maps [B,2048,10,10] in; everything libv2f_b200 covers"},
-            "roofline": roof.get("attn_fwd_kernel"),
-            "roofline_other": {k: v for k, v in roof.items() if k != "attn_fwd_kernel"},
+            "roofline": roof.get(roof_main),
+            "roofline_other": {k: v for k, v in roof.items() if k != roof_main},
             "cpu_baseline": cpu,
         }
         print(json.dumps(out), flush=True)

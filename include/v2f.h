@@ -315,6 +315,33 @@ int v2f_bn2d_relu_maxpool_fwd(int N, int H, int W, int C, const void* x, const f
                               float momentum, float eps, void* y, float* save_mean, float* save_rstd,
                               float* scale_shift, float* part, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Multi-tensor Adafactor step (csrc/adafactor.cu): configure_optimizers of the LightningModules,
+ * models/CrossAttnRNN210.py:229-230, models/GTM_Visuelle2.py:264-266 (fairseq Adafactor with scale_parameter,
+ * relative_step, warmup_init; beta1 = None, weight_decay = 0).  One descriptor per trainable tensor that has a
+ * gradient; ``kind``: 0 vector (state sq[numel]), 1 small matrices (nmat matrices of R x C, R,C <= 4: convolution
+ * weights), 2 big matrices (nmat x R x C, factored states row[nmat,R], col[nmat,C]).  Work-unit tables (int4, device):
+ *   vec_units   (desc, first element, count <= 1024, 0)     small_units (desc, first matrix, count <= 256, 0)
+ *   row_units   (desc, matrix, row, 0)                      col_units   (desc, matrix, first column of a 256 strip, 0)
+ * grads: device array of n_desc gradient pointers, refreshed by the caller every step; acc: [n_desc][2] doubles.
+ * beta2t = 1 - step^decay_rate and rel_step = min(1e-6 step, 1/sqrt(step)) (or the fixed lr) are computed by the
+ * caller, as the reference does on the host.                                                              */
+typedef struct v2f_af_desc {
+  float *p, *row, *col, *sq, *rms;
+  long long numel;
+  int nmat, R, C, kind;
+} v2f_af_desc;
+typedef struct v2f_adafactor_plan {
+  const v2f_af_desc* descs;
+  const void* grads;
+  double* acc;
+  const void *vec_units, *small_units, *row_units, *col_units;
+  int n_desc, n_vec, n_small, n_rows, n_cols;
+  float eps1, eps2, clip_threshold;
+  int scale_parameter;
+} v2f_adafactor_plan;
+int v2f_adafactor_step(const v2f_adafactor_plan* plan, double beta2t, double rel_step, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

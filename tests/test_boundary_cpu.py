@@ -128,3 +128,23 @@ def test_gtm_family_same_seed_same_init_as_reference(variant):
     assert set(rs) == set(ms)
     for k in rs:
         assert torch.equal(rs[k], ms[k]), k
+
+
+def test_fused_adafactor_interface_and_no_cpu_fallback():
+    """optim.Adafactor keeps the constructor contract of the fairseq / transformers optimizer and refuses CPU tensors."""
+    import pytest
+    import torch
+    from visuelle2_multimodal_fusion_b200.optim import Adafactor
+    p = torch.nn.Parameter(torch.zeros(4, 4))
+    with pytest.raises(ValueError):
+        Adafactor([p], lr=1e-3, relative_step=True)
+    with pytest.raises(ValueError):
+        Adafactor([p], lr=1e-3, relative_step=False, warmup_init=True)
+    with pytest.raises(NotImplementedError):
+        Adafactor([p], beta1=0.9)
+    opt = Adafactor([p], scale_parameter=True, relative_step=True, warmup_init=True, lr=None)
+    assert opt.param_groups[0]["lr"] is None
+    opt.step()                                   # no gradient anywhere: nothing to do
+    p.grad = torch.ones(4, 4)
+    with pytest.raises(RuntimeError):
+        opt.step()                               # CPU parameter: there is no fallback

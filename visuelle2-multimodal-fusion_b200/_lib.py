@@ -36,6 +36,20 @@ class DecodeParams(ctypes.Structure):
                 [(n, c_vp) for n in _PTRS] + [("ws_floats", c_ll), ("attn_ws", c_vp), ("tf_mask_dev", c_vp), ("persist_ws", c_vp)])
 
 
+class AfDesc(ctypes.Structure):
+    """Mirror of ``struct v2f_af_desc`` (include/v2f.h)."""
+    _fields_ = [("p", c_vp), ("row", c_vp), ("col", c_vp), ("sq", c_vp), ("rms", c_vp), ("numel", c_ll),
+                ("nmat", c_int), ("R", c_int), ("C", c_int), ("kind", c_int)]
+
+
+class AfPlan(ctypes.Structure):
+    """Mirror of ``struct v2f_adafactor_plan`` (include/v2f.h)."""
+    _fields_ = [("descs", c_vp), ("grads", c_vp), ("acc", c_vp), ("vec_units", c_vp), ("small_units", c_vp),
+                ("row_units", c_vp), ("col_units", c_vp), ("n_desc", c_int), ("n_vec", c_int), ("n_small", c_int),
+                ("n_rows", c_int), ("n_cols", c_int), ("eps1", c_float), ("eps2", c_float),
+                ("clip_threshold", c_float), ("scale_parameter", c_int)]
+
+
 def _declare(lib):
     lib.v2f_version.restype = c_int
     lib.v2f_launch_count.restype = c_ll
@@ -62,6 +76,8 @@ def _declare(lib):
     lib.v2f_prof_enable.argtypes = [c_int]
     lib.v2f_gru_persistent_enable.argtypes = [c_int]
     lib.v2f_gru_persistent_enable.restype = c_int
+    lib.v2f_adafactor_step.argtypes = [ctypes.POINTER(AfPlan), ctypes.c_double, ctypes.c_double, c_vp]
+    lib.v2f_adafactor_step.restype = c_int
     lib.v2f_decode_persistent_enable.argtypes = [c_int]
     lib.v2f_decode_persistent_enable.restype = c_int
     lib.v2f_decode_persist_stamps_enable.argtypes = [c_int]

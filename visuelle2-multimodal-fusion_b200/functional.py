@@ -477,6 +477,29 @@ STREAM_ATTENTION = True      # TMA-staged streaming attention kernels when the d
 PERSISTENT_DECODE = os.environ.get("V2F_PERSISTENT_DECODE", "1") != "0"
 
 
+KEEP_LAST_PERSIST_WS = False   # profiling: remember the persistent decoder's workspace (phase stamps live in it)
+_last_persist = []
+PERSIST_PHASES = ("P1 S-product", "P2 attention sweep", "P2b combine", "P3 HC-product", "P4 multimodal attention",
+                  "P5/P6 embedder + GRU gates")
+
+
+def persist_phase_times():
+    """Per-phase times (us, mean over the T steps, CTA 0's %globaltimer stamps) of the most recent persistent decode
+    forward run with v2f_decode_persist_stamps_enable(1) and KEEP_LAST_PERSIST_WS: {phase: (work_us, barrier_us)}."""
+    if not _last_persist:
+        return None
+    ws, (N, E, H, T, Li, Lt) = _last_persist
+    off = _lib.lib().v2f_decode_persist_stamps_offset(N, E, H) // 4
+    torch.cuda.synchronize()
+    st = ws[off:off + 2 * T * 16].cpu().view(torch.int64).view(T, 16)
+    out = {}
+    for k, name in enumerate(PERSIST_PHASES):
+        work = sum(int(st[t, 2 * k + 1]) - int(st[t, 2 * k]) for t in range(T)) / T / 1e3
+        wait = sum(int(st[t, 2 * k + 2]) - int(st[t, 2 * k + 1]) for t in range(T)) / T / 1e3
+        out[name] = (work, wait)
+    return out
+
+
 class _Decode(torch.autograd.Function):
     """The fused recurrent-attention decoder (v2f_decode_fwd / v2f_decode_bwd)."""
 
@@ -534,6 +557,8 @@ class _Decode(torch.autograd.Function):
             keep["attn_ws"] = _f32(N * ((Li + 7) // 8 + (Lt + 7) // 8) * (2 * E + 2), device=dev)
             if PERSISTENT_DECODE and gru and E in (256, 512):
                 keep["persist_ws"] = _f32(_lib.lib().v2f_decode_persist_ws_floats(N, E, H, T), device=dev)
+                if KEEP_LAST_PERSIST_WS:
+                    _last_persist[:] = [keep["persist_ws"], (N, E, H, T, Li, Lt)]
         for k, v in keep.items():
             setattr(p, k, ptr(v, allow_none=True))
         p.tf_mask_dev = ptr(tf_dev, torch.int32, allow_none=True)

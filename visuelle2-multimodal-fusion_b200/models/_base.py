@@ -41,11 +41,9 @@ except Exception:  # pragma: no cover - depends on the image
 
 def make_adafactor(params):
     """``Adafactor(scale_parameter=True, relative_step=True, warmup_init=True, lr=None)``
-    (models/CrossAttnRNN210.py:229-230); fairseq's when present, else the transformers port."""
-    try:
-        from fairseq.optim.adafactor import Adafactor
-    except Exception:
-        from transformers.optimization import Adafactor
+    (models/CrossAttnRNN210.py:229-230) as the multi-tensor CUDA step of this package (optim.Adafactor: same
+    algorithm, same state keys as fairseq's / transformers')."""
+    from ..optim import Adafactor
     return Adafactor(params, scale_parameter=True, relative_step=True, warmup_init=True, lr=None)
 
 
