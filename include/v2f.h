@@ -322,7 +322,7 @@ int v2f_bn2d_relu_maxpool_fwd(int N, int H, int W, int C, const void* x, const f
  * gradient; ``kind``: 0 vector (state sq[numel]), 1 small matrices (nmat matrices of R x C, R,C <= 4: convolution
  * weights), 2 big matrices (nmat x R x C, factored states row[nmat,R], col[nmat,C]).  Work-unit tables (int4, device):
  *   vec_units   (desc, first element, count <= 1024, 0)     small_units (desc, first matrix, count <= 256, 0)
- *   row_units   (desc, matrix, row, 0)                      col_units   (desc, matrix, first column of a 256 strip, 0)
+ *   row_units   (desc, matrix, row, 0)                      col_units   (desc, matrix, first column of a 32 strip, 0)
  * grads: device array of n_desc gradient pointers, refreshed by the caller every step; acc: [n_desc][2] doubles.
  * beta2t = 1 - step^decay_rate and rel_step = min(1e-6 step, 1/sqrt(step)) (or the fixed lr) are computed by the
  * caller, as the reference does on the host.                                                              */
@@ -330,13 +330,18 @@ typedef struct v2f_af_desc {
   float *p, *row, *col, *sq, *rms;
   long long numel;
   int nmat, R, C, kind;
+  /* kind 1 only: element (m, r, c) of the parameter AND of its gradient lives at
+   * (m / inner) * sO + (m % inner) * sI + r * sR + c * sC  -- row-major [O,I,R,C]: inner = I, (I*R*C, R*C, C, 1);
+   * channels_last convolution weights (the bf16 trunk keeps them so): (I*R*C, 1, C*I, I).  States stay row-major. */
+  int inner, pad_;
+  long long sO, sI, sR, sC;
 } v2f_af_desc;
 typedef struct v2f_adafactor_plan {
   const v2f_af_desc* descs;
   const void* grads;
   double* acc;
-  const void *vec_units, *small_units, *row_units, *col_units;
-  int n_desc, n_vec, n_small, n_rows, n_cols;
+  const void *vec_units, *small_units[3], *row_units, *col_units; /* small: [0] 1x1, [1] 3x3, [2] other shapes */
+  int n_desc, n_vec, n_small[3], n_rows, n_cols;
   float eps1, eps2, clip_threshold;
   int scale_parameter;
 } v2f_adafactor_plan;

@@ -26,14 +26,18 @@ def test_fused_adafactor_matches_transformers(kwargs):
     g = torch.Generator().manual_seed(5)
     ref_p = [torch.nn.Parameter(torch.randn(s, generator=g) * (0.02 + 0.3 * (i % 3))) for i, s in enumerate(SHAPES)]
     ref_p.append(torch.nn.Parameter(torch.randn(9, generator=g)))            # never receives a gradient
-    our_p = [torch.nn.Parameter(p.detach().clone().cuda()) for p in ref_p]
+    # 4-D tensors with more than one channel: channels_last on the device, like the convolution weights of the bf16 trunk
+    cl = lambda t: t.contiguous(memory_format=torch.channels_last) if (t.dim() == 4 and t.shape[1] > 1 and
+                                                                       1 < t.shape[2] * t.shape[3] <= 16) else t
+    our_p = [torch.nn.Parameter(cl(p.detach().clone().cuda())) for p in ref_p]
+    assert any(not p.is_contiguous() for p in our_p)
     ref, ours = Ref(ref_p, **kwargs), Adafactor(our_p, **kwargs)
     for step in range(6):
-        for rp, op in zip(ref_p[:-1], our_p[:-1]):
+        for i, (rp, op) in enumerate(zip(ref_p[:-1], our_p[:-1])):
             scale = 10.0 ** ((step % 3) - 2)                                   # exercises the update clipping
             gr = torch.randn(rp.shape, generator=g) * scale
             rp.grad = gr
-            op.grad = gr.clone().cuda()
+            op.grad = gr.clone().cuda() if (step + i) % 2 else cl(gr.clone().cuda())   # either layout may arrive
         ref.step()
         ours.step()
         ref.zero_grad()

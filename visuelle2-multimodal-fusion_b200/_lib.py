@@ -39,13 +39,14 @@ class DecodeParams(ctypes.Structure):
 class AfDesc(ctypes.Structure):
     """Mirror of ``struct v2f_af_desc`` (include/v2f.h)."""
     _fields_ = [("p", c_vp), ("row", c_vp), ("col", c_vp), ("sq", c_vp), ("rms", c_vp), ("numel", c_ll),
-                ("nmat", c_int), ("R", c_int), ("C", c_int), ("kind", c_int)]
+                ("nmat", c_int), ("R", c_int), ("C", c_int), ("kind", c_int), ("inner", c_int), ("pad_", c_int),
+                ("sO", c_ll), ("sI", c_ll), ("sR", c_ll), ("sC", c_ll)]
 
 
 class AfPlan(ctypes.Structure):
     """Mirror of ``struct v2f_adafactor_plan`` (include/v2f.h)."""
-    _fields_ = [("descs", c_vp), ("grads", c_vp), ("acc", c_vp), ("vec_units", c_vp), ("small_units", c_vp),
-                ("row_units", c_vp), ("col_units", c_vp), ("n_desc", c_int), ("n_vec", c_int), ("n_small", c_int),
+    _fields_ = [("descs", c_vp), ("grads", c_vp), ("acc", c_vp), ("vec_units", c_vp), ("small_units", c_vp * 3),
+                ("row_units", c_vp), ("col_units", c_vp), ("n_desc", c_int), ("n_vec", c_int), ("n_small", c_int * 3),
                 ("n_rows", c_int), ("n_cols", c_int), ("eps1", c_float), ("eps2", c_float),
                 ("clip_threshold", c_float), ("scale_parameter", c_int)]
 

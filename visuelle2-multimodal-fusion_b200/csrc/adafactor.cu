@@ -23,7 +23,8 @@ namespace v2f {
 
 constexpr int AF_THREADS = 256;
 constexpr int AF_DIM = 4;          // a "small" matrix has R <= 4 and C <= 4 (1x1 and 3x3 convolution kernels)
-constexpr int AF_VEC_CHUNK = 1024; // elements per CTA in the vector kernels
+constexpr int AF_COLSTRIP = 32;    // columns per CTA of the column-mean kernel
+constexpr int AF_ROWLANES = AF_THREADS / AF_COLSTRIP;
 
 struct AfHyper {
   float beta, omb;        // beta2t, 1 - beta2t
@@ -104,7 +105,9 @@ af_vec_kernel(const v2f_af_desc* __restrict__ descs, const float* const* __restr
 
 // ------------------------------------------------------------------------------------------ small matrices
 // unit: (desc, first matrix, count <= AF_THREADS); one thread per R x C matrix (R, C <= AF_DIM)
-template <bool APPLY>
+// RR, CC > 0: the matrix shape is known at compile time (1x1 and 3x3 convolution kernels are 99.9 % of the matrices;
+// a 1x1 "matrix" is one element: row = col, the row factor is exactly 1); 0: read it from the descriptor.
+template <bool APPLY, int RR, int CC>
 __global__ void __launch_bounds__(AF_THREADS)
 af_small_kernel(const v2f_af_desc* __restrict__ descs, const float* const* __restrict__ grads, double* __restrict__ acc,
                 const int4* __restrict__ units, AfHyper h) {
@@ -112,7 +115,8 @@ af_small_kernel(const v2f_af_desc* __restrict__ descs, const float* const* __res
   const int4 u = units[blockIdx.x];
   const v2f_af_desc d = descs[u.x];
   const float* g = grads[u.x];
-  const int R = d.R, C = d.C, RC = R * C;
+  constexpr int AF_DIM = RR > 0 ? (RR > CC ? RR : CC) : v2f::AF_DIM;
+  const int R = RR > 0 ? RR : d.R, C = CC > 0 ? CC : d.C;
   float lr = 0.f, cdiv = 1.f, rms = 0.f;
   if (APPLY) {
     step_scalars(d, acc + 2 * u.x, h, lr, cdiv, rms);
@@ -121,8 +125,10 @@ af_small_kernel(const v2f_af_desc* __restrict__ descs, const float* const* __res
   double sp = 0.0, su = 0.0;
   if ((int)threadIdx.x < u.z) {
     const long long m = (long long)u.y + threadIdx.x;
-    const float* gm = g + m * RC;
-    float* pm = d.p + m * RC;
+    const long long base = (m / d.inner) * d.sO + (m % d.inner) * d.sI;
+    const float* gm = g + base;
+    float* pm = d.p + base;
+    const long long sR = d.sR, sC = d.sC;
     float* rowm = d.row + m * R;
     float* colm = d.col + m * C;
     // R, C <= AF_DIM: fully unrolled with predicates so that everything stays in registers
@@ -130,7 +136,7 @@ af_small_kernel(const v2f_af_desc* __restrict__ descs, const float* const* __res
 #pragma unroll
     for (int r = 0; r < AF_DIM; r++)
 #pragma unroll
-      for (int c = 0; c < AF_DIM; c++) gv[r][c] = (r < R && c < C) ? gm[r * C + c] : 0.f;
+      for (int c = 0; c < AF_DIM; c++) gv[r][c] = (r < R && c < C) ? gm[r * sR + c * sC] : 0.f;
     if (!APPLY) {
 #pragma unroll
       for (int r = 0; r < AF_DIM; r++) {
@@ -176,7 +182,7 @@ af_small_kernel(const v2f_af_desc* __restrict__ descs, const float* const* __res
 #pragma unroll
       for (int c = 0; c < AF_DIM; c++)
         if (r < R && c < C) {
-          const int i = r * C + c;
+          const long long i = r * sR + c * sC;
           const float uu = gv[r][c] * (rowv[r] * colv[c]);
           if (!APPLY) {
             const float pv = pm[i];
@@ -198,7 +204,7 @@ af_small_kernel(const v2f_af_desc* __restrict__ descs, const float* const* __res
 }
 
 // ------------------------------------------------------------------------------------------ big matrices
-// row unit: (desc, matrix, row); column unit: (desc, matrix, first column of a 256-wide strip)
+// row unit: (desc, matrix, row); column unit: (desc, matrix, first column of a 32-wide strip)
 __global__ void __launch_bounds__(AF_THREADS)
 af_big_rowstat_kernel(const v2f_af_desc* __restrict__ descs, const float* const* __restrict__ grads,
                       double* __restrict__ acc, const int4* __restrict__ units, AfHyper h) {
@@ -225,30 +231,44 @@ af_big_rowstat_kernel(const v2f_af_desc* __restrict__ descs, const float* const*
   }
 }
 
+// CTA = 32 columns x 8 row lanes: thread (cl, rl) sums the rows r = rl (mod 8) of column u.z + cl, four loads in
+// flight; the 8 partials meet in shared memory.  (A thread per column alone left 3 CTAs with 1536 serial rows each
+// for the GRU weights.)
 __global__ void __launch_bounds__(AF_THREADS)
 af_big_colstat_kernel(const v2f_af_desc* __restrict__ descs, const float* const* __restrict__ grads,
                       const int4* __restrict__ units, AfHyper h) {
+  __shared__ float part[AF_ROWLANES][AF_COLSTRIP + 1];
   const int4 u = units[blockIdx.x];
   const v2f_af_desc d = descs[u.x];
-  const int c = u.z + threadIdx.x;
-  if (c >= d.C) return;
-  const float* g = grads[u.x] + (long long)u.y * d.R * d.C + c;
+  const int cl = threadIdx.x % AF_COLSTRIP, rl = threadIdx.x / AF_COLSTRIP;
+  const int c = u.z + cl;
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-  int r = 0;
-  for (; r + 3 < d.R; r += 4) {
-    const float a0 = g[(long long)r * d.C], a1 = g[(long long)(r + 1) * d.C], a2 = g[(long long)(r + 2) * d.C],
-                a3 = g[(long long)(r + 3) * d.C];
-    s0 += a0 * a0 + h.eps1;
-    s1 += a1 * a1 + h.eps1;
-    s2 += a2 * a2 + h.eps1;
-    s3 += a3 * a3 + h.eps1;
+  if (c < d.C) {
+    const float* g = grads[u.x] + (long long)u.y * d.R * d.C + c;
+    const long long st = (long long)AF_ROWLANES * d.C;
+    int r = rl;
+    for (; r + 3 * AF_ROWLANES < d.R; r += 4 * AF_ROWLANES) {
+      const float* gp = g + (long long)r * d.C;
+      const float a0 = gp[0], a1 = gp[st], a2 = gp[2 * st], a3 = gp[3 * st];
+      s0 += a0 * a0 + h.eps1;
+      s1 += a1 * a1 + h.eps1;
+      s2 += a2 * a2 + h.eps1;
+      s3 += a3 * a3 + h.eps1;
+    }
+    for (; r < d.R; r += AF_ROWLANES) {
+      const float a0 = g[(long long)r * d.C];
+      s0 += a0 * a0 + h.eps1;
+    }
   }
-  for (; r < d.R; r++) {
-    const float a0 = g[(long long)r * d.C];
-    s0 += a0 * a0 + h.eps1;
+  part[rl][cl] = (s0 + s1) + (s2 + s3);
+  __syncthreads();
+  if (rl == 0 && c < d.C) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < AF_ROWLANES; k++) s += part[k][cl];
+    float* col = d.col + (long long)u.y * d.C + c;
+    *col = *col * h.beta + (s / (float)d.R) * h.omb;
   }
-  float* col = d.col + (long long)u.y * d.C + c;
-  *col = *col * h.beta + (((s0 + s1) + (s2 + s3)) / (float)d.R) * h.omb;
 }
 
 // u = g * rsqrt(row[r] / mean(row)) * rsqrt(col[c]); APPLY: p -= lr u / cdiv, else accumulate sum u^2
@@ -293,7 +313,7 @@ using namespace v2f;
 extern "C" int v2f_adafactor_step(const v2f_adafactor_plan* pl, double beta2t, double rel_step, void* st) {
   V2F_REQUIRE(pl && pl->descs && pl->grads && pl->acc && pl->n_desc > 0, V2F_ERR_BAD_ARG);
   V2F_REQUIRE(pl->n_vec == 0 || pl->vec_units, V2F_ERR_BAD_ARG);
-  V2F_REQUIRE(pl->n_small == 0 || pl->small_units, V2F_ERR_BAD_ARG);
+  for (int k = 0; k < 3; k++) V2F_REQUIRE(pl->n_small[k] == 0 || pl->small_units[k], V2F_ERR_BAD_ARG);
   V2F_REQUIRE((pl->n_rows == 0 || pl->row_units) && (pl->n_cols == 0 || pl->col_units), V2F_ERR_BAD_ARG);
   cudaStream_t s = (cudaStream_t)st;
   AfHyper h;
@@ -307,7 +327,6 @@ extern "C" int v2f_adafactor_step(const v2f_adafactor_plan* pl, double beta2t, d
   const v2f_af_desc* D = pl->descs;
   const float* const* G = (const float* const*)pl->grads;
   const int4* VU = (const int4*)pl->vec_units;
-  const int4* SU = (const int4*)pl->small_units;
   const int4* RU = (const int4*)pl->row_units;
   const int4* CU = (const int4*)pl->col_units;
   if (cudaMemsetAsync(pl->acc, 0, sizeof(double) * 2 * (size_t)pl->n_desc, s) != cudaSuccess) return V2F_ERR_LAUNCH;
@@ -316,8 +335,16 @@ extern "C" int v2f_adafactor_step(const v2f_adafactor_plan* pl, double beta2t, d
     af_vec_kernel<false><<<pl->n_vec, AF_THREADS, 0, s>>>(D, G, pl->acc, VU, h);
     V2F_CHECK_LAUNCH();
   }
-  if (pl->n_small) {
-    af_small_kernel<false><<<pl->n_small, AF_THREADS, 0, s>>>(D, G, pl->acc, SU, h);
+  if (pl->n_small[0]) {
+    af_small_kernel<false, 1, 1><<<pl->n_small[0], AF_THREADS, 0, s>>>(D, G, pl->acc, (const int4*)pl->small_units[0], h);
+    V2F_CHECK_LAUNCH();
+  }
+  if (pl->n_small[1]) {
+    af_small_kernel<false, 3, 3><<<pl->n_small[1], AF_THREADS, 0, s>>>(D, G, pl->acc, (const int4*)pl->small_units[1], h);
+    V2F_CHECK_LAUNCH();
+  }
+  if (pl->n_small[2]) {
+    af_small_kernel<false, 0, 0><<<pl->n_small[2], AF_THREADS, 0, s>>>(D, G, pl->acc, (const int4*)pl->small_units[2], h);
     V2F_CHECK_LAUNCH();
   }
   if (pl->n_rows) {
@@ -333,8 +360,16 @@ extern "C" int v2f_adafactor_step(const v2f_adafactor_plan* pl, double beta2t, d
     af_vec_kernel<true><<<pl->n_vec, AF_THREADS, 0, s>>>(D, G, pl->acc, VU, h);
     V2F_CHECK_LAUNCH();
   }
-  if (pl->n_small) {
-    af_small_kernel<true><<<pl->n_small, AF_THREADS, 0, s>>>(D, G, pl->acc, SU, h);
+  if (pl->n_small[0]) {
+    af_small_kernel<true, 1, 1><<<pl->n_small[0], AF_THREADS, 0, s>>>(D, G, pl->acc, (const int4*)pl->small_units[0], h);
+    V2F_CHECK_LAUNCH();
+  }
+  if (pl->n_small[1]) {
+    af_small_kernel<true, 3, 3><<<pl->n_small[1], AF_THREADS, 0, s>>>(D, G, pl->acc, (const int4*)pl->small_units[1], h);
+    V2F_CHECK_LAUNCH();
+  }
+  if (pl->n_small[2]) {
+    af_small_kernel<true, 0, 0><<<pl->n_small[2], AF_THREADS, 0, s>>>(D, G, pl->acc, (const int4*)pl->small_units[2], h);
     V2F_CHECK_LAUNCH();
   }
   if (pl->n_rows) {

@@ -19,6 +19,12 @@ from ._lib import check, stream
 _SMALL_DIM = 4        # AF_DIM of csrc/adafactor.cu
 _VEC_CHUNK = 1024
 _THREADS = 256
+_COLSTRIP = 32      # AF_COLSTRIP
+
+
+def _strided_small(p):
+    """A dense 4-D small-matrix tensor in a non-row-major layout (channels_last convolution weights)."""
+    return p.dim() == 4 and _kind(tuple(p.shape)) == 1 and p.is_contiguous(memory_format=torch.channels_last)
 
 
 def _kind(shape):
@@ -68,13 +74,14 @@ class Adafactor(torch.optim.Optimizer):
         n = len(active)
         rms = torch.zeros(n, device=dev, dtype=torch.float32)
         descs = (_lib.AfDesc * n)()
-        vec, small, rows, cols = [], [], [], []
+        vec, small, rows, cols = [], ([], [], []), [], []
         for i, p in enumerate(active):
-            if not (p.is_cuda and p.dtype == torch.float32 and p.is_contiguous()):
-                raise RuntimeError("fused Adafactor needs contiguous fp32 CUDA parameters (no CPU fallback)")
-            st = self._init_state(p)
             shape = tuple(p.shape)
             kind = _kind(shape)
+            if not (p.is_cuda and p.dtype == torch.float32 and (p.is_contiguous() or _strided_small(p))):
+                raise RuntimeError("fused Adafactor needs fp32 CUDA parameters, contiguous or channels_last 4-D "
+                                   "convolution weights (no CPU fallback)")
+            st = self._init_state(p)
             d = descs[i]
             d.p, d.rms, d.numel, d.kind = p.data_ptr(), rms[i:i + 1].data_ptr(), p.numel(), kind
             for k in ("exp_avg_sq_row", "exp_avg_sq_col", "exp_avg_sq"):
@@ -94,14 +101,20 @@ class Adafactor(torch.optim.Optimizer):
                 d.row, d.col = st["exp_avg_sq_row"].data_ptr(), st["exp_avg_sq_col"].data_ptr()
                 d.nmat, d.R, d.C = nmat, R, C
                 if kind == 1:
+                    if p.is_contiguous():
+                        d.inner, d.sO, d.sI, d.sR, d.sC = 1, R * C, 0, C, 1
+                    else:                       # channels_last [O,I,R,C]
+                        d.inner = shape[1]
+                        d.sO, d.sI, d.sR, d.sC = p.stride()
                     m0 = np.arange(0, nmat, _THREADS, dtype=np.int64)
                     cnt = np.minimum(_THREADS, nmat - m0)
-                    small.append(np.stack([np.full_like(m0, i), m0, cnt, np.zeros_like(m0)], 1))
+                    cls = 0 if (R, C) == (1, 1) else (1 if (R, C) == (3, 3) else 2)
+                    small[cls].append(np.stack([np.full_like(m0, i), m0, cnt, np.zeros_like(m0)], 1))
                 else:
                     mm, rr = np.meshgrid(np.arange(nmat, dtype=np.int64), np.arange(R, dtype=np.int64), indexing="ij")
                     rows.append(np.stack([np.full(mm.size, i, np.int64), mm.ravel(), rr.ravel(),
                                           np.zeros(mm.size, np.int64)], 1))
-                    mm, cc = np.meshgrid(np.arange(nmat, dtype=np.int64), np.arange(0, C, _THREADS, dtype=np.int64),
+                    mm, cc = np.meshgrid(np.arange(nmat, dtype=np.int64), np.arange(0, C, _COLSTRIP, dtype=np.int64),
                                          indexing="ij")
                     cols.append(np.stack([np.full(mm.size, i, np.int64), mm.ravel(), cc.ravel(),
                                           np.zeros(mm.size, np.int64)], 1))
@@ -124,11 +137,16 @@ class Adafactor(torch.optim.Optimizer):
         keep["grads"] = torch.zeros(n, dtype=torch.int64, device=dev)
         keep["acc"] = torch.zeros(n, 2, dtype=torch.float64, device=dev)
         plan.descs, plan.grads, plan.acc = raw.data_ptr(), keep["grads"].data_ptr(), keep["acc"].data_ptr()
-        for name, parts in (("vec", vec), ("small", small), ("row", rows), ("col", cols)):
+        for name, parts in (("vec", vec), ("row", rows), ("col", cols)):
             t, cnt = table(parts)
             keep[name] = t
             setattr(plan, name + "_units", t.data_ptr() if t is not None else None)
-            setattr(plan, {"vec": "n_vec", "small": "n_small", "row": "n_rows", "col": "n_cols"}[name], cnt)
+            setattr(plan, {"vec": "n_vec", "row": "n_rows", "col": "n_cols"}[name], cnt)
+        for k in range(3):
+            t, cnt = table(small[k])
+            keep["small%d" % k] = t
+            plan.small_units[k] = t.data_ptr() if t is not None else None
+            plan.n_small[k] = cnt
         plan.n_desc = n
         plan.eps1, plan.eps2 = float(group["eps"][0]), float(group["eps"][1])
         plan.clip_threshold = float(group["clip_threshold"])
@@ -156,16 +174,23 @@ class Adafactor(torch.optim.Optimizer):
             if k["grads_ev"][turn] is not None:
                 k["grads_ev"][turn].synchronize()
             gh = k["grads_host"][turn]
-            for i, p in enumerate(active):
+            ptrs = []
+            for p in active:
                 g = p.grad
-                if g.is_sparse:
-                    raise RuntimeError("Adafactor does not support sparse gradients.")
-                if not (g.is_cuda and g.dtype == torch.float32 and g.is_contiguous()):
-                    g = p.grad = g.to(dtype=torch.float32).contiguous()
-                gh[i] = g.data_ptr()
+                if g.stride() != p.stride() or g.dtype != torch.float32 or not g.is_cuda:
+                    if g.is_sparse:
+                        raise RuntimeError("Adafactor does not support sparse gradients.")
+                    # strides of size-1 dims are arbitrary: two row-major tensors are the same layout whatever they say
+                    if g.dtype != torch.float32 or not g.is_cuda or not (p.is_contiguous() and g.is_contiguous()):
+                        g = g.to(device=p.device, dtype=torch.float32)
+                        if not (p.is_contiguous() and g.is_contiguous()):
+                            g = torch.empty_like(p).copy_(g)      # the parameter's memory layout (e.g. channels_last)
+                        p.grad = g
+                ptrs.append(g.data_ptr())
                 st = self.state[p]
                 st["step"] += 1
                 steps.add(st["step"])
+            gh.numpy()[:] = ptrs
             if len(steps) != 1:
                 raise RuntimeError("fused Adafactor: parameters of one group must share the step count")
             step = steps.pop()
