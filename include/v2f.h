@@ -316,6 +316,14 @@ int v2f_bn2d_relu_maxpool_fwd(int N, int H, int W, int C, const void* x, const f
                               float* scale_shift, float* part, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Device side of the image transform of dataset_fusion.py:50-65 (ToTensor + Normalize; decode and Resize stay on
+ * the host): uint8 NHWC pixels in, (float(u8)/255 - mean[c]) / std[c] out as bf16 or fp32 in the same NHWC order,
+ * i.e. a channels_last [B,3,H,W] tensor -- what the bf16 trunk consumes.  The batch then crosses PCIe as uint8
+ * (34 MB per 128 items instead of 137 MB).  in/out 16-byte aligned; mean, std: device float[C].          */
+int v2f_image_normalize_u8(long long pixels, int C, const void* in, const float* mean, const float* stdv,
+                           int out_bf16, void* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Multi-tensor Adafactor step (csrc/adafactor.cu): configure_optimizers of the LightningModules,
  * models/CrossAttnRNN210.py:229-230, models/GTM_Visuelle2.py:264-266 (fairseq Adafactor with scale_parameter,
  * relative_step, warmup_init; beta1 = None, weight_decay = 0).  One descriptor per trainable tensor that has a

@@ -77,6 +77,8 @@ def _declare(lib):
     lib.v2f_prof_enable.argtypes = [c_int]
     lib.v2f_gru_persistent_enable.argtypes = [c_int]
     lib.v2f_gru_persistent_enable.restype = c_int
+    lib.v2f_image_normalize_u8.argtypes = [c_ll, c_int, c_vp, c_vp, c_vp, c_int, c_vp, c_vp]
+    lib.v2f_image_normalize_u8.restype = c_int
     lib.v2f_adafactor_step.argtypes = [ctypes.POINTER(AfPlan), ctypes.c_double, ctypes.c_double, c_vp]
     lib.v2f_adafactor_step.restype = c_int
     lib.v2f_decode_persistent_enable.argtypes = [c_int]

@@ -76,3 +76,34 @@ class DevicePrefetcher:
 
     def __len__(self):
         return len(self.loader)
+
+
+IMAGENET_MEAN = (0.485, 0.456, 0.406)      # dataset_fusion.py:55
+IMAGENET_STD = (0.229, 0.224, 0.225)
+_norm_consts = {}
+
+
+def normalize_uint8_images(u8, dtype=torch.bfloat16, mean=IMAGENET_MEAN, std=IMAGENET_STD):
+    """Device side of the reference's per-item transform (dataset_fusion.py:50-65): ``u8`` is a CUDA uint8 tensor
+    [B,H,W,3] of decoded, already resized RGB pixels (what ``np.asarray(PIL image)`` gives); returns
+    ``Normalize(mean, std)(ToTensor(img))`` for the whole batch as a [B,3,H,W] tensor in channels_last memory
+    format (bf16 for the fused trunk, or fp32), computed by csrc/image_prep.cu.  The batch crosses PCIe as uint8:
+    a quarter of the bytes of the fp32 batch the reference's DataLoader produces."""
+    from . import _lib
+    if not (u8.is_cuda and u8.dtype == torch.uint8 and u8.dim() == 4 and u8.is_contiguous()):
+        raise RuntimeError("normalize_uint8_images expects a contiguous CUDA uint8 tensor [B,H,W,C] (no CPU fallback)")
+    if dtype not in (torch.bfloat16, torch.float32):
+        raise TypeError("dtype must be torch.bfloat16 or torch.float32")
+    B, H, W, C = u8.shape
+    key = (u8.device, tuple(mean), tuple(std))
+    if key not in _norm_consts:
+        _norm_consts[key] = (torch.tensor(mean, dtype=torch.float32, device=u8.device),
+                             torch.tensor(std, dtype=torch.float32, device=u8.device))
+    m, s = _norm_consts[key]
+    if len(mean) != C or len(std) != C:
+        raise ValueError("mean/std must have one entry per channel")
+    out = torch.empty((B, H, W, C), dtype=dtype, device=u8.device)
+    _lib.check(_lib.lib().v2f_image_normalize_u8(B * H * W, C, u8.data_ptr(), _lib.ptr(m), _lib.ptr(s),
+                                                 1 if dtype == torch.bfloat16 else 0, out.data_ptr(), _lib.stream()),
+               "v2f_image_normalize_u8")
+    return out.permute(0, 3, 1, 2)          # [B,C,H,W] view = channels_last tensor

@@ -7,6 +7,8 @@ The trunk's modules, parameters, buffers and state_dict keys are untouched (``im
 become one statistics pass + one apply pass (and two passes backward) over the activation instead of
 torch's separate batch_norm / add / relu kernels, which were 60 % of the end-to-end step.
 """
+import os
+
 import torch
 import torch.nn as nn
 
@@ -50,7 +52,7 @@ def _stem_fusable(conv, bn, pool, x):
 def stem(conv, bn, pool, x):
     """maxpool(relu(bn(conv(x)))) with BN + ReLU + max-pool in one sweep when no gradient flows through the
     stem (it is frozen in the reference); otherwise BN+ReLU fused and torch's max-pool."""
-    c = conv(x)
+    c = _conv(conv, x.to(torch.bfloat16) if (_w16 is not None and conv in _w16) else x)
     if not _stem_fusable(conv, bn, pool, x) or c.dtype != torch.bfloat16:
         return pool(bn_act(c, bn, relu=True))
     c = c.detach()
@@ -175,19 +177,85 @@ def bn_act_fork(x, bn, relu=True, res=None):
     return _BnActFork.apply(x, res, bn.weight, bn.bias, bn, relu)
 
 
+# ---------------------------------------------------------------------------------------------- bf16 weights
+# Under autocast every convolution casts its fp32 weight to bf16 (one elementwise launch each, 105 per forward) and
+# every trainable one casts the bf16 weight gradient back (84 launches per backward): 0.9 ms of a 28.6 ms step in
+# ~190 tiny kernels.  Here the trainable weights are cast by ONE multi-tensor copy before the first convolution and
+# their gradients come back through ONE multi-tensor copy after the last weight gradient; frozen weights are cast
+# once and cached until they change.
+class _CastWeights(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, *ws):
+        ctx.set_materialize_grads(False)
+        outs = [torch.empty_like(w, dtype=torch.bfloat16) for w in ws]       # same strides (channels_last stays)
+        torch._foreach_copy_(outs, [w.detach() for w in ws])
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *gs):
+        idx = [i for i, g in enumerate(gs) if g is not None]
+        outs = [torch.empty_like(gs[i], dtype=torch.float32) for i in idx]
+        if idx:
+            torch._foreach_copy_(outs, [gs[i] for i in idx])
+        res = [None] * len(gs)
+        for i, o in zip(idx, outs):
+            res[i] = o
+        return tuple(res)
+
+
+BATCHED_WEIGHT_CASTS = os.environ.get("V2F_BATCHED_CASTS", "1") != "0"      # A/B switch
+_frozen_cache = {}      # id(weight) -> (version, bf16 copy)
+
+
+def _bf16_weights(convs):
+    """{conv: bf16 weight} for the convolutions of one trunk forward."""
+    out = {}
+    train = [c for c in convs if c.weight.requires_grad and torch.is_grad_enabled()]
+    if train:
+        for c, w in zip(train, _CastWeights.apply(*[c.weight for c in train])):
+            out[c] = w
+    stale = []
+    for c in convs:
+        if c in out:
+            continue
+        hit = _frozen_cache.get(id(c.weight))
+        if hit is not None and hit[0] == c.weight._version and hit[1].device == c.weight.device:
+            out[c] = hit[1]
+        else:
+            stale.append(c)
+    if stale:
+        with torch.no_grad():
+            ws = [torch.empty_like(c.weight, dtype=torch.bfloat16) for c in stale]
+            torch._foreach_copy_(ws, [c.weight.detach() for c in stale])
+        for c, w in zip(stale, ws):
+            _frozen_cache[id(c.weight)] = (c.weight._version, w)
+            out[c] = w
+    return out
+
+
+_w16 = None             # inside forward(): {conv: bf16 weight}
+
+
+def _conv(conv, x):
+    w = _w16.get(conv) if _w16 is not None else None
+    if w is None or conv.bias is not None or conv.padding_mode != "zeros":
+        return conv(x)
+    return torch.nn.functional.conv2d(x, w, None, conv.stride, conv.padding, conv.dilation, conv.groups)
+
+
 def _bottleneck(blk, x, x_res=None, fork=False):
     """torchvision.models.resnet.Bottleneck.forward with the fused normalisation sweeps.  ``x`` feeds conv1,
     ``x_res`` (same values; defaults to ``x``) the identity / downsample branch; ``fork``: return the output as a
     pair for the next block."""
     x_res = x if x_res is None else x_res
-    out = bn_act(blk.conv1(x), blk.bn1, relu=True)
-    out = bn_act(blk.conv2(out), blk.bn2, relu=True)
+    out = bn_act(_conv(blk.conv1, x), blk.bn1, relu=True)
+    out = bn_act(_conv(blk.conv2, out), blk.bn2, relu=True)
     identity = x_res
     if blk.downsample is not None:
-        identity = bn_act(blk.downsample[0](x_res), blk.downsample[1], relu=False)
+        identity = bn_act(_conv(blk.downsample[0], x_res), blk.downsample[1], relu=False)
     if fork:
-        return bn_act_fork(blk.conv3(out), blk.bn3, relu=True, res=identity)
-    return bn_act(blk.conv3(out), blk.bn3, relu=True, res=identity)
+        return bn_act_fork(_conv(blk.conv3, out), blk.bn3, relu=True, res=identity)
+    return bn_act(_conv(blk.conv3, out), blk.bn3, relu=True, res=identity)
 
 
 def supported(cnn):
@@ -213,14 +281,16 @@ def supported(cnn):
 
 def forward(cnn, images):
     """images [B,3,H,W] fp32 (any memory format) -> feature map [B,2048,h,w] bf16 channels_last."""
-    global _pending_counters
+    global _pending_counters, _w16
     mods = list(cnn.children())
     x = images.contiguous(memory_format=_CL)
     _pending_counters = []
+    blocks = [blk for layer in mods[4:] for blk in layer]
     try:
+        convs = [mods[0]] + [m for blk in blocks for m in blk.modules() if isinstance(m, nn.Conv2d)]
+        _w16 = _bf16_weights(convs) if BATCHED_WEIGHT_CASTS else None
         with torch.autocast("cuda", dtype=torch.bfloat16):
             x = stem(mods[0], mods[1], mods[3], x)
-            blocks = [blk for layer in mods[4:] for blk in layer]
             x_res = None
             for i, blk in enumerate(blocks):
                 if i + 1 < len(blocks):
@@ -231,4 +301,5 @@ def forward(cnn, images):
             torch._foreach_add_(_pending_counters, 1)
     finally:
         _pending_counters = None
+        _w16 = None
     return x
