@@ -76,11 +76,14 @@ bn_stats_kernel(long long R, int C, const uint4* __restrict__ x, float* __restri
     if (roff < g.RB) {
       const long long stride = (long long)gridDim.x * g.RB;
       long long r = (long long)blockIdx.x * g.RB + roff;
-      // 4 independent 16-byte loads in flight per thread
-      for (; r + 3 * stride < R; r += 4 * stride) {
+      // 4 independent 16-byte loads in flight per thread; the last round is predicated instead of falling into a
+      // serial tail (small late-layer tensors are 2-3 rounds in total: a tail of dependent round trips was a third
+      // of their time)
+      for (; r < R; r += 4 * stride) {
         uint4 u[4];
 #pragma unroll
-        for (int k = 0; k < 4; k++) u[k] = ldg_stream(x + (r + k * stride) * g.CV + v);
+        for (int k = 0; k < 4; k++)
+          u[k] = (r + k * stride < R) ? ldg_stream(x + (r + k * stride) * g.CV + v) : make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
         for (int k = 0; k < 4; k++) {
           float f[8];
@@ -90,15 +93,6 @@ bn_stats_kernel(long long R, int C, const uint4* __restrict__ x, float* __restri
             s[i] += f[i];
             q[i] = fmaf(f[i], f[i], q[i]);
           }
-        }
-      }
-      for (; r < R; r += stride) {
-        float f[8];
-        unpack8(ldg_stream(x + r * g.CV + v), f);
-#pragma unroll
-        for (int i = 0; i < 8; i++) {
-          s[i] += f[i];
-          q[i] = fmaf(f[i], f[i], q[i]);
         }
       }
     }
@@ -228,12 +222,13 @@ bn_apply_kernel(long long R, int C, const uint4* __restrict__ x, const uint4* __
     }
     const long long stride = (long long)gridDim.x * g.RB;
     long long r = (long long)blockIdx.x * g.RB + roff;
-    for (; r + 3 * stride < R; r += 4 * stride) {
+    for (; r < R; r += 4 * stride) {
       uint4 u[4], w[4];
 #pragma unroll
       for (int k = 0; k < 4; k++) {
-        u[k] = ldg_stream(x + (r + k * stride) * g.CV + v);
-        if (RES) w[k] = ldg_stream(res + (r + k * stride) * g.CV + v);
+        const bool ok = r + k * stride < R;
+        u[k] = ok ? ldg_stream(x + (r + k * stride) * g.CV + v) : make_uint4(0u, 0u, 0u, 0u);
+        if (RES) w[k] = ok ? ldg_stream(res + (r + k * stride) * g.CV + v) : make_uint4(0u, 0u, 0u, 0u);
       }
 #pragma unroll
       for (int k = 0; k < 4; k++) {
@@ -246,20 +241,8 @@ bn_apply_kernel(long long R, int C, const uint4* __restrict__ x, const uint4* __
           if (RES) t += h[i];
           f[i] = RELU ? fmaxf(t, 0.f) : t;
         }
-        y[(r + k * stride) * g.CV + v] = pack8(f);
+        if (r + k * stride < R) y[(r + k * stride) * g.CV + v] = pack8(f);
       }
-    }
-    for (; r < R; r += stride) {
-      float f[8], h[8];
-      unpack8(ldg_stream(x + r * g.CV + v), f);
-      if (RES) unpack8(ldg_stream(res + r * g.CV + v), h);
-#pragma unroll
-      for (int i = 0; i < 8; i++) {
-        float t = fmaf(f[i], sc[i], sh[i]);
-        if (RES) t += h[i];
-        f[i] = RELU ? fmaxf(t, 0.f) : t;
-      }
-      y[r * g.CV + v] = pack8(f);
     }
   }
 }
@@ -289,14 +272,16 @@ bn_bwd_reduce_kernel(long long R, int C, const uint4* __restrict__ dy, const uin
     if (roff < g.RB) {
       const long long stride = (long long)gridDim.x * g.RB;
       long long r = (long long)blockIdx.x * g.RB + roff;
-      for (; r + stride < R; r += 2 * stride) {
+      const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+      for (; r < R; r += 2 * stride) {
         uint4 ud[2], ue[2], ux[2], uy[2];
 #pragma unroll
         for (int k = 0; k < 2; k++) {
-          ud[k] = ldg_stream(dy + (r + k * stride) * g.CV + v);
-          if (ADD2) ue[k] = ldg_stream(dy2 + (r + k * stride) * g.CV + v);
-          ux[k] = ldg_stream(x + (r + k * stride) * g.CV + v);
-          if (RELU) uy[k] = ldg_stream(y + (r + k * stride) * g.CV + v);
+          const bool ok = r + k * stride < R;       // predicated last round: zero gradient adds nothing to the sums
+          ud[k] = ok ? ldg_stream(dy + (r + k * stride) * g.CV + v) : z4;
+          if (ADD2) ue[k] = ok ? ldg_stream(dy2 + (r + k * stride) * g.CV + v) : z4;
+          ux[k] = ok ? ldg_stream(x + (r + k * stride) * g.CV + v) : z4;
+          if (RELU) uy[k] = ok ? ldg_stream(y + (r + k * stride) * g.CV + v) : z4;
         }
 #pragma unroll
         for (int k = 0; k < 2; k++) {
@@ -312,23 +297,8 @@ bn_bwd_reduce_kernel(long long R, int C, const uint4* __restrict__ dy, const uin
             s[i] += d[i];
             q[i] = fmaf(d[i], (xv[i] - mu[i]) * rs[i], q[i]);
           }
-          if (WRITE_DZ) dz[(r + k * stride) * g.CV + v] = pack8(d);
+          if (WRITE_DZ && r + k * stride < R) dz[(r + k * stride) * g.CV + v] = pack8(d);
         }
-      }
-      for (; r < R; r += stride) {
-        float d[8], e[8], xv[8], yv[8];
-        unpack8(ldg_stream(dy + r * g.CV + v), d);
-        if (ADD2) unpack8(ldg_stream(dy2 + r * g.CV + v), e);
-        unpack8(ldg_stream(x + r * g.CV + v), xv);
-        if (RELU) unpack8(ldg_stream(y + r * g.CV + v), yv);
-#pragma unroll
-        for (int i = 0; i < 8; i++) {
-          if (ADD2) d[i] += e[i];
-          if (RELU && !(yv[i] > 0.f)) d[i] = 0.f;
-          s[i] += d[i];
-          q[i] = fmaf(d[i], (xv[i] - mu[i]) * rs[i], q[i]);
-        }
-        if (WRITE_DZ) dz[r * g.CV + v] = pack8(d);
       }
     }
     const int W8 = g.CVB * 8;
@@ -416,7 +386,7 @@ bn_bwd_elemt_kernel(long long R, int C, const uint4* __restrict__ dy, const uint
         dx[(r + k * stride) * g.CV + v] = pack8(d);
       }
     }
-    for (; r < R; r += stride) {
+    for (; r < R; r += stride) {       // (a predicated last round costs registers this kernel does not have: 64, 4 CTAs/SM)
       float d[8], xv[8], yv[8];
       unpack8(ldg_stream(dy + r * g.CV + v), d);
       unpack8(ldg_stream(x + r * g.CV + v), xv);
@@ -471,6 +441,27 @@ bn_relu_maxpool_kernel(int N, int H, int W, int C, int OH, int OW, const uint4* 
   y[i] = pack8(m);
 }
 
+// Resident CTAs per SM of one kernel instantiation (cached): the sweeps are sized to exactly one wave --
+// a kernel that needs 80-98 registers fits 2-3 CTAs of 256 threads per SM, and a grid of 4 per SM would then
+// run a second, quarter-full wave.
+template <typename K>
+static int resident_per_sm(K kern, size_t smem) {
+  static int cached = 0;
+  if (!cached) {
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, BN_THREADS, smem) != cudaSuccess || n < 1) n = 1;
+    cached = n > 4 ? 4 : n;
+  }
+  return cached;
+}
+template <typename K>
+static int wave_blocks(K kern, size_t smem, long long R, int C) {
+  const Geo g = make_geo(C);
+  const long long need = (R + g.RB - 1) / g.RB;
+  const long long cap = 148LL * resident_per_sm(kern, smem);
+  return (int)(need < cap ? need : cap);
+}
+
 static inline int sweep_blocks(long long R, int C) {
   const Geo g = make_geo(C);
   long long need = (R + g.RB - 1) / g.RB;           // one block-iteration per RB rows
@@ -516,10 +507,13 @@ extern "C" int v2f_bn2d_act_fwd(long long R, int C, const void* x, const void* r
   const uint4 *xp = (const uint4*)x, *rp = (const uint4*)res;
   uint4* yp = (uint4*)y;
   const float *sc = scale_shift, *sh = scale_shift + C;
-  if (res && relu) bn_apply_kernel<true, true><<<nblk, BN_THREADS, 0, s>>>(R, C, xp, rp, sc, sh, yp);
-  else if (res) bn_apply_kernel<true, false><<<nblk, BN_THREADS, 0, s>>>(R, C, xp, rp, sc, sh, yp);
-  else if (relu) bn_apply_kernel<false, true><<<nblk, BN_THREADS, 0, s>>>(R, C, xp, rp, sc, sh, yp);
-  else bn_apply_kernel<false, false><<<nblk, BN_THREADS, 0, s>>>(R, C, xp, rp, sc, sh, yp);
+#define BN_APPLY(RES_, RELU_) \
+  bn_apply_kernel<RES_, RELU_><<<wave_blocks(bn_apply_kernel<RES_, RELU_>, 0, R, C), BN_THREADS, 0, s>>>(R, C, xp, rp, sc, sh, yp)
+  if (res && relu) BN_APPLY(true, true);
+  else if (res) BN_APPLY(true, false);
+  else if (relu) BN_APPLY(false, true);
+  else BN_APPLY(false, false);
+#undef BN_APPLY
   prof_end(V2F_K_BN_APPLY, s);
   V2F_CHECK_LAUNCH();
   return V2F_OK;
@@ -545,8 +539,13 @@ extern "C" int v2f_bn2d_act_bwd(long long R, int C, const void* dy, const void* 
   prof_begin(V2F_K_BN_BWD_REDUCE, s);
   const bool have_dz = dz && (relu || dy2);
   prof_bytes(V2F_K_BN_BWD_REDUCE, tb * (2 + (relu ? 1 : 0) + (have_dz ? 1 : 0) + (dy2 ? 1 : 0)));
-#define BN_RED(RELU_, WDZ_, ADD2_) \
-  bn_bwd_reduce_kernel<RELU_, WDZ_, ADD2_><<<nblk, BN_THREADS, smem, s>>>(R, C, dyp, dy2p, xp, yp, save_mean, save_rstd, dzp, part)
+  int nred = nblk;       // blocks of the reduce pass = partial rows the finalize merges (<= sweep_blocks = rows of ``part``)
+#define BN_RED(RELU_, WDZ_, ADD2_)                                                                    \
+  do {                                                                                                \
+    nred = wave_blocks(bn_bwd_reduce_kernel<RELU_, WDZ_, ADD2_>, smem, R, C);                         \
+    bn_bwd_reduce_kernel<RELU_, WDZ_, ADD2_><<<nred, BN_THREADS, smem, s>>>(R, C, dyp, dy2p, xp, yp, save_mean, \
+                                                                           save_rstd, dzp, part);     \
+  } while (0)
   if (dy2 && relu) BN_RED(true, true, true);
   else if (dy2) BN_RED(false, true, true);
   else if (relu && dz) BN_RED(true, true, false);
@@ -555,14 +554,17 @@ extern "C" int v2f_bn2d_act_bwd(long long R, int C, const void* dy, const void* 
 #undef BN_RED
   prof_end(V2F_K_BN_BWD_REDUCE, s);
   V2F_CHECK_LAUNCH();
-  bn_bwd_finalize_kernel<<<(C + 31) / 32, dim3(32, FIN_Y), 0, s>>>(R, C, nblk, part, gamma, save_mean, save_rstd, training, dgamma, dbeta, coef);
+  bn_bwd_finalize_kernel<<<(C + 31) / 32, dim3(32, FIN_Y), 0, s>>>(R, C, nred, part, gamma, save_mean, save_rstd, training, dgamma, dbeta, coef);
   V2F_CHECK_LAUNCH();
   prof_begin(V2F_K_BN_BWD_ELEMT, s);
   prof_bytes(V2F_K_BN_BWD_ELEMT, tb * (3 + ((relu && !dz) ? 1 : 0)));
-  if (have_dz && !relu) bn_bwd_elemt_kernel<false, false><<<nblk, BN_THREADS, 0, s>>>(R, C, (const uint4*)dz, xp, yp, coef, dxp);
-  else if (relu && dz) bn_bwd_elemt_kernel<true, true><<<nblk, BN_THREADS, 0, s>>>(R, C, (const uint4*)dz, xp, yp, coef, dxp);
-  else if (relu) bn_bwd_elemt_kernel<true, false><<<nblk, BN_THREADS, 0, s>>>(R, C, dyp, xp, yp, coef, dxp);
-  else bn_bwd_elemt_kernel<false, false><<<nblk, BN_THREADS, 0, s>>>(R, C, dyp, xp, yp, coef, dxp);
+#define BN_ELEMT(RELU_, HAVE_, SRC_) \
+  bn_bwd_elemt_kernel<RELU_, HAVE_><<<wave_blocks(bn_bwd_elemt_kernel<RELU_, HAVE_>, 0, R, C), BN_THREADS, 0, s>>>(R, C, SRC_, xp, yp, coef, dxp)
+  if (have_dz && !relu) BN_ELEMT(false, false, (const uint4*)dz);
+  else if (relu && dz) BN_ELEMT(true, true, (const uint4*)dz);
+  else if (relu) BN_ELEMT(true, false, dyp);
+  else BN_ELEMT(false, false, dyp);
+#undef BN_ELEMT
   prof_end(V2F_K_BN_BWD_ELEMT, s);
   V2F_CHECK_LAUNCH();
   return V2F_OK;
