@@ -15,6 +15,8 @@
 // partial sums per block are merged in double by the finalize kernels (no atomics, deterministic).
 #include <cuda_bf16.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace v2f {
@@ -76,16 +78,18 @@ bn_stats_kernel(long long R, int C, const uint4* __restrict__ x, float* __restri
     if (roff < g.RB) {
       const long long stride = (long long)gridDim.x * g.RB;
       long long r = (long long)blockIdx.x * g.RB + roff;
-      // 4 independent 16-byte loads in flight per thread; the last round is predicated instead of falling into a
-      // serial tail (small late-layer tensors are 2-3 rounds in total: a tail of dependent round trips was a third
-      // of their time)
-      for (; r < R; r += 4 * stride) {
-        uint4 u[4];
+      // the last round is predicated instead of falling into a serial tail (small late-layer tensors are 2-3 rounds
+      // in total: a tail of dependent round trips was a third of their time)
+      // a read-only sweep needs more bytes in flight than the read+write ones to cover the HBM latency: 8 x 16 B per
+      // thread, 128 KB per SM (with 4 it stopped at 0.61 of the HBM peak on 369 MB tensors, the apply pass at 0.87)
+      constexpr int UN = 8;
+      for (; r < R; r += UN * stride) {
+        uint4 u[UN];
 #pragma unroll
-        for (int k = 0; k < 4; k++)
+        for (int k = 0; k < UN; k++)
           u[k] = (r + k * stride < R) ? ldg_stream(x + (r + k * stride) * g.CV + v) : make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
+        for (int k = 0; k < UN; k++) {
           float f[8];
           unpack8(u[k], f);
 #pragma unroll
@@ -465,7 +469,13 @@ static int wave_blocks(K kern, size_t smem, long long R, int C) {
 static inline int sweep_blocks(long long R, int C) {
   const Geo g = make_geo(C);
   long long need = (R + g.RB - 1) / g.RB;           // one block-iteration per RB rows
-  long long cap = 148 * 4;                          // 4 CTAs of 256 threads per SM, 64 B in flight per thread
+  static int per_sm = 0;
+  if (!per_sm) {
+    const char* e = getenv("V2F_BN_STATS_CTAS");    // experiment knob: resident CTAs per SM of the statistics sweep
+    per_sm = e ? atoi(e) : 4;
+    if (per_sm < 1 || per_sm > 8) per_sm = 4;
+  }
+  long long cap = 148LL * per_sm;
   return (int)(need < cap ? need : cap);
 }
 
