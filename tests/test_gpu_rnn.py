@@ -227,3 +227,33 @@ def test_persistent_decoder_equals_step_per_launch_path(model, B, E, T, precisio
         floor = 1e-6 if k.endswith("attn_linear.bias") else 1e-9
         assert float((a - b).abs().max()) <= tol * float(b.abs().max()) + floor, (k, float((a - b).abs().max()),
                                                                                  float(b.abs().max()))
+
+
+@pytest.mark.parametrize("model", ["CrossAttnRNN210", "CrossAttnRNNDemand"])
+def test_graphed_forecast_equals_eager_eval_forward(model):
+    """graphs.GraphedForecast: the reference's no-grad forecast loop (forecast_dl.py:123-171) replayed from a CUDA
+    graph gives the eager eval forward's numbers and leaves the host RNG where the eager call leaves it."""
+    import visuelle2_multimodal_fusion_b200.synth as synth
+    from visuelle2_multimodal_fusion_b200.graphs import GraphedForecast
+    demand = model == "CrossAttnRNNDemand"
+    m = _head_model(model, 256)
+    m.on_validation_epoch_start()
+
+    def inputs(seed, B=6):
+        data, feat = synth.make_batch(B, out_len=10, demand=demand, seed=seed, feat_hw=10)
+        return tuple(t.cuda() for t in data) + (feat.cuda(),)
+
+    fc = GraphedForecast(m, inputs(1))
+    for seed in (2, 3):
+        torch.manual_seed(40 + seed)
+        got = fc(inputs(seed))[0].clone()
+        after_graph = torch.rand(1)
+        torch.manual_seed(40 + seed)
+        with torch.no_grad():
+            want = m(*inputs(seed))[0]
+        after_eager = torch.rand(1)
+        assert torch.equal(after_graph, after_eager)
+        assert float((got - want).abs().max()) <= 1e-6 * float(want.abs().max()) + 1e-9
+    torch.manual_seed(7)
+    small = fc(inputs(5, B=3))[0]                 # other batch size: eager fallback
+    assert small.shape[0] == 3

@@ -97,3 +97,52 @@ class GraphedTrainStep:
         """Back to eager: the module draws its teacher-forcing bits on the host again."""
         if self.has_tf:
             self.model._tf_mask_dev = None
+
+
+class GraphedForecast:
+    """The no-grad forecast loop of the reference's drivers (forecast_dl.py:123-171, forecast_Gated_v4.py:89-124:
+    ``model.eval(); with torch.no_grad(): y_hat = model(*inputs)`` per batch) with the forward captured once into a
+    CUDA graph and replayed per batch: ``fc = GraphedForecast(model, example_inputs); y_hat = fc(inputs)``.
+
+    ``inputs`` is the positional tuple the module's ``forward`` takes (dataset_fusion.py batch layout: the data
+    tuple followed by the images).  Batches must keep the example's shapes (the last, smaller batch of a loader runs
+    eagerly through ``model`` -- ``__call__`` falls back to it when shapes differ).  The host random draws the
+    reference makes per forward (CrossAttnRNNDemand draws 12 numbers even in eval, models/CrossAttnRNNDemand.py:343-345)
+    are still made per call, so the host RNG stream stays the reference's."""
+
+    def __init__(self, model, example_inputs, warmup=2):
+        self.model = model.eval()
+        dev = next(model.parameters()).device
+        self.static_in = _tree_map(lambda t: t.to(dev, copy=True), tuple(example_inputs))
+        self.has_tf = hasattr(model, "draw_tf_mask")
+        if self.has_tf:
+            model._tf_mask_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+        side = self.side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(warmup):
+                model(*self.static_in)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.no_grad(), torch.cuda.graph(self.graph, stream=side):
+            self.static_out = model(*self.static_in)
+        if self.has_tf:
+            self._tf_zero = model._tf_mask_dev     # the captured kernels read this word (all zero: no forcing in a forecast)
+            model._tf_mask_dev = None              # eager calls draw on the host again
+
+    def _same_shapes(self, inputs):
+        flat_a, flat_b = [], []
+        _tree_map(lambda t: flat_a.append(tuple(t.shape)), self.static_in)
+        _tree_map(lambda t: flat_b.append(tuple(t.shape)), tuple(inputs))
+        return flat_a == flat_b
+
+    def __call__(self, inputs):
+        if not self._same_shapes(inputs):
+            with torch.no_grad():
+                return self.model(*inputs)
+        if self.has_tf:
+            self.model.draw_tf_mask(False)        # consume the host draws of this forward; eval ignores the bits
+        _tree_copy(self.static_in, tuple(inputs))
+        self.graph.replay()
+        return self.static_out
