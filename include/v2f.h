@@ -161,6 +161,12 @@ int v2f_decode_persist_stamps_enable(int on);
 /* Timing experiments only (results become invalid): bit 0 skips the activation loads of the products,
  * bit 1 their MMAs.  Default 0.                                                                   */
 int v2f_decode_persist_debug(int bits);
+/* Host logic of the persistent decoder, callable without a GPU: which output columns CTA c of a G-CTA grid owns.
+ * out[11] = a_lo, na (columns of S that feed the attention queries), u_lo, nu (hidden units: gh columns of S and the
+ * gate columns of GI), n1 = na + 3 nu, m3 (0 image / 1 trend context rows in P3), e_lo3, n3 (columns of HC),
+ * x_lo, nx (columns of CTX), n5 = nx + 3 nu.  The kernel supports a configuration when every CTA has
+ * n1 <= 24, n3 <= 8, n5 <= 16, 1 <= nu <= 4.                                                       */
+int v2f_decode_persist_ownership(int c, int G, int E, int H, int* out);
 long long v2f_decode_persist_stamps_offset(int N, int E, int H);
 
 /* ------------------------------------------------------------------------------------------

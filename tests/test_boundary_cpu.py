@@ -148,3 +148,29 @@ def test_fused_adafactor_interface_and_no_cpu_fallback():
     p.grad = torch.ones(4, 4)
     with pytest.raises(RuntimeError):
         opt.step()                               # CPU parameter: there is no fallback
+
+
+def test_persistent_decoder_column_ownership_is_a_partition():
+    """Host logic of csrc/decode_persist.cu (no GPU): over the CTAs of a grid, the owned ranges tile every output
+    column of the three weight-stationary products exactly once, and the B200 grid (148 SMs) fits the shared-memory
+    envelope (n1 <= 24, n3 <= 8, n5 <= 16, nu <= 4) at the reference's dims."""
+    from visuelle2_multimodal_fusion_b200 import build
+    lib = ctypes.CDLL(build.build())
+    out = (ctypes.c_int * 11)()
+    for G, E, H in [(148, 512, 512), (148, 256, 256), (132, 512, 512), (160, 512, 448), (2, 256, 64)]:
+        s_cols, units, ctx_cols = [], [], []
+        hc = {0: [], 1: []}
+        for c in range(G):
+            assert lib.v2f_decode_persist_ownership(c, G, E, H, out) == 0
+            a_lo, na, u_lo, nu, n1, m3, e_lo3, n3, x_lo, nx, n5 = list(out)
+            assert n1 == na + 3 * nu and n5 == nx + 3 * nu and m3 == c % 2
+            s_cols += list(range(a_lo, a_lo + na))
+            units += list(range(u_lo, u_lo + nu))
+            ctx_cols += list(range(x_lo, x_lo + nx))
+            hc[m3] += list(range(e_lo3, e_lo3 + n3))
+            if (G, E, H) == (148, 512, 512):
+                assert n1 <= 24 and n3 <= 8 and n5 <= 16 and 1 <= nu <= 4
+        assert s_cols == list(range(3 * E)) and units == list(range(H)) and ctx_cols == list(range(E))
+        assert hc[0] == list(range(E)) and hc[1] == list(range(E))
+    assert lib.v2f_decode_persist_ownership(5, 1, 512, 512, out) != 0          # bad grid
+    assert lib.v2f_decode_persist_ws_floats(128, 512, 512, 10) > 3 * 512 * 512

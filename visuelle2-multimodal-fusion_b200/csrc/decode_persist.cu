@@ -861,6 +861,15 @@ extern "C" int v2f_decode_persist_debug(int bits) {   // timing experiments only
   v2f::g_dp_dbg = bits;
   return V2F_OK;
 }
+// Column ownership of CTA c of a G-CTA grid (host logic of the persistent decoder, exposed for the CPU tests):
+// out[11] = a_lo, na, u_lo, nu, n1, m3, e_lo3, n3, x_lo, nx, n5 (struct DpOwn).  No GPU needed.
+extern "C" int v2f_decode_persist_ownership(int c, int G, int E, int H, int* out) {
+  V2F_REQUIRE(out && G >= 2 && c >= 0 && c < G && E > 0 && H > 0, V2F_ERR_BAD_ARG);
+  const v2f::DpOwn o = v2f::dp_own(c, G, E, H);
+  const int v[11] = {o.a_lo, o.na, o.u_lo, o.nu, o.n1, o.m3, o.e_lo3, o.n3, o.x_lo, o.nx, o.n5};
+  for (int i = 0; i < 11; i++) out[i] = v[i];
+  return V2F_OK;
+}
 extern "C" long long v2f_decode_persist_ws_floats(int N, int E, int H, int T) {
   if (N <= 0 || E <= 0 || H <= 0 || T <= 0) return 0;
   return v2f::decode_persist_ws_floats(N, E, H, T);
