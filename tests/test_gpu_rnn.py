@@ -257,3 +257,42 @@ def test_graphed_forecast_equals_eager_eval_forward(model):
     torch.manual_seed(7)
     small = fc(inputs(5, B=3))[0]                 # other batch size: eager fallback
     assert small.shape[0] == 3
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-5), ("bf16", 2e-2)])
+def test_full_size_properties_of_the_decoder(precision, tol):
+    """BASELINE.json's full size (B = 128 items, E = A = H = 512, 100 image positions, 52 trend steps, 12 steps), where
+    the CPU oracle is too slow: properties that hold at any size.  (1) every attention map the Demand forward returns
+    is a distribution; (2) items are independent: permuting the batch permutes the forecasts and the feature-map
+    gradient (the work split of the streaming sweep moves with the row order, so to rounding, not bit for bit);
+    (3) the loss gradient of an item that does not enter the loss is exactly zero."""
+    import visuelle2_multimodal_fusion_b200.synth as synth
+    m = _head_model("CrossAttnRNNDemand", 512)
+    m.precision = precision
+    m.on_validation_epoch_start()
+    B = 128
+    data, feat = synth.make_batch(B, out_len=10, demand=True, seed=17, feat_hw=10)
+    data = tuple(t.cuda() for t in data)
+    feat = feat.cuda()
+
+    def run(d, f, weight):
+        f = f.clone().requires_grad_(True)
+        torch.manual_seed(3)
+        out, ia, ma = m(*d, f)
+        (out.squeeze(-1) * weight).square().sum().backward()
+        g = f.grad.clone()
+        m.zero_grad(set_to_none=True)
+        return out.detach(), torch.stack(ia), torch.stack(ma), g
+
+    w = torch.ones(B, 1, device="cuda")
+    w[5] = 0.0                                     # item 5 does not enter the loss
+    out, ia, ma, g = run(data, feat, w)
+    assert ia.shape == (12, B, 100) and ma.shape == (12, B, 4)
+    assert float((ia.sum(-1) - 1).abs().max()) < 1e-5 and float((ma.sum(-1) - 1).abs().max()) < 1e-5
+    assert float(ia.min()) >= 0.0 and float(ma.min()) >= 0.0
+    assert float(g[5].abs().max()) == 0.0 and float(g[4].abs().max()) > 0.0
+    perm = torch.randperm(B, generator=torch.Generator().manual_seed(2)).cuda()
+    out_p, ia_p, ma_p, g_p = run(tuple(t[perm] for t in data), feat[perm], w[perm])
+    assert float((out_p - out[perm]).abs().max()) <= tol * float(out.abs().max())
+    assert float((ia_p - ia[:, perm]).abs().max()) <= tol
+    assert float((g_p - g[perm]).abs().max()) <= tol * float(g.abs().max())
