@@ -795,6 +795,12 @@ static int dp_launch(const DpArgs& a, int G, size_t smem, cudaStream_t s) {
   prof_begin(V2F_K_DECODE_PERSIST_FWD, s);
   const cudaError_t e = cudaLaunchCooperativeKernel((void*)kern, dim3(G), dim3(DP_THREADS), params, smem, s);
   prof_end(V2F_K_DECODE_PERSIST_FWD, s);
+  if (e == cudaErrorCooperativeLaunchTooLarge || e == cudaErrorLaunchOutOfResources) {
+    // the grid cannot be co-resident right now (SMs shared with another context, MPS, a smaller partition):
+    // not an error -- the caller walks the steps with one launch per kernel instead
+    cudaGetLastError();
+    return V2F_ERR_UNSUPPORTED;
+  }
   if (e != cudaSuccess) return V2F_ERR_LAUNCH;
   ++g_v2f_launches;
   return V2F_OK;
