@@ -10,7 +10,7 @@
 
 namespace v2f {
 
-constexpr int SD_THREADS = 256;
+constexpr int SD_THREADS = 512;   // 16 warps: the 13 x 32 register tiles of the [52 x 128] products fit one round
 constexpr int SD_MAXL = 64;
 
 struct SdpaArgs {
