@@ -199,3 +199,27 @@ def test_bn_act_fork_sums_the_two_consumer_gradients(res):
     x3 = x.detach().clone().requires_grad_(True)
     trunk.bn_act(x3, bn, relu=True, res=r.detach() if res else None).backward(g1)
     assert _rel(only_first, x3.grad) < 1e-6
+
+
+def test_frozen_weight_cache_does_not_outlive_its_parameter():
+    """trunk._bf16_weights caches the bf16 copies of frozen convolution weights; a second model built after the
+    first was freed must never be served the first model's copies (its parameters may reuse the freed ids)."""
+    import gc
+    import torch.nn as nn
+    from visuelle2_multimodal_fusion_b200 import trunk
+    for rep in range(6):
+        cin, cout = (8, 16) if rep % 2 == 0 else (32, 8)
+        convs = [nn.Conv2d(cin, cout, 3, bias=False).cuda() for _ in range(40)]
+        for c in convs:
+            c.weight.requires_grad_(False)
+        got = trunk._bf16_weights(convs)
+        for c in convs:
+            assert got[c].shape == c.weight.shape and got[c].dtype == torch.bfloat16
+            assert torch.equal(got[c], c.weight.to(torch.bfloat16))
+        again = trunk._bf16_weights(convs)
+        assert all(again[c] is got[c] for c in convs)                  # cached while the parameter is unchanged
+        with torch.no_grad():
+            convs[0].weight.add_(1.0)                                  # in-place update bumps the version
+        assert torch.equal(trunk._bf16_weights(convs)[convs[0]], convs[0].weight.to(torch.bfloat16))
+        del convs, got, again
+        gc.collect()

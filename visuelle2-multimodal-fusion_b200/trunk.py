@@ -11,6 +11,7 @@ import os
 
 import torch
 import torch.nn as nn
+from torch.utils.weak import WeakTensorKeyDictionary
 
 from . import _lib
 from ._lib import check, ptr, stream
@@ -204,7 +205,9 @@ class _CastWeights(torch.autograd.Function):
 
 
 BATCHED_WEIGHT_CASTS = os.environ.get("V2F_BATCHED_CASTS", "1") != "0"      # A/B switch
-_frozen_cache = {}      # id(weight) -> (version, bf16 copy)
+# weight Parameter -> (version, data_ptr, bf16 copy); weak keys: an entry dies with its parameter (an id()-keyed dict
+# handed the copy of a freed model's weight to the next model whose parameter reused the id)
+_frozen_cache = WeakTensorKeyDictionary()
 
 
 def _bf16_weights(convs):
@@ -218,9 +221,10 @@ def _bf16_weights(convs):
     for c in convs:
         if c in out:
             continue
-        hit = _frozen_cache.get(id(c.weight))
-        if hit is not None and hit[0] == c.weight._version and hit[1].device == c.weight.device:
-            out[c] = hit[1]
+        hit = _frozen_cache.get(c.weight)
+        if hit is not None and hit[0] == c.weight._version and hit[1] == c.weight.data_ptr() and \
+                hit[2].shape == c.weight.shape:
+            out[c] = hit[2]
         else:
             stale.append(c)
     if stale:
@@ -228,7 +232,7 @@ def _bf16_weights(convs):
             ws = [torch.empty_like(c.weight, dtype=torch.bfloat16) for c in stale]
             torch._foreach_copy_(ws, [c.weight.detach() for c in stale])
         for c, w in zip(stale, ws):
-            _frozen_cache[id(c.weight)] = (c.weight._version, w)
+            _frozen_cache[c.weight] = (c.weight._version, c.weight.data_ptr(), w)
             out[c] = w
     return out
 
