@@ -15,8 +15,6 @@
 // partial sums per block are merged in double by the finalize kernels (no atomics, deterministic).
 #include <cuda_bf16.h>
 
-#include <cstdlib>
-
 #include "common.cuh"
 
 namespace v2f {
@@ -469,13 +467,8 @@ static int wave_blocks(K kern, size_t smem, long long R, int C) {
 static inline int sweep_blocks(long long R, int C) {
   const Geo g = make_geo(C);
   long long need = (R + g.RB - 1) / g.RB;           // one block-iteration per RB rows
-  static int per_sm = 0;
-  if (!per_sm) {
-    const char* e = getenv("V2F_BN_STATS_CTAS");    // experiment knob: resident CTAs per SM of the statistics sweep
-    per_sm = e ? atoi(e) : 4;
-    if (per_sm < 1 || per_sm > 8) per_sm = 4;
-  }
-  long long cap = 148LL * per_sm;
+  // 4 CTAs of 256 threads per SM (6 and 8 were measured slower for the statistics sweep: tools/bn_probe.py)
+  long long cap = 148 * 4;
   return (int)(need < cap ? need : cap);
 }
 
