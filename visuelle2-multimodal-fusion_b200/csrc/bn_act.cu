@@ -120,64 +120,65 @@ bn_stats_kernel(long long R, int C, const uint4* __restrict__ x, float* __restri
 // Merge of the block partials of one channel group: block (32 channels, 32 slices of the partial
 // range), two independent double accumulators per thread so the loads pipeline, fixed order.
 // Returns the totals to the threads with threadIdx.y == 0.
-constexpr int FIN_Y = 32;
+constexpr int FIN_X = 8;      // channels per finalize block (one 32-byte sector of a partial row)
+constexpr int FIN_Y = 128;    // slices of the partial range per block
+constexpr int FIN_R = 5;      // partial rows per thread: FIN_Y * FIN_R >= 148 * 4 blocks of a sweep
+// Merge of the block partials of FIN_X channels by one block of FIN_X x FIN_Y threads: every thread issues its (at most
+// five) row loads at once, so the merge is one L2 round trip deep; C / 8 blocks instead of C / 32 (the 64-channel layers
+// had 2 blocks walking 592 rows).  Fixed summation order, double.  Totals returned to the threads with threadIdx.y == 0.
 __device__ __forceinline__ void merge_partials(int C, int c, int nblk, const float* __restrict__ part,
                                                double& S, double& Q) {
-  __shared__ double red[2][FIN_Y][33];
-  double s0 = 0.0, q0 = 0.0, s1 = 0.0, q1 = 0.0;
+  __shared__ double red[2][FIN_Y][FIN_X + 1];
+  double s = 0.0, q = 0.0;
   if (c < C) {
-    // partials b = y, y+32, y+64, ...: eight of them (16 independent loads) are issued before the first add, so the
-    // merge is not a chain of dependent L2 round trips (it was 19 of them for 592 blocks)
-    int b = threadIdx.y;
-    for (; b + 7 * FIN_Y < nblk; b += 8 * FIN_Y) {
-      float vs[8], vq[8];
+    for (int b0 = threadIdx.y; b0 < nblk; b0 += FIN_Y * FIN_R) {
+      float vs[FIN_R], vq[FIN_R];
 #pragma unroll
-      for (int k = 0; k < 8; k++) {
-        vs[k] = part[((long long)(b + k * FIN_Y) * 2) * C + c];
-        vq[k] = part[((long long)(b + k * FIN_Y) * 2 + 1) * C + c];
+      for (int k = 0; k < FIN_R; k++) {
+        const int b = b0 + k * FIN_Y;
+        vs[k] = b < nblk ? part[((long long)b * 2) * C + c] : 0.f;
+        vq[k] = b < nblk ? part[((long long)b * 2 + 1) * C + c] : 0.f;
       }
 #pragma unroll
-      for (int k = 0; k < 8; k += 2) {
-        s0 += (double)vs[k];
-        q0 += (double)vq[k];
-        s1 += (double)vs[k + 1];
-        q1 += (double)vq[k + 1];
+      for (int k = 0; k < FIN_R; k++) {
+        s += (double)vs[k];
+        q += (double)vq[k];
       }
-    }
-    for (; b + FIN_Y < nblk; b += 2 * FIN_Y) {
-      const float a0 = part[((long long)b * 2) * C + c], a1 = part[((long long)b * 2 + 1) * C + c];
-      const float b0 = part[((long long)(b + FIN_Y) * 2) * C + c], b1 = part[((long long)(b + FIN_Y) * 2 + 1) * C + c];
-      s0 += (double)a0;
-      q0 += (double)a1;
-      s1 += (double)b0;
-      q1 += (double)b1;
-    }
-    if (b < nblk) {
-      s0 += (double)part[((long long)b * 2) * C + c];
-      q0 += (double)part[((long long)b * 2 + 1) * C + c];
     }
   }
-  red[0][threadIdx.y][threadIdx.x] = s0 + s1;
-  red[1][threadIdx.y][threadIdx.x] = q0 + q1;
+  red[0][threadIdx.y][threadIdx.x] = s;
+  red[1][threadIdx.y][threadIdx.x] = q;
+  __syncthreads();
+  if (threadIdx.y < 8) {          // 128 slices -> 8 sums of 16
+    double a = 0.0, b = 0.0;
+#pragma unroll
+    for (int i = 0; i < FIN_Y / 8; i++) {
+      a += red[0][threadIdx.y + 8 * i][threadIdx.x];
+      b += red[1][threadIdx.y + 8 * i][threadIdx.x];
+    }
+    __syncwarp();
+    red[0][threadIdx.y][threadIdx.x] = a;      // rows 0..7 are read above only by their own thread (i = 0)
+    red[1][threadIdx.y][threadIdx.x] = b;
+  }
   __syncthreads();
   S = Q = 0.0;
   if (threadIdx.y == 0)
 #pragma unroll
-    for (int i = 0; i < FIN_Y; i++) {
+    for (int i = 0; i < 8; i++) {
       S += red[0][i][threadIdx.x];
       Q += red[1][i][threadIdx.x];
     }
 }
 
 // Per channel: merge the block partials, produce scale/shift, the saved mean / rstd and the
-// running-statistics update (momentum, unbiased variance).  grid = ceil(C/32), block (32,32).
+// running-statistics update (momentum, unbiased variance).  grid = ceil(C/8), block (8,128).
 __global__ void bn_fwd_finalize_kernel(long long R, int C, int nblk, const float* __restrict__ part,
                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                        float* __restrict__ run_mean, float* __restrict__ run_var,
                                        int training, float momentum, float eps, float* __restrict__ scale,
                                        float* __restrict__ shift, float* __restrict__ save_mean,
                                        float* __restrict__ save_rstd) {
-  const int c = blockIdx.x * 32 + threadIdx.x;
+  const int c = blockIdx.x * FIN_X + threadIdx.x;
   double S = 0.0, Q = 0.0;
   if (training) merge_partials(C, c, nblk, part, S, Q);
   if (c >= C || threadIdx.y != 0) return;
@@ -331,7 +332,7 @@ __global__ void bn_bwd_finalize_kernel(long long R, int C, int nblk, const float
                                        const float* __restrict__ rstd,
                                        int training, float* __restrict__ dgamma, float* __restrict__ dbeta,
                                        float* __restrict__ coef) {
-  const int c = blockIdx.x * 32 + threadIdx.x;
+  const int c = blockIdx.x * FIN_X + threadIdx.x;
   double S, Q;
   merge_partials(C, c, nblk, part, S, Q);
   if (c >= C || threadIdx.y != 0) return;
@@ -501,7 +502,7 @@ extern "C" int v2f_bn2d_act_fwd(long long R, int C, const void* x, const void* r
     prof_end(V2F_K_BN_STATS, s);
     V2F_CHECK_LAUNCH();
   }
-  bn_fwd_finalize_kernel<<<(C + 31) / 32, dim3(32, FIN_Y), 0, s>>>(R, C, nblk, part, gamma, beta, run_mean, run_var, training,
+  bn_fwd_finalize_kernel<<<(C + FIN_X - 1) / FIN_X, dim3(FIN_X, FIN_Y), 0, s>>>(R, C, nblk, part, gamma, beta, run_mean, run_var, training,
                                                          momentum, eps, scale_shift, scale_shift + C, save_mean,
                                                          save_rstd);
   V2F_CHECK_LAUNCH();
@@ -557,7 +558,7 @@ extern "C" int v2f_bn2d_act_bwd(long long R, int C, const void* dy, const void* 
 #undef BN_RED
   prof_end(V2F_K_BN_BWD_REDUCE, s);
   V2F_CHECK_LAUNCH();
-  bn_bwd_finalize_kernel<<<(C + 31) / 32, dim3(32, FIN_Y), 0, s>>>(R, C, nred, part, gamma, save_mean, save_rstd, training, dgamma, dbeta, coef);
+  bn_bwd_finalize_kernel<<<(C + FIN_X - 1) / FIN_X, dim3(FIN_X, FIN_Y), 0, s>>>(R, C, nred, part, gamma, save_mean, save_rstd, training, dgamma, dbeta, coef);
   V2F_CHECK_LAUNCH();
   prof_begin(V2F_K_BN_BWD_ELEMT, s);
   prof_bytes(V2F_K_BN_BWD_ELEMT, tb * (3 + ((relu && !dz) ? 1 : 0)));
@@ -592,7 +593,7 @@ extern "C" int v2f_bn2d_relu_maxpool_fwd(int N, int H, int W, int C, const void*
     bn_stats_kernel<<<nblk, BN_THREADS, smem, s>>>(R, C, (const uint4*)x, part);
     V2F_CHECK_LAUNCH();
   }
-  bn_fwd_finalize_kernel<<<(C + 31) / 32, dim3(32, FIN_Y), 0, s>>>(R, C, nblk, part, gamma, beta, run_mean, run_var,
+  bn_fwd_finalize_kernel<<<(C + FIN_X - 1) / FIN_X, dim3(FIN_X, FIN_Y), 0, s>>>(R, C, nblk, part, gamma, beta, run_mean, run_var,
                                                                    training, momentum, eps, scale_shift,
                                                                    scale_shift + C, save_mean, save_rstd);
   V2F_CHECK_LAUNCH();
