@@ -84,3 +84,28 @@ def test_fused_adafactor_state_dict_round_trip_with_reference_optimizer():
         ours.step()
     for rp, op in zip(ref_p, our_p):
         _close(op, rp, 2e-6, f"param {tuple(rp.shape)}")
+
+
+def test_fused_adafactor_parameters_with_different_ages():
+    """A parameter that starts receiving gradients later has its own step count (relative step size, decay): the fused
+    optimizer steps it as its own sub-group, as the per-parameter loop of the reference does."""
+    from transformers.optimization import Adafactor as Ref
+    from visuelle2_multimodal_fusion_b200.optim import Adafactor
+    kw = dict(scale_parameter=True, relative_step=True, warmup_init=True, lr=None)
+    g = torch.Generator().manual_seed(11)
+    shapes = [(50,), (20, 30), (4, 3, 3, 3)]
+    ref_p = [torch.nn.Parameter(torch.randn(s, generator=g)) for s in shapes]
+    our_p = [torch.nn.Parameter(p.detach().clone().cuda()) for p in ref_p]
+    ref, ours = Ref(ref_p, **kw), Adafactor(our_p, **kw)
+    for t in range(5):
+        for i, (rp, op) in enumerate(zip(ref_p, our_p)):
+            if i == 1 and t < 2:               # the matrix joins at step 3
+                rp.grad = op.grad = None
+                continue
+            gr = torch.randn(rp.shape, generator=g)
+            rp.grad, op.grad = gr, gr.clone().cuda()
+        ref.step()
+        ours.step()
+    assert [ours.state[p]["step"] for p in our_p] == [5, 3, 5] == [ref.state[p]["step"] for p in ref_p]
+    for rp, op in zip(ref_p, our_p):
+        _close(op, rp, 2e-6, f"param {tuple(rp.shape)}")

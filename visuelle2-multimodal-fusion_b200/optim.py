@@ -151,7 +151,7 @@ class Adafactor(torch.optim.Optimizer):
         plan.eps1, plan.eps2 = float(group["eps"][0]), float(group["eps"][1])
         plan.clip_threshold = float(group["clip_threshold"])
         plan.scale_parameter = 1 if group["scale_parameter"] else 0
-        return dict(plan=plan, keep=keep, active=active, key=tuple(id(p) for p in active))
+        return dict(plan=plan, keep=keep, active=active)      # ``active`` keeps the parameters (and their ids) alive
 
     # ------------------------------------------------------------------------------------------ step
     @torch.no_grad()
@@ -164,44 +164,52 @@ class Adafactor(torch.optim.Optimizer):
             active = [p for p in group["params"] if p.grad is not None]
             if not active:
                 continue
-            key = tuple(id(p) for p in active)
-            pl = self._plans.get(gi)
-            if pl is None or pl["key"] != key:
-                pl = self._plans[gi] = self._build(group, active)
-            steps = set()
-            k = pl["keep"]
-            turn = k["turn"] = (k["turn"] + 1) % 4
-            if k["grads_ev"][turn] is not None:
-                k["grads_ev"][turn].synchronize()
-            gh = k["grads_host"][turn]
-            ptrs = []
+            # the step count is per parameter (a parameter that starts receiving gradients later is younger); all of them
+            # share it in the reference's models, so there is normally ONE sub-group = one multi-tensor step
+            by_step = {}
             for p in active:
-                g = p.grad
-                if g.stride() != p.stride() or g.dtype != torch.float32 or not g.is_cuda:
-                    if g.is_sparse:
-                        raise RuntimeError("Adafactor does not support sparse gradients.")
-                    # strides of size-1 dims are arbitrary: two row-major tensors are the same layout whatever they say
-                    if g.dtype != torch.float32 or not g.is_cuda or not (p.is_contiguous() and g.is_contiguous()):
-                        g = g.to(device=p.device, dtype=torch.float32)
-                        if not (p.is_contiguous() and g.is_contiguous()):
-                            g = torch.empty_like(p).copy_(g)      # the parameter's memory layout (e.g. channels_last)
-                        p.grad = g
-                ptrs.append(g.data_ptr())
                 st = self.state[p]
+                if len(st) == 0:
+                    self._init_state(p)
                 st["step"] += 1
-                steps.add(st["step"])
-            gh.numpy()[:] = ptrs
-            if len(steps) != 1:
-                raise RuntimeError("fused Adafactor: parameters of one group must share the step count")
-            step = steps.pop()
-            k["grads"].copy_(gh, non_blocking=True)
-            k["grads_ev"][turn] = torch.cuda.Event()
-            k["grads_ev"][turn].record()
-            if group["relative_step"]:
-                min_step = 1e-6 * step if group["warmup_init"] else 1e-2
-                rel = min(min_step, 1.0 / math.sqrt(step))
-            else:
-                rel = float(group["lr"])
-            beta2t = 1.0 - math.pow(step, group["decay_rate"])
-            check(_lib.lib().v2f_adafactor_step(ctypes.byref(pl["plan"]), beta2t, rel, stream()), "v2f_adafactor_step")
+                by_step.setdefault(st["step"], []).append(p)
+            for step, params in by_step.items():
+                self._step_subgroup(gi, group, step, params)
         return loss
+
+    def _step_subgroup(self, gi, group, step, active):
+        key = (gi,) + tuple(id(p) for p in active)
+        pl = self._plans.get(key)
+        if pl is None:
+            if len(self._plans) > 16:            # sets that keep changing: do not hoard plans
+                self._plans.clear()
+            pl = self._plans[key] = self._build(group, active)
+        k = pl["keep"]
+        turn = k["turn"] = (k["turn"] + 1) % 4
+        if k["grads_ev"][turn] is not None:
+            k["grads_ev"][turn].synchronize()
+        gh = k["grads_host"][turn]
+        ptrs = []
+        for p in active:
+            g = p.grad
+            if g.stride() != p.stride() or g.dtype != torch.float32 or not g.is_cuda:
+                if g.is_sparse:
+                    raise RuntimeError("Adafactor does not support sparse gradients.")
+                # strides of size-1 dims are arbitrary: two row-major tensors are the same layout whatever they say
+                if g.dtype != torch.float32 or not g.is_cuda or not (p.is_contiguous() and g.is_contiguous()):
+                    g = g.to(device=p.device, dtype=torch.float32)
+                    if not (p.is_contiguous() and g.is_contiguous()):
+                        g = torch.empty_like(p).copy_(g)      # the parameter's memory layout (e.g. channels_last)
+                    p.grad = g
+            ptrs.append(g.data_ptr())
+        gh.numpy()[:] = ptrs
+        k["grads"].copy_(gh, non_blocking=True)
+        k["grads_ev"][turn] = torch.cuda.Event()
+        k["grads_ev"][turn].record()
+        if group["relative_step"]:
+            min_step = 1e-6 * step if group["warmup_init"] else 1e-2
+            rel = min(min_step, 1.0 / math.sqrt(step))
+        else:
+            rel = float(group["lr"])
+        beta2t = 1.0 - math.pow(step, group["decay_rate"])
+        check(_lib.lib().v2f_adafactor_step(ctypes.byref(pl["plan"]), beta2t, rel, stream()), "v2f_adafactor_step")
