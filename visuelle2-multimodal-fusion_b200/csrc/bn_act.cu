@@ -15,6 +15,8 @@
 // partial sums per block are merged in double by the finalize kernels (no atomics, deterministic).
 #include <cuda_bf16.h>
 
+#include <unordered_map>
+
 #include "common.cuh"
 
 namespace v2f {
@@ -449,13 +451,17 @@ bn_relu_maxpool_kernel(int N, int H, int W, int C, int OH, int OW, const uint4* 
 // run a second, quarter-full wave.
 template <typename K>
 static int resident_per_sm(K kern, size_t smem) {
-  static int cached = 0;
-  if (!cached) {
-    int n = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, BN_THREADS, smem) != cudaSuccess || n < 1) n = 1;
-    cached = n > 4 ? 4 : n;
-  }
-  return cached;
+  // keyed by the kernel's ADDRESS: the instantiations of one template share a function type, so a function-local
+  // static would hand the first variant's occupancy to all of them
+  static std::unordered_map<const void*, int> cache;
+  const void* key = reinterpret_cast<const void*>(kern);
+  auto it = cache.find(key);
+  if (it != cache.end()) return it->second;
+  int n = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, BN_THREADS, smem) != cudaSuccess || n < 1) n = 1;
+  if (n > 4) n = 4;
+  cache[key] = n;
+  return n;
 }
 template <typename K>
 static int wave_blocks(K kern, size_t smem, long long R, int C) {
