@@ -109,3 +109,31 @@ def test_fused_adafactor_parameters_with_different_ages():
     assert [ours.state[p]["step"] for p in our_p] == [5, 3, 5] == [ref.state[p]["step"] for p in ref_p]
     for rp, op in zip(ref_p, our_p):
         _close(op, rp, 2e-6, f"param {tuple(rp.shape)}")
+
+
+def test_fused_adafactor_matches_the_oracle():
+    """CUDA path vs oracle/optim.py (numpy restatement, pinned to transformers' Adafactor on CPU in
+    tests/test_oracle_golden.py) on the same parameters and gradients."""
+    from oracle import optim as oo
+    from visuelle2_multimodal_fusion_b200.optim import Adafactor
+    kw = dict(scale_parameter=True, relative_step=True, warmup_init=True, lr=None)
+    g = torch.Generator().manual_seed(21)
+    shapes = [(300,), (64, 48), (16, 8, 3, 3), (32, 16, 1, 1), (700, 33)]
+    init = [torch.randn(s, generator=g) * 0.2 for s in shapes]
+    ref = [t.numpy().copy() for t in init]
+    states = [oo.adafactor_init(p) for p in ref]
+    our_p = [torch.nn.Parameter(t.clone().cuda()) for t in init]
+    ours = Adafactor(our_p, **kw)
+    for t in range(4):
+        grads = [torch.randn(s, generator=g) * 10.0 ** (t % 3 - 2) for s in shapes]
+        for p, gr, st in zip(ref, grads, states):
+            oo.adafactor_step(p, gr.numpy(), st, **kw)
+        for op, gr in zip(our_p, grads):
+            op.grad = gr.clone().cuda()
+        ours.step()
+    for rp, op, st in zip(ref, our_p, states):
+        _close(op, torch.from_numpy(rp), 2e-6, f"param {rp.shape}")
+        os_ = ours.state[op]
+        for k in ("exp_avg_sq_row", "exp_avg_sq_col", "exp_avg_sq"):
+            if k in st:
+                _close(os_[k], torch.from_numpy(st[k]), 5e-6, f"{k} {rp.shape}")

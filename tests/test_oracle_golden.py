@@ -40,3 +40,46 @@ def _check(name, TOL, floor):
         else:
             assert P[k].grad is not None, f"{name}: {k} has no oracle grad"
             assert_close(P[k].grad, g, TOL, f"{name}:grad:{k}", floor=2e-5 if k in noisy else floor)
+
+
+def test_adafactor_oracle_matches_transformers():
+    """oracle/optim.py (numpy restatement of the fairseq Adafactor the reference's configure_optimizers builds) against
+    transformers.optimization.Adafactor -- the port of that optimizer available in the image -- on CPU."""
+    import numpy as np
+    import torch
+    from transformers.optimization import Adafactor
+    from oracle import optim as oo
+    for kw in (dict(scale_parameter=True, relative_step=True, warmup_init=True, lr=None),
+               dict(scale_parameter=False, relative_step=False, warmup_init=False, lr=1e-3)):
+        g = torch.Generator().manual_seed(4)
+        shapes = [(13,), (40, 24), (6, 5, 3, 3), (2, 3, 10, 12)]
+        ref_p = [torch.nn.Parameter(torch.randn(s, generator=g) * 0.3) for s in shapes]
+        ours = [p.detach().numpy().copy() for p in ref_p]
+        states = [oo.adafactor_init(p) for p in ours]
+        opt = Adafactor(ref_p, **kw)
+        for t in range(5):
+            grads = [torch.randn(s, generator=g) * 10.0 ** (t % 3 - 2) for s in shapes]
+            for p, gr in zip(ref_p, grads):
+                p.grad = gr
+            opt.step()
+            for p, gr, st in zip(ours, grads, states):
+                oo.adafactor_step(p, gr.numpy(), st, **kw)
+        for rp, p, st in zip(ref_p, ours, states):
+            ref = rp.detach().numpy()
+            assert np.abs(p - ref).max() <= 2e-6 * np.abs(ref).max(), rp.shape
+            rs = opt.state[rp]
+            for k in ("exp_avg_sq_row", "exp_avg_sq_col", "exp_avg_sq"):
+                if k in rs:
+                    assert np.abs(st[k] - rs[k].numpy()).max() <= 5e-6 * np.abs(rs[k].numpy()).max(), (rp.shape, k)
+
+
+def test_image_transform_oracle_matches_torchvision():
+    import numpy as np
+    import torch
+    from PIL import Image
+    from torchvision.transforms import Compose, Normalize, ToTensor
+    from oracle import optim as oo
+    u8 = torch.randint(0, 256, (3, 31, 17, 3), dtype=torch.uint8, generator=torch.Generator().manual_seed(0)).numpy()
+    tf = Compose([ToTensor(), Normalize(mean=[0.485, 0.456, 0.406], std=[0.229, 0.224, 0.225])])
+    ref = torch.stack([tf(Image.fromarray(im)) for im in u8]).numpy()
+    assert np.array_equal(oo.normalize_uint8(u8), ref)
