@@ -141,8 +141,8 @@ typedef struct v2f_decode_params {
   const unsigned* tf_mask_dev;
   /* optional scratch of v2f_decode_persist_ws_floats(N,E,H,T) floats: enables the persistent decoder
    * (csrc/decode_persist.cu): the whole T-step loop as ONE cooperative launch with the recurrent and
-   * fusion weights resident in shared memory.  Taken when E is 256 or 512, H % 64 == 0, H <= 512, image and
-   * trend attention are both on, variant != 1 and attn_ws is given; otherwise (or when NULL) the
+   * fusion weights resident in shared memory.  Taken when E is 256 or 512, H % 64 == 0, 148 <= H <= 512 (every CTA of the grid
+   * owns at least one hidden unit), image and trend attention are both on, variant != 1 and attn_ws is given; otherwise (or when NULL) the
    * step-per-launch path runs.  Both paths fill the same saved activations.                         */
   float *persist_ws;
 } v2f_decode_params;

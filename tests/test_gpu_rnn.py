@@ -167,7 +167,7 @@ def test_cuda_graph_replay_equals_eager_step(model):
             assert d <= 1e-5 * float(p.grad.abs().max()) + 1e-9, (k, d)
 
 
-def _head_model(model, E=512, T=None):
+def _head_model(model, E=512, T=None, H=None):
     import torch.nn as nn
     import visuelle2_multimodal_fusion_b200.synth as synth
     import visuelle2_multimodal_fusion_b200.models.modules as mods
@@ -178,9 +178,9 @@ def _head_model(model, E=512, T=None):
         torch.manual_seed(0)
         cat_d, col_d, fab_d = synth.label_dicts()
         if model == "CrossAttnRNN210":
-            m = CrossAttnRNN210.CrossAttnRNN(E, E, E, cat_d, col_d, fab_d, synth.STORE_N, 3, out_len=T or 10)
+            m = CrossAttnRNN210.CrossAttnRNN(E, E, H or E, cat_d, col_d, fab_d, synth.STORE_N, 3, out_len=T or 10)
         else:
-            m = CrossAttnRNNDemand.CrossAttnRNN(E, E, 3, E, cat_d, col_d, fab_d, synth.STORE_N, True, True, True,
+            m = CrossAttnRNNDemand.CrossAttnRNN(E, E, 3, H or E, cat_d, col_d, fab_d, synth.STORE_N, True, True, True,
                                                 True, out_len=T or 12, use_teacher_forcing=True)
     finally:
         mods.resnet101_trunk = orig
@@ -296,3 +296,41 @@ def test_full_size_properties_of_the_decoder(precision, tol):
     assert float((out_p - out[perm]).abs().max()) <= tol * float(out.abs().max())
     assert float((ia_p - ia[:, perm]).abs().max()) <= tol
     assert float((g_p - g[perm]).abs().max()) <= tol * float(g.abs().max())
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 2e-5), ("bf16", 2e-2)])
+@pytest.mark.parametrize("model,E,H", [("CrossAttnRNN210", 512, 256), ("CrossAttnRNN210", 256, 512),
+                                       ("CrossAttnRNNDemand", 512, 256)])
+def test_persistent_decoder_with_hidden_dim_different_from_embedding_dim(model, E, H, precision, tol):
+    """hidden_dim != embedding_dim (the reference's constructors take them separately, train_dl.py:197-199 merely sets
+    both to 512): the persistent decoder against the step-per-launch path."""
+    import visuelle2_multimodal_fusion_b200.functional as Fv
+    import visuelle2_multimodal_fusion_b200.synth as synth
+    from visuelle2_multimodal_fusion_b200 import _lib
+    demand = model == "CrossAttnRNNDemand"
+    m = _head_model(model, E, None, H)
+    m.precision = precision
+    m.use_teacher_forcing = True
+    data, feat = synth.make_batch(20, out_len=10, demand=demand, seed=6, feat_hw=10)
+    data = tuple(t.cuda() for t in data)
+    res, launches = {}, {}
+    for flag in (True, False):
+        Fv.PERSISTENT_DECODE = flag
+        try:
+            f = feat.cuda().clone().requires_grad_(True)
+            torch.manual_seed(9)
+            n0 = _lib.launch_count()
+            out = m(*data, f)[0]
+            launches[flag] = _lib.launch_count() - n0
+            out.square().mean().backward()
+            res[flag] = [out.detach().clone(), f.grad.clone()] + \
+                [p.grad.clone() for _, p in sorted(m.named_parameters()) if p.grad is not None]
+            names = ["out", "grad_feat"] + [k for k, p in sorted(m.named_parameters()) if p.grad is not None]
+            m.zero_grad(set_to_none=True)
+        finally:
+            Fv.PERSISTENT_DECODE = True
+    assert launches[True] < launches[False] - 40, launches
+    for k, a, b in zip(names, res[True], res[False]):
+        floor = 1e-6 if k.endswith("attn_linear.bias") else 1e-9
+        assert float((a - b).abs().max()) <= tol * float(b.abs().max()) + floor, (k, float((a - b).abs().max()),
+                                                                                 float(b.abs().max()))
