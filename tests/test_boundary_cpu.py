@@ -174,3 +174,39 @@ def test_persistent_decoder_column_ownership_is_a_partition():
         assert hc[0] == list(range(E)) and hc[1] == list(range(E))
     assert lib.v2f_decode_persist_ownership(5, 1, 512, 512, out) != 0          # bad grid
     assert lib.v2f_decode_persist_ws_floats(128, 512, 512, 10) > 3 * 512 * 512
+
+
+def test_batched_weight_cast_host_logic():
+    """trunk._bf16_weights / _CastWeights (host logic, runs on CPU tensors too): trainable weights are cast by one
+    multi-tensor copy whose backward returns fp32 gradients equal to the per-convolution ``weight.to(bf16)`` path that
+    autocast takes; frozen weights are cached until they change."""
+    import torch
+    import torch.nn as nn
+    import torch.nn.functional as F
+    from visuelle2_multimodal_fusion_b200 import trunk
+    torch.manual_seed(0)
+    convs = [nn.Conv2d(4, 6, 3, padding=1, bias=False), nn.Conv2d(6, 5, 1, bias=False), nn.Conv2d(5, 3, 3, bias=False)]
+    convs[1].weight.requires_grad_(False)                        # a frozen one in the middle
+    x = torch.randn(2, 4, 8, 8).to(torch.bfloat16)
+
+    def run(weights):
+        y = x
+        for c, w in zip(convs, weights):
+            y = F.conv2d(y, w, None, c.stride, c.padding, c.dilation, c.groups)
+        return y.float().square().sum()
+
+    w16 = trunk._bf16_weights(convs)
+    assert all(w16[c].dtype == torch.bfloat16 and w16[c].shape == c.weight.shape for c in convs)
+    assert w16[convs[1]] is trunk._bf16_weights(convs)[convs[1]]            # frozen: cached
+    run([w16[c] for c in convs]).backward()
+    got = [c.weight.grad.clone() if c.weight.grad is not None else None for c in convs]
+    for c in convs:
+        c.weight.grad = None
+    run([c.weight.to(torch.bfloat16) for c in convs]).backward()
+    for c, g in zip(convs, got):
+        if not c.weight.requires_grad:
+            assert g is None and c.weight.grad is None
+        else:
+            assert g.dtype == torch.float32 and torch.equal(g, c.weight.grad)
+    with torch.no_grad():
+        assert all(not w.requires_grad for w in trunk._bf16_weights(convs).values())   # inference: plain cached copies
