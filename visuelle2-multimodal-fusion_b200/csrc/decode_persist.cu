@@ -784,7 +784,9 @@ static int dp_launch(const DpArgs& a, int G, size_t smem, cudaStream_t s) {
   static bool attr = false;
   auto kern = decode_persist_fwd_kernel<CPT, TC>;
   if (!attr) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    // once per instantiation, for the largest configuration it can be asked to run (the size depends on H as well:
+    // setting it to the first call's size made a later, larger H fall back to the step-per-launch path)
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
       return V2F_ERR_LAUNCH;
     attr = true;
   }
