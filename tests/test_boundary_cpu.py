@@ -42,6 +42,14 @@ def test_decode_params_struct_matches_header():
         decl = re.sub(r"^(const\s+)?(unsigned|int|float|long long)\s*", "", decl)
         fields += [f.strip().lstrip("*").strip() for f in decl.split(",")]
     assert fields == [f[0] for f in DecodeParams._fields_]
+    import subprocess
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:                      # and the same size as the C compiler gives it
+        c = os.path.join(d, "s.c")
+        open(c, "w").write('#include <stdio.h>\n#include "v2f.h"\n'
+                           'int main(void){printf("%zu", sizeof(v2f_decode_params));return 0;}\n')
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", os.path.join(d, "s")])
+        assert int(subprocess.check_output([os.path.join(d, "s")]).decode()) == ctypes.sizeof(DecodeParams)
 
 
 @pytest.mark.parametrize("name", ["rnn210_small", "rnn21_small", "demand_small", "gtm_demand_eval", "gtm_ar_eval",
@@ -210,3 +218,30 @@ def test_batched_weight_cast_host_logic():
             assert g.dtype == torch.float32 and torch.equal(g, c.weight.grad)
     with torch.no_grad():
         assert all(not w.requires_grad for w in trunk._bf16_weights(convs).values())   # inference: plain cached copies
+
+
+@pytest.mark.parametrize("cname,mirror", [("v2f_af_desc", "AfDesc"), ("v2f_adafactor_plan", "AfPlan")])
+def test_adafactor_structs_match_header(cname, mirror):
+    """Field order AND size of the ctypes mirrors of the optimizer's ABI structs == the C declarations (the size is
+    checked by compiling a two-line C program against include/v2f.h with the host compiler)."""
+    import subprocess
+    import tempfile
+    from visuelle2_multimodal_fusion_b200 import _lib
+    cls = getattr(_lib, mirror)
+    src = open(os.path.join(ROOT, "include", "v2f.h")).read()
+    body = src[src.index("typedef struct %s {" % cname):src.index("} %s;" % cname)]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S).split("{", 1)[1]
+    fields = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        decl = re.sub(r"^(const\s+)?(v2f_af_desc|unsigned|int|float|double|long long|void)\s*", "", decl)
+        fields += [re.sub(r"\[\d+\]$", "", f.strip().lstrip("*").strip()) for f in decl.split(",")]
+    assert fields == [f[0] for f in cls._fields_]
+    with tempfile.TemporaryDirectory() as d:
+        c = os.path.join(d, "s.c")
+        open(c, "w").write('#include <stdio.h>\n#include "v2f.h"\nint main(void){printf("%%zu", sizeof(%s));return 0;}\n' % cname)
+        exe = os.path.join(d, "s")
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
+        assert int(subprocess.check_output([exe]).decode()) == ctypes.sizeof(cls)
