@@ -220,3 +220,58 @@ def compare_blob(blob, tol, report=None, precision="fp32"):
         else:
             cmp("grad:" + k, mine, g)
     return rows
+
+
+def oracle_vs_cuda_default_dims(model, T, precision, tol, B=4, E=512, H=512, seed=11):
+    """One forward + loss + backward of a CrossAttnRNN drop-in at the reference's default dims (E=A=H=512, Li=100,
+    Lt=52, train_dl.py:197-199; feature maps in) on cuda:0 through the C ABI, compared with the oracle (CPU) on
+    outputs, loss, feature-map gradient and every parameter gradient.  Returns the number of tensors compared."""
+    import torch.nn as nn
+    import visuelle2_multimodal_fusion_b200.models.modules as mods
+    import visuelle2_multimodal_fusion_b200.synth as synth
+    torch.manual_seed(3)
+    cfg = dict(E=E, A=E, H=H, T=T, B=B, tf=True, seed=seed)
+    blob = dict(model=model, cfg=cfg, state={})
+    orig = mods.resnet101_trunk
+    mods.resnet101_trunk = lambda: nn.Identity()
+    try:
+        from visuelle2_multimodal_fusion_b200.models import CrossAttnRNN21, CrossAttnRNN210, CrossAttnRNNDemand
+        cat_d, col_d, fab_d = synth.label_dicts()
+        # random weights from the product module's own (reference-identical) initialisation
+        if model == "CrossAttnRNN210":
+            m = CrossAttnRNN210.CrossAttnRNN(E, E, H, cat_d, col_d, fab_d, synth.STORE_N, 3, out_len=T)
+        elif model == "CrossAttnRNN21":
+            m = CrossAttnRNN21.CrossAttnRNN(E, E, H, cat_d, col_d, fab_d, synth.STORE_N, 3)
+        else:
+            m = CrossAttnRNNDemand.CrossAttnRNN(E, E, 3, H, cat_d, col_d, fab_d, synth.STORE_N, True, True, True,
+                                                True, out_len=T, use_teacher_forcing=True)
+    finally:
+        mods.resnet101_trunk = orig
+    blob["state"] = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    demand = model == "CrossAttnRNNDemand"
+    data, feat = synth.make_batch(B, out_len=(1 if model == "CrossAttnRNN21" else 10), demand=demand, seed=seed,
+                                  feat_hw=10)
+    keys = ["ts", "cat", "col", "fab", "store", "temporal", "gtrends"] if demand else \
+        ["X", "y", "cat", "col", "fab", "store", "temporal", "gtrends"]
+    blob["inputs"] = dict(zip(keys, data), feat=feat)
+    torch.manual_seed(cfg["seed"] + 1)
+    blob["tf_mask"] = [bool(torch.rand(1) < 0.5) for _ in range(T)]
+    o_out, o_loss, o_extras, P, o_feat = oracle_run(blob)
+    o_loss.backward()
+    m = m.cuda().eval()
+    m.precision = precision
+    out, loss, extras, grads, gfeat = product_run(m, blob)
+    assert_close(out, o_out, tol, "out")
+    assert_close(loss, o_loss, tol, "loss")
+    assert_close(gfeat, o_feat.grad, tol, "grad_feat")
+    n = 3
+    for k, p in P.items():
+        if p.grad is None:
+            continue
+        assert grads.get(k) is not None, k
+        # attn_linear.bias feeds a softmax, so its true gradient is exactly 0 (the kernel returns 0,
+        # autograd returns rounding noise): compare those absolutely
+        floor = 1e-6 if k.endswith("attn_linear.bias") else 1e-6 * float(p.grad.abs().max() + 1e-3)
+        assert_close(grads[k], p.grad, tol, "grad:" + k, floor=floor)
+        n += 1
+    return n

@@ -22,6 +22,10 @@ def shard_batch(batch, rank, world):
 
     def cut(t):
         n = t.shape[0]
+        if n % world:
+            # a silently dropped remainder would also make the mean of the per-rank mean losses differ from the
+            # global mean; the caller pads or drops the last incomplete batch (DataLoader(drop_last=True))
+            raise ValueError(f"batch of {n} items does not split evenly over {world} ranks")
         per = n // world
         return t[rank * per:(rank + 1) * per]
 
@@ -29,7 +33,7 @@ def shard_batch(batch, rank, world):
 
 
 class GradReducer:
-    def __init__(self, module, bucket_bytes=25 << 20, group=None, hooks=True):
+    def __init__(self, module, bucket_bytes=25 << 20, group=None, hooks=True, broadcast=True):
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         params = [p for p in module.parameters() if p.requires_grad]
@@ -51,6 +55,12 @@ class GradReducer:
         self.avg_in_collective = self.cuda and dist.is_initialized() and dist.get_backend(group) == "nccl"
         self.stream = torch.cuda.Stream() if self.cuda else None
         self._reset()
+        if broadcast and self.world > 1:
+            # replicas start from rank 0's parameters AND buffers (BatchNorm running statistics, counters), like
+            # DistributedDataParallel does; afterwards the buffers evolve per rank (per-rank batch statistics)
+            with torch.no_grad():
+                for t in list(module.parameters()) + list(module.buffers()):
+                    dist.broadcast(t.data, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
         # hooks=False: no overlap with backward; call reduce_now() after the step (CUDA-graph replay, where the
         # backward is one opaque launch and the hooks would only fire at capture time)
         self.hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in params] if hooks else []

@@ -16,7 +16,48 @@ What makes the step capturable:
 Gradients are left in ``p.grad`` (static storage): run the optimizer / ``ddp.GradReducer.reduce_now``
 after the call.
 """
+import contextlib
+
 import torch
+
+
+class _TfWord:
+    """The teacher-forcing bits of one replay: a device word the captured kernels read, refreshed from a small ring
+    of pinned host words guarded by events (the host may run several steps ahead of the GPU: a single pinned word
+    could be overwritten before its copy has executed, and step i would train with step i+1's bits)."""
+
+    def __init__(self, dev, depth=4):
+        self.dev = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.host = [torch.zeros(1, dtype=torch.int32).pin_memory() for _ in range(depth)]
+        self.ev = [None] * depth
+        self.turn = 0
+
+    def set(self, bits):
+        t = self.turn = (self.turn + 1) % len(self.host)
+        if self.ev[t] is not None:
+            self.ev[t].synchronize()
+        self.host[t][0] = int(bits) & 0x7FFFFFFF
+        self.dev.copy_(self.host[t], non_blocking=True)
+        self.ev[t] = torch.cuda.Event()
+        self.ev[t].record()
+
+
+@contextlib.contextmanager
+def _tf_installed(model, word):
+    """The module reads ``model._tf_mask_dev`` instead of drawing on the host ONLY while a Graphed* object warms up /
+    captures; eager calls (validation_step between graphed epochs, a forecast after training) never see it."""
+    if word is None:
+        yield
+        return
+    prev = model.__dict__.get("_tf_mask_dev")
+    model._tf_mask_dev = word.dev
+    try:
+        yield
+    finally:
+        if prev is None:
+            model.__dict__.pop("_tf_mask_dev", None)
+        else:
+            model._tf_mask_dev = prev
 
 
 def _tree_map(fn, obj):
@@ -54,13 +95,11 @@ class GraphedTrainStep:
         self.device = dev
         self.static_batch = _tree_map(lambda t: t.to(dev, copy=True), example_batch)
         self.has_tf = hasattr(model, "draw_tf_mask")
-        if self.has_tf:
-            model._tf_mask_dev = torch.zeros(1, dtype=torch.int32, device=dev)
-            self._tf_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self._tf = _TfWord(dev) if self.has_tf else None      # owned here, not by the module
         self.params = [p for p in model.parameters() if p.requires_grad]
         side = self.side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(side):
+        with torch.cuda.stream(side), _tf_installed(model, self._tf):
             for i in range(warmup):                       # lazy initialisations happen outside the capture
                 self._refresh_tf()
                 loss = model.training_step(self.static_batch, i)
@@ -74,7 +113,8 @@ class GraphedTrainStep:
         from . import _lib
         l0 = _lib.launch_count()
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph, stream=side):     # same stream as the warm-up: no AccumulateGrad stream mismatch
+        # same stream as the warm-up: no AccumulateGrad stream mismatch
+        with _tf_installed(model, self._tf), torch.cuda.graph(self.graph, stream=side):
             self.static_loss = model.training_step(self.static_batch, 0)
             self.static_loss.backward()
             if reducer is not None:
@@ -83,9 +123,8 @@ class GraphedTrainStep:
 
     def _refresh_tf(self):
         if self.has_tf:
-            y = self.static_batch[0][1] if not isinstance(self.static_batch[0], dict) else None
-            self._tf_host[0] = self.model.draw_tf_mask(y is not None) & 0x7FFFFFFF
-            self.model._tf_mask_dev.copy_(self._tf_host, non_blocking=True)
+            # the reference's host draws of this step, in its order; 0 when teacher forcing is off
+            self._tf.set(self.model.draw_tf_mask(True))
 
     def __call__(self, batch):
         _tree_copy(self.static_batch, batch)              # device->device (or pinned host->device) into the graph's inputs
@@ -94,9 +133,8 @@ class GraphedTrainStep:
         return self.static_loss
 
     def release(self):
-        """Back to eager: the module draws its teacher-forcing bits on the host again."""
-        if self.has_tf:
-            self.model._tf_mask_dev = None
+        """Kept for callers of the first version: the module is never left in graph mode any more (the device word
+        is installed only around warm-up and capture), so there is nothing to undo."""
 
 
 class GraphedForecast:
@@ -115,21 +153,25 @@ class GraphedForecast:
         dev = next(model.parameters()).device
         self.static_in = _tree_map(lambda t: t.to(dev, copy=True), tuple(example_inputs))
         self.has_tf = hasattr(model, "draw_tf_mask")
-        if self.has_tf:
-            model._tf_mask_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._tf = _TfWord(dev) if self.has_tf else None
         side = self.side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(side), torch.no_grad():
+        with torch.cuda.stream(side), torch.no_grad(), _tf_installed(model, self._tf):
             for _ in range(warmup):
+                self._refresh_tf(self.static_in)
                 model(*self.static_in)
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         self.graph = torch.cuda.CUDAGraph()
-        with torch.no_grad(), torch.cuda.graph(self.graph, stream=side):
+        with torch.no_grad(), _tf_installed(model, self._tf), torch.cuda.graph(self.graph, stream=side):
             self.static_out = model(*self.static_in)
+
+    def _refresh_tf(self, inputs):
+        """Consume the host draws the reference makes in this forward and hand the bits to the captured kernels:
+        0 unless the module has teacher forcing on AND targets are among the inputs (a forecast normally has it off;
+        CrossAttnRNNDemand draws 12 numbers even then, models/CrossAttnRNNDemand.py:343-345)."""
         if self.has_tf:
-            self._tf_zero = model._tf_mask_dev     # the captured kernels read this word (all zero: no forcing in a forecast)
-            model._tf_mask_dev = None              # eager calls draw on the host again
+            self._tf.set(self.model.draw_tf_mask(self.model.tf_targets_given(inputs)))
 
     def _same_shapes(self, inputs):
         flat_a, flat_b = [], []
@@ -141,8 +183,7 @@ class GraphedForecast:
         if not self._same_shapes(inputs):
             with torch.no_grad():
                 return self.model(*inputs)
-        if self.has_tf:
-            self.model.draw_tf_mask(False)        # consume the host draws of this forward; eval ignores the bits
+        self._refresh_tf(inputs)
         _tree_copy(self.static_in, tuple(inputs))
         self.graph.replay()
         return self.static_out

@@ -45,7 +45,14 @@ class CrossAttnRNN(LightningBase):
         self.decoder_fc = nn.Linear(hidden_dim, 1)
 
     precision = "fp32"     # "bf16": tcgen05 tensor-core GEMMs (2e-2 contract), see functional.set_precision
-    _tf_mask_dev = None    # int32[1] CUDA tensor when the step is replayed from a CUDA graph
+    # int32[1] CUDA tensor, installed by graphs.Graphed* ONLY around their warm-up / capture (the captured kernels
+    # read the bits from it; the Graphed object refreshes them per replay with draw_tf_mask); None in every eager call
+    _tf_mask_dev = None
+
+    @staticmethod
+    def tf_targets_given(inputs):
+        """``y`` of a positional ``forward`` input tuple."""
+        return inputs[1] is not None
 
     def draw_tf_mask(self, has_y=True):
         """The reference's host draws: ``torch.rand(1) < ratio`` once per step, only when teacher forcing is on

@@ -58,7 +58,13 @@ class CrossAttnRNN(LightningBase):
         self.save_hyperparameters()
 
     precision = "fp32"     # "bf16": tcgen05 tensor-core GEMMs (2e-2 contract), see functional.set_precision
-    _tf_mask_dev = None    # int32[1] CUDA tensor when the step is replayed from a CUDA graph
+    # int32[1] CUDA tensor, installed by graphs.Graphed* ONLY around their warm-up / capture; None in every eager call
+    _tf_mask_dev = None
+
+    @staticmethod
+    def tf_targets_given(inputs):
+        """``ts`` of a positional ``forward`` input tuple."""
+        return inputs[0] is not None
 
     def draw_tf_mask(self, has_y=True):
         """One host draw per step, always -- even in eval (reference :343-345); the bits are only honoured when

@@ -213,3 +213,7 @@ class Adafactor(torch.optim.Optimizer):
             rel = float(group["lr"])
         beta2t = 1.0 - math.pow(step, group["decay_rate"])
         check(_lib.lib().v2f_adafactor_step(ctypes.byref(pl["plan"]), beta2t, rel, stream()), "v2f_adafactor_step")
+        # fairseq writes group["lr"] = _get_lr(...) for every parameter, so the value the reference prints/logs in
+        # validation_epoch_end is the LAST parameter's: rel * max(eps2, RMS(p)) (device scalar, read lazily)
+        if group["relative_step"]:
+            group["lr"] = (k["rms"][-1].clamp_min(float(group["eps"][1])) * rel) if group["scale_parameter"] else rel

@@ -205,6 +205,7 @@ class _CastWeights(torch.autograd.Function):
 
 
 BATCHED_WEIGHT_CASTS = os.environ.get("V2F_BATCHED_CASTS", "1") != "0"      # A/B switch
+CAST_GROUP_ELEMS = int(os.environ.get("V2F_CAST_GROUP_ELEMS", str(6 << 20)))   # ~25 MB of fp32 gradient per group
 # weight Parameter -> (version, data_ptr, bf16 copy); weak keys: an entry dies with its parameter (an id()-keyed dict
 # handed the copy of a freed model's weight to the next model whose parameter reused the id)
 _frozen_cache = WeakTensorKeyDictionary()
@@ -213,9 +214,29 @@ _frozen_cache = WeakTensorKeyDictionary()
 def _bf16_weights(convs):
     """{conv: bf16 weight} for the convolutions of one trunk forward."""
     out = {}
-    train = [c for c in convs if c.weight.requires_grad and torch.is_grad_enabled()]
+    # trainable weights are re-cast on EVERY forward, with or without autograd: optim.Adafactor updates them from a
+    # CUDA kernel through raw pointers, which does not bump Tensor._version, so a cached copy keyed on the version went
+    # stale after the first no_grad pass (validation / forecast used the weights of that first pass for ever).  Only
+    # frozen weights (requires_grad=False: layer1/layer2 and the stem in the reference) are cached.
+    train = [c for c in convs if c.weight.requires_grad]
     if train:
-        for c, w in zip(train, _CastWeights.apply(*[c.weight for c in train])):
+        if torch.is_grad_enabled():
+            # one multi-tensor cast per group of consecutive layers (~CAST_GROUP_ELEMS weights): a group's fp32
+            # gradients appear as soon as ITS earliest layer's weight gradient exists, not at the very end of the
+            # backward, so ddp.GradReducer's buckets can be all-reduced while the rest of the trunk still runs
+            cast, grp, n = [], [], 0
+            for c in train:
+                grp.append(c)
+                n += c.weight.numel()
+                if n >= CAST_GROUP_ELEMS:
+                    cast.extend(_CastWeights.apply(*[g.weight for g in grp]))
+                    grp, n = [], 0
+            if grp:
+                cast.extend(_CastWeights.apply(*[g.weight for g in grp]))
+        else:
+            cast = [torch.empty_like(c.weight, dtype=torch.bfloat16) for c in train]
+            torch._foreach_copy_(cast, [c.weight.detach() for c in train])
+        for c, w in zip(train, cast):
             out[c] = w
     stale = []
     for c in convs:
