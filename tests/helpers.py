@@ -275,3 +275,101 @@ def oracle_vs_cuda_default_dims(model, T, precision, tol, B=4, E=512, H=512, see
         assert_close(grads[k], p.grad, tol, "grad:" + k, floor=floor)
         n += 1
     return n
+
+
+# ------------------------------------------------------------------ full-size fixtures (oracle/make_golden_full.py)
+def sample_index(numel, k=4096):
+    if numel <= k:
+        return torch.arange(numel)
+    return torch.linspace(0, numel - 1, k).long().unique()
+
+
+def full_model(blob, device="cpu"):
+    """The drop-in module of a full_*.pt fixture: constructed under the fixture's seed (backbone = identity), with the
+    per-tensor checksums of the reference's state verified -- the fixture does not carry the 80 MB of weights."""
+    import torch.nn as nn
+    import visuelle2_multimodal_fusion_b200.models.modules as mods
+    import visuelle2_multimodal_fusion_b200.synth as synth
+    from visuelle2_multimodal_fusion_b200.models import CrossAttnRNN21, CrossAttnRNN210, CrossAttnRNNDemand
+    cfg, kind = blob["cfg"], blob["kind"]
+    E, H, T = cfg["E"], cfg["H"], cfg["T"]
+    cat_d, col_d, fab_d = synth.label_dicts()
+    orig = mods.resnet101_trunk
+    mods.resnet101_trunk = lambda: nn.Identity()
+    try:
+        torch.manual_seed(cfg["seed"])
+        if kind == "rnn210":
+            m = CrossAttnRNN210.CrossAttnRNN(E, E, H, cat_d, col_d, fab_d, synth.STORE_N, 3, out_len=T,
+                                             use_teacher_forcing=cfg["tf"], teacher_forcing_ratio=0.5)
+        elif kind == "rnn21":
+            m = CrossAttnRNN21.CrossAttnRNN(E, E, H, cat_d, col_d, fab_d, synth.STORE_N, 3)
+        else:
+            m = CrossAttnRNNDemand.CrossAttnRNN(E, E, 3, H, cat_d, col_d, fab_d, synth.STORE_N, True, True, True, True,
+                                                out_len=T, use_teacher_forcing=cfg["tf"], teacher_forcing_ratio=0.5)
+    finally:
+        mods.resnet101_trunk = orig
+    sd = m.state_dict()
+    for k, (s, a) in blob["checksum"].items():
+        v = sd[k].double()
+        assert abs(float(v.sum()) - s) <= 1e-9 * max(a, 1.0) and abs(float(v.abs().sum()) - a) <= 1e-9 * max(a, 1.0), \
+            f"same-seed initialisation differs from the reference's for {k}"
+    return m.to(device)
+
+
+def full_inputs(blob):
+    import visuelle2_multimodal_fusion_b200.synth as synth
+    cfg, kind = blob["cfg"], blob["kind"]
+    data, feat = synth.make_batch(cfg["B"], out_len=(1 if kind == "rnn21" else 10), demand=(kind == "demand"),
+                                  seed=cfg["seed"] + 1, feat_hw=cfg["hw"])
+    if kind == "demand":
+        data = (data[0][:, :cfg["T"]].contiguous(),) + data[1:]
+    return data, feat
+
+
+def full_compare(blob, out, loss, extras, grads, gfeat, tol):
+    """outputs / loss / attention maps in full; every gradient by L2 norm and by the strided sample."""
+    assert_close(out, blob["out"], tol, "out")
+    assert_close(loss, blob["loss"], tol, "loss")
+    for k, v in blob["extras"].items():
+        assert_close(extras[k], v, tol, k, floor=1e-6)
+    n = 2
+
+    def one(what, mine, ref):
+        nonlocal n
+        assert mine is not None, what + " missing"
+        mine = mine.detach().double().cpu().reshape(-1)
+        floor = 1e-6 if what.endswith("attn_linear.bias") else 1e-6 * (ref["absmax"] + 1e-3)
+        d = float((mine[sample_index(mine.numel())] - ref["sample"].double()).abs().max())
+        assert d <= tol * ref["absmax"] + floor, f"{what}: sample max|diff|={d:.3e} absmax={ref['absmax']:.3e} tol={tol}"
+        dn = abs(float(mine.norm()) - ref["norm"])
+        assert dn <= tol * ref["norm"] + floor * mine.numel() ** 0.5, f"{what}: norm {float(mine.norm()):.6e} vs {ref['norm']:.6e}"
+        n += 1
+
+    one("grad_feat", gfeat, blob["grad_feat"])
+    for k, ref in blob["grads"].items():
+        if ref is None:
+            assert grads.get(k) is None or float(grads[k].abs().max()) == 0.0, k
+        else:
+            one("grad:" + k, grads.get(k), ref)
+    return n
+
+
+def full_run(m, blob, device):
+    """forward + training loss + backward of module ``m`` (product on CUDA) on the fixture's regenerated inputs."""
+    import torch.nn.functional as F
+    data, feat = full_inputs(blob)
+    data = tuple(t.to(device) for t in data)
+    feat = feat.to(device).requires_grad_(True)
+    kind = blob["kind"]
+    torch.manual_seed(blob["cfg"]["seed"] + 2)       # the host teacher-forcing draws of make_golden_full
+    extras = {}
+    if kind == "demand":
+        out, ia, ma = m(*data, feat)
+        extras = dict(img_alphas=torch.stack(ia), mm_alphas=torch.stack(ma))
+        loss = F.mse_loss(data[0], out.squeeze())
+    else:
+        out, _ = m(*data, feat)
+        y = data[1]
+        loss = F.mse_loss(y.reshape(out.shape) if kind == "rnn210" else y, out)
+    loss.backward()
+    return out, loss, extras, {k: p.grad for k, p in m.named_parameters()}, feat.grad

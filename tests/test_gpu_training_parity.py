@@ -16,8 +16,8 @@ def _product(blob):
     import torch.nn as nn
     import visuelle2_multimodal_fusion_b200.synth as synth
     import visuelle2_multimodal_fusion_b200.models.modules as mods
-    from visuelle2_multimodal_fusion_b200.models import CrossAttnRNN210, CrossAttnRNNDemand
-    cfg, kind = blob["cfg"], blob["kind"]
+    from visuelle2_multimodal_fusion_b200.models import CrossAttnRNN21, CrossAttnRNN210, CrossAttnRNNDemand
+    cfg, kind = blob["cfg"], blob["kind"].replace("dropout_", "")
     cat_d, col_d, fab_d = synth.label_dicts()
     E, H = cfg["E"], cfg["H"]
     orig = mods.resnet101_trunk
@@ -25,6 +25,8 @@ def _product(blob):
     try:
         if kind == "rnn210":
             m = CrossAttnRNN210.CrossAttnRNN(E, E, H, cat_d, col_d, fab_d, synth.STORE_N, 3, out_len=10)
+        elif kind == "rnn21":
+            m = CrossAttnRNN21.CrossAttnRNN(E, E, H, cat_d, col_d, fab_d, synth.STORE_N, 3)
         elif kind == "demand":
             m = CrossAttnRNNDemand.CrossAttnRNN(E, E, 3, H, cat_d, col_d, fab_d, synth.STORE_N, True, True, True, True,
                                                 out_len=12)
@@ -38,24 +40,16 @@ def _product(blob):
     return m.cuda()
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16"])
-@pytest.mark.parametrize("kind", ["rnn210", "demand", "gtm", "v4"])
-def test_training_run_matches_reference_metrics(kind, precision):
+def _check_run(kind, precision, blob, m, batches, val):
     from oracle.make_golden_train import metrics, run_training
-    from oracle.refshim import zero_dropout
-    blob = load_golden("train_" + kind)
-    m = zero_dropout(_product(blob))
-    m.precision = precision
-    to = lambda b: (tuple(t.cuda() for t in b[0]), b[1].cuda())
-    losses, y, f = run_training(m, [to(b) for b in blob["batches"]], to(blob["val"]), blob["cfg"]["steps"])
+    losses, y, f = run_training(m, batches, val, blob["cfg"]["steps"])
     mae, wape = metrics(y, f, blob["cfg"]["abs_den"])
     print(f"{kind} {precision}: MAE {mae:.4f} vs {blob['mae']:.4f}   WAPE {wape:.3f} vs {blob['wape']:.3f}   "
           f"last loss {losses[-1]:.6f} vs {blob['losses'][-1]:.6f}")
-    # the contract: forecast metrics within 0.1 points of the reference run.  The bound is meant for WAPEs of
-    # order 100 %; an untrained model on the sparse synthetic targets sits at 440-1150 %, so it is applied per
-    # 100 points of reference WAPE (i.e. 0.1 % relative there), and as is to the MAE.
+    # the contract as written (BASELINE.json): forecast metrics within 0.1 points of the reference run, both
+    # precisions.  The fixtures use dense targets, so the WAPE is of order 100 %.
     assert abs(mae - blob["mae"]) <= 0.1
-    assert abs(wape - blob["wape"]) <= 0.1 * max(1.0, blob["wape"] / 100.0)
+    assert abs(wape - blob["wape"]) <= 0.1
     ref = torch.tensor(blob["losses"])
     got = torch.tensor(losses)
     curve = float(((got - ref).abs() / ref.abs().clamp_min(1e-6)).max())
@@ -63,7 +57,7 @@ def test_training_run_matches_reference_metrics(kind, precision):
         # RNN family: bit-level agreement of the whole run.  GTM family: Adafactor turns the rounding-noise
         # gradients of parameters whose exact gradient is 0 (biases in front of a train-mode BatchNorm) into
         # O(lr) random-walk updates on both sides, which the running statistics then carry into eval mode.
-        tight = kind in ("rnn210", "demand")
+        tight = kind in ("rnn210", "rnn21", "demand")
         assert curve < (1e-4 if tight else 3e-3), curve
         tol = 1e-4 if tight else 2e-3
         assert float((f - blob["val_forecast"]).abs().max()) <= tol * float(blob["val_forecast"].abs().max()) + 1e-6
@@ -74,3 +68,65 @@ def test_training_run_matches_reference_metrics(kind, precision):
                 assert d <= 1e-3 * float(v.abs().max()) + 1e-6, (k, d)
     else:
         assert curve < 2e-2, curve
+
+
+def _to(b):
+    return tuple(t.cuda() for t in b[0]), b[1].cuda()
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("kind", ["rnn210", "rnn21", "demand", "gtm", "v4"])
+def test_training_run_matches_reference_metrics(kind, precision):
+    """Small dims (E=32): 60 Adafactor steps + validation; SO-fore2-10, SO-fore2-1, Demand, GTM, v4."""
+    from oracle.refshim import zero_dropout
+    blob = load_golden("train_" + kind)
+    m = zero_dropout(_product(blob))
+    m.precision = precision
+    _check_run(kind, precision, blob, m, [_to(b) for b in blob["batches"]], _to(blob["val"]))
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("kind", ["rnn210", "rnn21", "demand"])
+def test_training_run_at_default_dims_matches_reference_metrics(kind, precision):
+    """E=A=H=512: the trajectories run on the kernels the benchmark times (persistent decoder, streaming attention,
+    tcgen05 GEMMs, persistent GRU).  Weights from the fixture's seed (checksums verified), batches from its seeds."""
+    import visuelle2_multimodal_fusion_b200.synth as synth
+    from helpers import full_model
+    from oracle.refshim import zero_dropout
+    blob = load_golden("train512_" + kind)
+    cfg = blob["cfg"]
+    m = zero_dropout(full_model(blob, "cuda"))
+    m.precision = precision
+
+    def mk(s, n):
+        return _to(synth.make_batch(n, out_len=cfg["out_len"], demand=cfg["demand"], seed=s, feat_hw=cfg["hw"],
+                                    dense_sales=True))
+
+    _check_run(kind, precision, blob, m, [mk(s, cfg["B"]) for s in cfg["batch_seeds"]], mk(cfg["val_seed"], cfg["val_B"]))
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_dropout_on_training_is_statistically_the_reference(precision):
+    """Dropout ON: 12 independent 30-step runs per side from the same initial state.  The masks come from different
+    generators (the product's kernels use torch's CUDA Philox stream), so the comparison is of distributions: at every
+    step the product's mean loss must lie within 4 standard errors of the reference's mean, and the spread of the
+    runs (what dropout adds) must be of the same size."""
+    from oracle.make_golden_train import run_dropout_training
+    blob = load_golden("train_dropout_rnn210")
+    ref = blob["curves"].double()
+    S, K = ref.shape
+    batches = [_to(b) for b in blob["batches"]]
+    curves = []
+    for s in range(S):
+        m = _product(blob)
+        m.precision = precision
+        curves.append(run_dropout_training(m, batches, K, 19000 + 31 * s))
+    got = torch.tensor(curves).double()
+    se = ((ref.var(0) + got.var(0)) / S).sqrt()
+    z = ((got.mean(0) - ref.mean(0)).abs() / se.clamp_min(1e-9))
+    print(f"dropout-on {precision}: max z {float(z.max()):.2f}, mean loss {float(got.mean()):.5f} vs {float(ref.mean()):.5f}, "
+          f"run-to-run std {float(got.std(0).mean()):.5f} vs {float(ref.std(0).mean()):.5f}")
+    assert float(z.max()) < 4.0, z
+    assert abs(float(got.mean()) - float(ref.mean())) <= 0.03 * float(ref.mean())
+    ratio = float(got.std(0).mean() / ref.std(0).mean())
+    assert 0.6 < ratio < 1.6, ratio

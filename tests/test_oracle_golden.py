@@ -83,3 +83,32 @@ def test_image_transform_oracle_matches_torchvision():
     tf = Compose([ToTensor(), Normalize(mean=[0.485, 0.456, 0.406], std=[0.229, 0.224, 0.225])])
     ref = torch.stack([tf(Image.fromarray(im)) for im in u8]).numpy()
     assert np.array_equal(oo.normalize_uint8(u8), ref)
+
+
+@pytest.mark.parametrize("kind", ["rnn210", "demand", "rnn21"])
+def test_oracle_matches_reference_at_full_size(kind):
+    """The oracle pinned at the reference's default dims too (E=A=H=512, Li=100, Lt=52, B=8): fixtures of
+    oracle/make_golden_full.py, weights re-created from the seed (checksums verified)."""
+    import torch.nn.functional as F
+    from helpers import full_compare, full_inputs, full_model
+    from oracle import rnn
+    blob = load_golden("full_" + kind)
+    m = full_model(blob, "cpu")
+    P = {k: v.detach().clone().requires_grad_(v.is_floating_point()) for k, v in m.state_dict().items()}
+    data, feat = full_inputs(blob)
+    feat.requires_grad_(True)
+    T = blob["cfg"]["T"]
+    extras = {}
+    if kind == "rnn210":
+        out, _ = rnn.rnn210_forward(P, *data, feat, out_len=T, use_teacher_forcing=True, tf_mask=blob["tf_mask"])
+        loss = F.mse_loss(data[1].reshape(out.shape), out)
+    elif kind == "rnn21":
+        out, _ = rnn.rnn21_forward(P, *data, feat)
+        loss = F.mse_loss(data[1], out)
+    else:
+        out, ia, ma = rnn.demand_forward(P, *data, feat, out_len=T, use_teacher_forcing=True, tf_mask=blob["tf_mask"])
+        extras = dict(img_alphas=torch.stack(ia), mm_alphas=torch.stack(ma))
+        loss = F.mse_loss(data[0], out.squeeze())
+    loss.backward()
+    grads = {k: p.grad for k, p in P.items()}
+    full_compare(blob, out, loss, extras, grads, feat.grad, 1e-5)

@@ -14,15 +14,19 @@ def label_dicts():
     return ({i: i for i in range(CAT_N)}, {i: i for i in range(COL_N)}, {i: i for i in range(FAB_N)})
 
 
-def _sales(gen, *shape):
-    """Sparse small counts already divided by 53 (the code never normalises sales itself)."""
+def _sales(gen, *shape, dense=False):
+    """Sparse small counts already divided by 53 (the code never normalises sales itself).  ``dense``: counts of
+    8..53 with no zeros -- targets whose WAPE denominator (sum |gt|) is of the size of the numerator, for the
+    training-trajectory fixtures (WAPE of order 100 %, where a 0.1-point bound means something)."""
+    if dense:
+        return torch.randint(8, 54, shape, generator=gen).float() / 53.0
     k = torch.randint(1, 11, shape, generator=gen).float() / 53.0
     keep = (torch.rand(shape, generator=gen) >= 0.6).float()
     return k * keep
 
 
 def make_batch(batch, *, out_len=10, demand=False, seed=21, image_hw=299, images=True,
-               feat_hw=None, num_trends=3, trend_len=52):
+               feat_hw=None, num_trends=3, trend_len=52, dense_sales=False):
     """Returns ``(data_tuple, images_or_feature_map)`` on CPU.
 
     ``feat_hw`` set -> second element is a backbone feature map ``[B,2048,feat_hw,feat_hw]``
@@ -39,10 +43,10 @@ def make_batch(batch, *, out_len=10, demand=False, seed=21, image_hw=299, images
     hi = gt.max(dim=2, keepdim=True).values
     gt = (gt - lo) / (hi - lo)                     # per-series MinMax, dataset_fusion.py:148-160
     if demand:
-        head = (_sales(g, batch, 12),)
+        head = (_sales(g, batch, 12, dense=dense_sales),)
     else:
         windows = 12 - 2 - out_len + 1             # dataset_fusion.py:98
-        head = (_sales(g, batch, windows, 2), _sales(g, batch, windows, out_len))
+        head = (_sales(g, batch, windows, 2, dense=dense_sales), _sales(g, batch, windows, out_len, dense=dense_sales))
     if feat_hw is not None:
         img = torch.randn(batch, 2048, feat_hw, feat_hw, generator=g).abs() * 0.5   # post-ReLU-like
     elif images:
