@@ -1,5 +1,8 @@
 """GPU parity of the fused BatchNorm2d(+add)(+ReLU) sweeps (csrc/bn_act.cu) and of the fused trunk walk
 against torch's own BatchNorm2d / torchvision forward on the same bf16 channels_last inputs."""
+import copy
+import warnings
+
 import pytest
 import torch
 import torch.nn as nn
@@ -223,3 +226,92 @@ def test_frozen_weight_cache_does_not_outlive_its_parameter():
         assert torch.equal(trunk._bf16_weights(convs)[convs[0]], convs[0].weight.to(torch.bfloat16))
         del convs, got, again
         gc.collect()
+
+
+def test_full_model_training_with_fused_trunk_tracks_the_autocast_trunk():
+    """End-to-end criterion for the fused bf16 trunk: the full CrossAttnRNN210 (random-init ResNet-101 + head, bf16
+    mode) trained for 30 Adafactor steps twice from the same initial state -- once with the fused BatchNorm/add/ReLU
+    sweeps, once with the unmodified torchvision modules under bf16 autocast (same cuDNN convolutions).  The two loss
+    curves must agree like two bf16 executions of the same network do."""
+    import visuelle2_multimodal_fusion_b200.synth as synth
+    from visuelle2_multimodal_fusion_b200.models.CrossAttnRNN210 import CrossAttnRNN
+    from oracle.refshim import zero_dropout
+    cat_d, col_d, fab_d = synth.label_dicts()
+    steps, B = 30, 8
+    batches = []
+    for i in range(4):
+        data, im = synth.make_batch(B, out_len=10, seed=300 + i, dense_sales=True)
+        batches.append((tuple(t.cuda() for t in data), im.cuda()))
+    curves = {}
+    state0 = None
+    for fused in (True, False):
+        torch.manual_seed(77)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            m = CrossAttnRNN(512, 512, 512, cat_d, col_d, fab_d, synth.STORE_N, 3).cuda()
+        if state0 is None:
+            state0 = copy.deepcopy(m.state_dict())
+        else:
+            m.load_state_dict(state0)
+        zero_dropout(m).train()
+        m.on_train_epoch_start()
+        m.image_encoder.use_bf16_backbone(True)
+        m.image_encoder.fused_trunk = fused
+        m.precision = "bf16"
+        opt = m.configure_optimizers()[0]
+        losses = []
+        for s in range(steps):
+            torch.manual_seed(4000 + s)
+            loss = m.training_step(batches[s % 4], s)
+            opt.zero_grad()
+            loss.backward()
+            opt.step()
+            losses.append(float(loss))
+        curves[fused] = torch.tensor(losses)
+        del m, opt
+    a, b = curves[True], curves[False]
+    rel = ((a - b).abs() / b.abs().clamp_min(1e-6))
+    print(f"fused vs autocast trunk, 30 steps: loss {float(a[0]):.5f}->{float(a[-1]):.5f} vs {float(b[0]):.5f}->{float(b[-1]):.5f}; "
+          f"rel diff mean {float(rel.mean()):.4f} max {float(rel.max()):.4f}")
+    assert float(rel.mean()) < 0.02 and float(rel.max()) < 0.06, (rel.mean(), rel.max())
+
+
+def test_eval_forward_sees_optimizer_updates_of_trainable_trunk_weights():
+    """optim.Adafactor updates parameters from a CUDA kernel (no Tensor._version bump); a no_grad
+    forward after the step must use the NEW layer3/layer4 weights, not a cached bf16 copy of the old ones."""
+    import visuelle2_multimodal_fusion_b200.synth as synth
+    from visuelle2_multimodal_fusion_b200.models.CrossAttnRNN210 import CrossAttnRNN
+    cat_d, col_d, fab_d = synth.label_dicts()
+    torch.manual_seed(5)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        m = CrossAttnRNN(64, 64, 64, cat_d, col_d, fab_d, synth.STORE_N, 3).cuda()
+    m.image_encoder.use_bf16_backbone(True)
+    m.precision = "bf16"
+    data, im = synth.make_batch(4, out_len=10, seed=1)
+    batch = (tuple(t.cuda() for t in data), im.cuda())
+    trunk_params = [p for n, p in m.image_encoder.cnn.named_parameters() if p.requires_grad and p.dim() == 4]
+    opt = m.configure_optimizers()[0]
+
+    def feat():
+        m.eval()
+        with torch.no_grad():
+            f = m.image_encoder(batch[1]).float().clone()
+        return f
+
+    f0 = feat()                               # first no_grad pass (what Lightning's sanity check does)
+    m.train()
+    for s in range(3):
+        loss = m.training_step(batch, s)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+    w_before = trunk_params[-1].detach().clone()
+    f1 = feat()
+    # reference: the same eval forward with every cache dropped
+    from visuelle2_multimodal_fusion_b200 import trunk
+    trunk._frozen_cache.clear() if hasattr(trunk._frozen_cache, "clear") else None
+    f2 = feat()
+    assert torch.equal(trunk_params[-1].detach(), w_before)
+    assert float((f1 - f2).abs().max()) == 0.0, "eval forward depends on a stale weight cache"
+    assert float((f1 - f0).abs().max()) > 0.0, "eval output did not change after three optimizer steps"
