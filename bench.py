@@ -482,6 +482,7 @@ def _roofline_passes(r, args, nsteps):
     phases = None
     if Fv.PERSISTENT_DECODE and hasattr(Fv, "persist_phase_times"):
         _lib.lib().v2f_decode_persist_stamps_enable(1)
+        _lib.lib().v2f_decode_team_stamps_enable(1)
         Fv.KEEP_LAST_PERSIST_WS = True
         try:
             r.step_head(0, lag)
@@ -489,6 +490,7 @@ def _roofline_passes(r, args, nsteps):
         finally:
             Fv.KEEP_LAST_PERSIST_WS = False
             _lib.lib().v2f_decode_persist_stamps_enable(0)
+            _lib.lib().v2f_decode_team_stamps_enable(0)
     peak, peak_src = _peaks()
     N, T = r.B, 10
     tile_bytes = N * 4 * (2 * LI + 2 * LT) * E
@@ -516,6 +518,7 @@ def _roofline_passes(r, args, nsteps):
     if "decode_persist_fwd_kernel" in roof and phases:
         rr = roof["decode_persist_fwd_kernel"]
         rr["phases_us_per_step"] = {k: {"work": round(w, 2), "barrier_wait": round(b, 2)} for k, (w, b) in phases.items()}
+        rr["decoder"] = "row-team tcgen05 kernel (csrc/decode_team.cu)" if len(phases) == 5 else "column-split kernel (csrc/decode_persist.cu)"
         if "P2 attention sweep" in phases:
             w, b = phases["P2 attention sweep"]
             pa = (tile_bytes + small) / ((w + b) * 1e-6) / 1e9

@@ -145,11 +145,27 @@ typedef struct v2f_decode_params {
    * owns at least one hidden unit), image and trend attention are both on, variant != 1 and attn_ws is given; otherwise (or when NULL) the
    * step-per-launch path runs.  Both paths fill the same saved activations.                         */
   float *persist_ws;
+  /* optional scratch of v2f_decode_team_ws_floats(N,B,T,Li,Lt) floats (team_ws_floats = its size): enables the row-team
+   * persistent decoder (csrc/decode_team.cu): one cooperative launch for the T-step loop, rows dealt to teams of 64
+   * CTAs, products on tcgen05 with the bf16 weight slices resident in shared memory, bf16 attention tiles.  Taken in
+   * tensor-core mode (precision 1) when E = H = 512, N <= 128, image and trend attention on, variant != 1 and
+   * persist_ws is given too; otherwise the paths above run.  Fills the same saved activations.                    */
+  float *team_ws;
+  long long team_ws_floats;
 } v2f_decode_params;
 
 int v2f_decode_fwd(const v2f_decode_params* p, void* stream);
 int v2f_decode_bwd(const v2f_decode_params* p, void* stream);
 long long v2f_decode_persist_ws_floats(int N, int E, int H, int T);
+long long v2f_decode_team_ws_floats(int N, int B, int T, int Li, int Lt);
+/* A/B switch (default 1): 0 keeps the decoder off the row-team kernel. */
+int v2f_decode_team_enable(int on);
+/* Profiling: CTA 0 of the row-team decoder stamps %globaltimer (ns), [T][16] unsigned long long at byte offset
+ * v2f_decode_team_stamps_offset(...) of team_ws: stamp 2k = phase k starts, 2k+1 = CTA 0 finished its work of phase k,
+ * k = 0 P1 (S product), 1 P2 (attention sweep + combine), 2 P3 (HC), 3 P4 (multimodal attention), 4 P5 (gates);
+ * stamp 10 = step end.                                                                                       */
+int v2f_decode_team_stamps_enable(int on);
+long long v2f_decode_team_stamps_offset(int N, int B, int T, int Li, int Lt);
 /* A/B switch (default 1): 0 forces the step-per-launch path even when persist_ws is given. */
 int v2f_decode_persistent_enable(int on);
 /* Profiling: CTA 0 of the persistent decoder stamps %globaltimer (ns) around its phases,

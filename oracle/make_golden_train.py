@@ -163,7 +163,13 @@ if __name__ == "__main__":
         elif kind.startswith("512:"):
             blob, name = case512(kind[4:]), "train512_" + kind[4:]
         else:
-            blob, name = case(kind), "train_" + kind
+            # GTM family: 30 steps.  Biases in front of a train-mode BatchNorm have an exactly-zero gradient; autograd
+            # returns rounding noise there and Adafactor turns noise into O(lr) steps, so those parameters random-walk
+            # (differently on every platform: the reference run with 1 / 4 / 8 host threads ends at WAPE 118.402 /
+            # 118.404 / 118.390 after 60 steps) and the running statistics carry the walk into eval mode.  Under
+            # warmup_init the walk grows with the square of the step count; 30 steps keep it well inside the 0.1-point
+            # contract while still exercising optimizer, running statistics and validation.
+            blob, name = case(kind, steps=30 if kind in ("gtm", "v4") else 60), "train_" + kind
         path = os.path.join(GOLDEN_DIR, name + ".pt")
         torch.save(blob, path)
         if kind == "dropout":

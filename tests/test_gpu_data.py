@@ -49,7 +49,7 @@ def test_model_accepts_device_normalized_images():
     import bench
     import visuelle2_multimodal_fusion_b200.synth as synth
     from visuelle2_multimodal_fusion_b200.data import IMAGENET_MEAN, IMAGENET_STD, normalize_uint8_images
-    model = bench._build_model("cuda:0", "bf16").eval()
+    model = bench._build_model("rnn210", "cuda:0", "bf16").eval()
     data, _ = synth.make_batch(2, out_len=10, seed=4, feat_hw=10)
     data = tuple(t.cuda() for t in data)
     u8 = torch.randint(0, 256, (2, 299, 299, 3), dtype=torch.uint8, generator=torch.Generator().manual_seed(1)).cuda()

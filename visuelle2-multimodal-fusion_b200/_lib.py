@@ -33,7 +33,8 @@ class DecodeParams(ctypes.Structure):
              "dWcat", "dbcat", "dw_att", "db_tl", "dWe_mm", "dW_me", "db_me", "dW_ihc", "dw_x",
              "db_ih", "dw_fc", "db_fc", "WcatT", "W_ihcT", "W_meT", "We_mmT", "ws"]
     _fields_ = ([(n, c_int) for n in _INTS] + [("tf_mask", ctypes.c_uint), ("precision", c_int)] +
-                [(n, c_vp) for n in _PTRS] + [("ws_floats", c_ll), ("attn_ws", c_vp), ("tf_mask_dev", c_vp), ("persist_ws", c_vp)])
+                [(n, c_vp) for n in _PTRS] + [("ws_floats", c_ll), ("attn_ws", c_vp), ("tf_mask_dev", c_vp), ("persist_ws", c_vp),
+                 ("team_ws", c_vp), ("team_ws_floats", c_ll)])
 
 
 class AfDesc(ctypes.Structure):
@@ -89,6 +90,12 @@ def _declare(lib):
     lib.v2f_decode_persist_ws_floats.restype = c_ll
     lib.v2f_decode_persist_stamps_offset.argtypes = [c_int, c_int, c_int]
     lib.v2f_decode_persist_stamps_offset.restype = c_ll
+    lib.v2f_decode_team_ws_floats.argtypes = [c_int] * 5
+    lib.v2f_decode_team_ws_floats.restype = c_ll
+    lib.v2f_decode_team_stamps_offset.argtypes = [c_int] * 5
+    lib.v2f_decode_team_stamps_offset.restype = c_ll
+    lib.v2f_decode_team_enable.argtypes = [c_int]
+    lib.v2f_decode_team_stamps_enable.argtypes = [c_int]
     lib.v2f_prof_read.argtypes = [c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(c_ll)]
     lib.v2f_prof_read_bytes.argtypes = [c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(c_ll),
                                         ctypes.POINTER(c_ll)]

@@ -1,0 +1,814 @@
+// Row-team persistent decoder (forward): ONE cooperative launch for the whole T-step horizon of the
+// CrossAttnRNN210 / CrossAttnRNNDemand decode loop at the reference's default dims (E = A = H = 512), products on
+// tcgen05 tensor cores with the weights resident in shared memory, attention tiles streamed as bf16.  sm_100a.
+//
+// Reference arithmetic: /root/reference/models/CrossAttnRNN210.py:191-225 (loop), :83-89 (AdditiveAttention),
+// :135-140,210-211 (decoder nn.GRU cell), :141,212-225 (decoder_fc + teacher forcing);
+// /root/reference/models/CrossAttnRNNDemand.py:285-347,134-149.  Same equations and the same saved activations as
+// decode_persist.cu / rnn_decode.cu (the backward consumes them unchanged).
+//
+// Why a second persistent design.  decode_persist.cu splits the WEIGHT columns over all 148 CTAs, so every product
+// needs every row's activations in every CTA (38 MB of L2->SM traffic per phase), runs on legacy mma.sync, needs a
+// 148-way grid barrier per phase and a combine pass for attention partials: 64 us per step, of which 19 us stream
+// tiles.  Here rows are dealt to TEAMS of 64 CTAs, 64 rows per team:
+//   * a CTA owns 1/64 of the weight rows -- 8 query columns of each attention, 8 hidden units x 3 gates of W_hh,
+//     8 rows of We_mm, 8 units x 3 gates of W' = W_ihc W_me: 80 rows x 512 bf16 = 80 KB, loaded once by TMA
+//     (128-byte swizzle) and kept for all T steps -- and is the owner of ONE row for the row-local phases;
+//   * a product is D[weight row, batch row] = W_slice (A operand, M = 128 tile over the resident slice; rows
+//     beyond the slice are don't-care) x X^T (B operand: the team's 64 activation rows, bf16, TMA-loaded in 64-wide
+//     K chunks through an 8-slot mbarrier ring), tcgen05.mma kind::f16 issued by one thread, fp32 accumulator in
+//     TMEM, read back with tcgen05.ld: 64 KB of activations per CTA per product instead of 256 KB;
+//   * the attention sweep of a row runs entirely inside its owner CTA (two 8-warp groups with a 4-slot bulk-copy
+//     ring each, bf16 tiles, online softmax, partials combined in shared memory): no combine phase, no partial
+//     traffic through L2, 304 KB per row and step instead of 608 KB;
+//   * barriers are per team (64 arrivals) and there are five per step.
+// GI = CTX W_ihc^T is re-associated to U (W_ihc W_me)^T (exact); CTX itself (saved for the backward) is one GEMM
+// over all T*N rows after the loop.  The GRU state, softmax, gates and all saved activations stay fp32; bf16 is
+// the operand format of the products and the storage format of the streamed tiles (tensor-core mode, 2e-2 contract).
+#include "attn.cuh"
+#include "gemm_dispatch.cuh"
+#include "tc.cuh"
+
+namespace v2f {
+
+constexpr int DT_E = 512;                    // E = A = H = 512 only (train_dl.py:197-199)
+constexpr int DT_NG = 64;                    // rows per team = MMA N
+constexpr int DT_CG = 64;                    // CTAs per team
+constexpr int DT_CONS = 512;                 // 16 consumer warps = 2 groups of 8
+constexpr int DT_GRP = 256;
+constexpr int DT_THREADS = DT_CONS + 64;     // + warp 16 (TMA / bulk-copy producer of group 0), warp 17 (MMA issuer / producer of group 1)
+constexpr int DT_WROWS = 80;                 // resident weight rows per CTA: 24 W' | 8 We_mm | 48 Wcat
+constexpr int DT_R5 = 0, DT_R3 = 24, DT_R1 = 32;
+constexpr int DT_KCH = DT_E / 64;            // 8 K chunks of 64 bf16 (one 128-byte swizzle span)
+constexpr int DT_WCHUNK = DT_WROWS * 128;    // bytes of one K chunk of the weight slice
+constexpr int DT_WBYTES = DT_KCH * DT_WCHUNK;
+constexpr int DT_BSLOT = DT_NG * 128;        // 8 KB: 64 activation rows x 64 bf16
+constexpr int DT_NBS = 8;
+constexpr int DT_CH = 8;                     // positions per attention chunk
+constexpr int DT_TSLOT = DT_CH * DT_E * 2;   // 8 KB: one operand (H or V) of one chunk, bf16
+constexpr int DT_TSLOTS = 4;                 // ring slots per group
+constexpr int DT_RING = DT_NBS * DT_BSLOT;   // 64 KB, shared by the B ring (products) and the tile rings (sweep)
+constexpr int DT_P1 = 65, DT_P3 = 129;       // staging pitches (odd: conflict-free transposed writes)
+constexpr int DT_NCTR = 8;
+constexpr int DT_BARW = DT_NCTR * 32;        // unsigned words of barrier counters per team
+constexpr int DT_STAMPS = 16;
+constexpr uint32_t DT_TMEM_COLS = 256;       // D1: 0..63, D3: 64..191, D5: 192..255
+constexpr int DT_MAXTEAMS = 2;
+
+static_assert(DT_RING == 2 * DT_TSLOTS * DT_TSLOT, "the two rings alias");
+
+struct DtArgs {
+  v2f_decode_params p;
+  const float* bp;                                  // [3H] = W_ihc b_me + b_ih
+  const __nv_bfloat16 *Himg, *Vimg, *Htr, *Ptr;     // bf16 copies of the tiles
+  __nv_bfloat16 *hb, *Cb, *Ub;                      // [Np,512], [2,Np,512], [Np,512]: B operands of the products
+  float* ypart;                                     // [64, Np] per-CTA partial decoder_fc dot products
+  unsigned* bar;                                    // [teams, DT_BARW] (zeroed before launch)
+  unsigned long long* stamps;                       // optional [T, DT_STAMPS]
+  int Np;                                           // teams * 64
+};
+
+__device__ __forceinline__ unsigned long long dt_globaltimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+// Team barrier: 64 arrivals spread over DT_NCTR monotonic counters on separate 128-byte lines; lanes 0..7 of warp 0
+// poll one each (a sum of monotonic counters read one by one is a lower bound of the arrivals).  Bounded spin.
+__device__ __forceinline__ void dt_team_barrier(unsigned* ctr, int c, unsigned& epoch) {
+  asm volatile("fence.proxy.async.global;" ::: "memory");   // this thread's hb / Cb / Ub stores -> the next phase's TMA loads
+  __syncthreads();
+  ++epoch;
+  if (threadIdx.x < 32) {
+    if (threadIdx.x == 0)
+      asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr + (c % DT_NCTR) * 32) : "memory");
+    const unsigned target = epoch * DT_CG;
+    const unsigned* cp = ctr + (threadIdx.x % DT_NCTR) * 32;
+    const long long t0 = clock64();
+    for (;;) {
+      unsigned v = 0;
+      if (threadIdx.x < DT_NCTR) asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(cp) : "memory");
+#pragma unroll
+      for (int o = DT_NCTR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+      v = __shfl_sync(FULL, v, 0);
+      if (v >= target) break;
+      if (clock64() - t0 > (1LL << 31)) __trap();   // ~1 s: a protocol bug must not hang the device
+    }
+  }
+  __syncthreads();
+}
+
+// 16 accumulator columns of this warp's 32 TMEM lanes
+__device__ __forceinline__ void dt_tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Global data written through the generic proxy (st.global by this or another CTA) and then read by TMA (async proxy):
+// writers fence after their stores, the TMA-issuing thread fences after the team barrier's acquire.
+__device__ __forceinline__ void dt_fence_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
+
+__device__ __forceinline__ float2 dt_bf2(uint32_t w) {   // two packed bf16 -> two fp32
+  return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+}
+__device__ __forceinline__ uint32_t dt_pack(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// global column (of S / bcat) of weight row j (0..47) of the P1 slice of CTA c
+__device__ __forceinline__ int dt_col1(int j, int c) {
+  return j < 24 ? (j >> 3) * DT_E + 8 * c + (j & 7) : 3 * DT_E + ((j - 24) >> 3) * DT_E + 8 * c + ((j - 24) & 7);
+}
+
+__global__ void __launch_bounds__(DT_THREADS, 1)
+decode_team_fwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapH,
+                       const __grid_constant__ CUtensorMap mapC, const __grid_constant__ CUtensorMap mapU,
+                       const __grid_constant__ DtArgs a) {
+  constexpr int E = DT_E, H = DT_E, ldS = 6 * DT_E;
+  extern __shared__ uint8_t raw[];
+  const v2f_decode_params& p = a.p;
+  const int N = p.N, T = p.T, Li = p.Li, Lt = p.Lt, Wn = p.W, Np = a.Np;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int team = blockIdx.x / DT_CG, c = blockIdx.x % DT_CG;
+  const int n0 = team * DT_NG;
+  const int n_own = n0 + c;                       // the row this CTA owns in the row-local phases
+  const bool own = n_own < N;
+
+  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* Wsm = sm;                                            // [8 chunks][80 rows][128 B], swizzled by TMA
+  uint8_t* ring = sm + DT_WBYTES;                               // B ring / tile rings
+  float* stage1 = reinterpret_cast<float*>(ring + DT_RING);     // [48][65]: S columns and GH of the team's rows
+  float* stage5 = stage1 + 48 * DT_P1;                          // [24][65] GI  (P3: [8][129] HC)
+  float* cvec = stage5 + 24 * DT_P1 + 8;                        // [2][512] contexts of the own row
+  float* pacc = cvec + 2 * E;                                   // [4][512] attention partials
+  float* pml = pacc + 4 * E;                                    // [4][2] (m, l)
+  int* pmod = reinterpret_cast<int*>(pml + 8);                  // [4] modality of a partial, -1 = unused
+  float* e_sh = reinterpret_cast<float*>(pmod + 4);             // [2 groups][2][8]
+  float* red = e_sh + 32;                                       // [64]
+  uint64_t* bfull = reinterpret_cast<uint64_t*>(red + 64);      // [8] B ring
+  uint64_t* bempty = bfull + DT_NBS;                            // [8]
+  uint64_t* tfull = bempty + DT_NBS;                            // [2][4] tile rings
+  uint64_t* tempty = tfull + 2 * DT_TSLOTS;                     // [2][4]
+  uint64_t* mma_done = tempty + 2 * DT_TSLOTS;
+  uint64_t* wfull = mma_done + 1;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(wfull + 1);
+
+  // ------------------------------------------------------------------ one-time set-up
+  if (tid == 0) {
+    for (int s = 0; s < DT_NBS; s++) {
+      mbar_init(&bfull[s], 1);
+      mbar_init(&bempty[s], 1);
+    }
+    for (int s = 0; s < 2 * DT_TSLOTS; s++) {
+      mbar_init(&tfull[s], 1);
+      mbar_init(&tempty[s], DT_GRP / 32);
+    }
+    mbar_init(mma_done, 1);
+    mbar_init(wfull, 1);
+    mbar_fence_init();
+  }
+  if (warp == 17) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)),
+                 "r"(DT_TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = *tmem_ptr;
+  if (warp == 16 && lane == 0) {                    // the weight slice: 8 boxes of [80 rows x 128 B]
+    mbar_expect_tx(wfull, DT_WBYTES);
+    for (int kc = 0; kc < DT_KCH; kc++) tma_load_3d(Wsm + kc * DT_WCHUNK, &mapW, wfull, kc * 64, c * DT_WROWS, 0);
+  }
+
+  const __nv_bfloat16* Vimg_b = a.Vimg;
+  const bool byproj = p.variant == 2;
+  const int mod_mask = p.mod_mask;
+  const unsigned* mask_dev = p.y ? p.tf_mask_dev : nullptr;
+  unsigned* bar = a.bar + team * DT_BARW;
+  unsigned epoch = 0;
+  uint32_t bq = 0;                 // B-ring chunks issued (producer) / consumed (MMA thread) so far
+  uint32_t md = 0;                 // completed waits on mma_done
+  const int grp = warp < 8 ? 0 : (warp < 16 ? 1 : warp - 16);
+  const int gt = tid & (DT_GRP - 1), gw = (tid >> 5) & 7;
+  uint8_t* gring = ring + grp * DT_TSLOTS * DT_TSLOT;
+  uint64_t* gfull = tfull + grp * DT_TSLOTS;
+  uint64_t* gempty = tempty + grp * DT_TSLOTS;
+  float* ge = e_sh + grp * 16;
+  uint32_t tq = 0;                 // tile-ring slots used by this group so far
+  const int cpi = (Li + DT_CH - 1) / DT_CH, cpt = (Lt + DT_CH - 1) / DT_CH, ctot = cpi + cpt;
+  const int chalf = (ctot + 1) / 2;
+  const int c_lo = grp == 0 ? 0 : chalf, c_hi = grp == 0 ? chalf : ctot;
+  const uint32_t idesc = umma_idesc<0>(DT_NG);
+  auto stamp = [&](int t, int k) {
+    if (a.stamps && blockIdx.x == 0 && tid == 0) a.stamps[t * DT_STAMPS + k] = dt_globaltimer();
+  };
+
+  // gate threads: (row nl of the team, hidden unit u of this CTA); the state h lives in a register for all T steps
+  const int nl = tid >> 3, gu = tid & 7;
+  const int ng = n0 + nl;
+  const bool gact = tid < DT_CONS && ng < N;
+  float hreg = 0.f;
+  if (gact) {
+    hreg = p.h_all[(long long)ng * H + 8 * c + gu];
+    a.hb[(long long)ng * H + 8 * c + gu] = __float2bfloat16_rn(hreg);
+  }
+  // B ring helpers (warp 16 lane 0 produces, warp 17 lane 0 issues the MMAs)
+  auto load_b = [&](const CUtensorMap* map, int row0, int nch) {
+    dt_fence_async_global();
+    for (int i = 0; i < nch; i++, bq++) {
+      const uint32_t s = bq % DT_NBS, r = bq / DT_NBS;
+      mbar_wait(&bempty[s], (r & 1) ^ 1);
+      mbar_expect_tx(&bfull[s], DT_BSLOT);
+      tma_load_3d(ring + s * DT_BSLOT, map, &bfull[s], (i % DT_KCH) * 64, row0 + (i / DT_KCH) * Np, 0);
+    }
+  };
+  auto issue = [&](int r0, uint32_t dcol, int nch) {      // nch = 8 per 64-column accumulator block
+    for (int i = 0; i < nch; i++, bq++) {
+      const uint32_t s = bq % DT_NBS, r = bq / DT_NBS;
+      const int kc = i % DT_KCH;
+      mbar_wait(&bfull[s], r & 1);
+      tc_fence_after();
+      const uint64_t ad = umma_desc_sw128(smem_u32(Wsm + kc * DT_WCHUNK + r0 * 128));
+      const uint64_t bd = umma_desc_sw128(smem_u32(ring + s * DT_BSLOT));
+#pragma unroll
+      for (int k = 0; k < 4; k++)
+        umma<0>(tmem_d + dcol + (uint32_t)(i / DT_KCH) * DT_NG, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc,
+                (kc | k) ? 1u : 0u);
+      umma_commit(&bempty[s]);
+    }
+    umma_commit(mma_done);
+  };
+  if (warp == 17 && lane == 0) mbar_wait(wfull, 0);
+  dt_team_barrier(bar, c, epoch);                  // hb of step 0 is complete
+
+  for (int t = 0; t < T; t++) {
+    float* S = p.S_all + (long long)t * N * ldS;
+    float* C = p.C + (long long)t * N * 2 * E;
+    float* HC = p.HC + (long long)t * N * 2 * E;
+    float* U = p.U + (long long)t * N * E;
+    float* al_img = p.alpha_img + (long long)t * N * Li;
+    float* al_tr = p.alpha_tr + (long long)t * N * Lt;
+    stamp(t, 0);
+    // ================================================================ P1: S^T slice = Wcat_slice h^T (+ bcat)
+    if (warp == 16) {
+      if (lane == 0) load_b(&mapH, n0, DT_KCH);
+      __syncwarp();
+    } else if (warp == 17) {
+      if (lane == 0) issue(DT_R1, 0, DT_KCH);
+      __syncwarp();
+    } else {
+      if (warp < 2) {
+        mbar_wait(mma_done, md & 1);
+        tc_fence_after();
+        const int j = warp * 32 + lane;            // TMEM lane = weight row of the slice
+        const float bias = j < 48 ? p.bcat[dt_col1(j, c)] : 0.f;
+#pragma unroll
+        for (int c0 = 0; c0 < DT_NG; c0 += 16) {
+          uint32_t v[16];
+          dt_tmem_ld16(tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+          if (j < 48)
+#pragma unroll
+            for (int q = 0; q < 16; q++) stage1[j * DT_P1 + c0 + q] = __uint_as_float(v[q]) + bias;
+        }
+        tc_fence_before();
+      }
+      md++;
+      named_bar_sync(3, DT_CONS);
+      {   // 8 consecutive columns (32 B) per (row, segment): s_img | s_tr | s_mm | gh_r | gh_z | gh_n
+        const int seg = tid & 7;
+        if (seg < 6 && ng < N) {
+          float v[8];
+#pragma unroll
+          for (int q = 0; q < 8; q++) v[q] = stage1[(seg * 8 + q) * DT_P1 + nl];
+          float* dst = S + (long long)ng * ldS + dt_col1(seg * 8, c);
+          st4(dst, make_float4(v[0], v[1], v[2], v[3]));
+          st4(dst + 4, make_float4(v[4], v[5], v[6], v[7]));
+        }
+      }
+    }
+    stamp(t, 1);
+    dt_team_barrier(bar, c, epoch);
+    stamp(t, 2);
+    // ================================================================ P2: additive attention of the own row
+    if (own) {
+      const int n = n_own, b = n / Wn;
+      if (warp >= 16) {
+        if (lane == 0) {
+          uint32_t q = tq;
+          for (int cc0 = c_lo; cc0 < c_hi; cc0++, q += 2) {
+            const int mod = cc0 >= cpi, cc = mod ? cc0 - cpi : cc0;
+            const int L = mod ? Lt : Li, j0 = cc * DT_CH, nj = min(DT_CH, L - j0);
+            const long long off = ((long long)b * L + j0) * E;
+            const uint32_t bytes = (uint32_t)nj * E * 2u;
+            const uint32_t sH = q % DT_TSLOTS, rH = q / DT_TSLOTS;
+            mbar_wait(&gempty[sH], (rH & 1) ^ 1);
+            mbar_expect_tx(&gfull[sH], bytes);
+            bulk_g2s(gring + sH * DT_TSLOT, (mod ? a.Htr : a.Himg) + off, bytes, &gfull[sH]);
+            const uint32_t sV = (q + 1) % DT_TSLOTS, rV = (q + 1) / DT_TSLOTS;
+            mbar_wait(&gempty[sV], (rV & 1) ^ 1);
+            mbar_expect_tx(&gfull[sV], bytes);
+            bulk_g2s(gring + sV * DT_TSLOT, (mod ? a.Ptr : Vimg_b) + off, bytes, &gfull[sV]);
+          }
+        }
+        __syncwarp();
+      } else {
+        float4 sreg[4], wreg[4];        // columns 8*lane + 256*k + [0,8) for k = 0,1: two float4 each
+        float cacc0 = 0.f, cacc1 = 0.f;
+        float m_run = -INFINITY, l_run = 0.f, beta = 0.f;
+        int cur_mod = -1, nseg = 0;
+        auto flush = [&]() {
+          const int ps = grp * 2 + nseg;
+          if (gt == 0) {
+            pml[2 * ps] = m_run;
+            pml[2 * ps + 1] = l_run;
+            pmod[ps] = cur_mod;
+          }
+          *reinterpret_cast<float2*>(pacc + ps * E + 2 * gt) = make_float2(cacc0, cacc1);
+          nseg++;
+        };
+        if (gt < 2) pmod[grp * 2 + gt] = -1;
+        uint32_t q = tq;
+        int par = 0;
+        for (int cc0 = c_lo; cc0 < c_hi; cc0++, q += 2, par ^= 1) {
+          const int mod = cc0 >= cpi, cc = mod ? cc0 - cpi : cc0;
+          const int L = mod ? Lt : Li, j0 = cc * DT_CH, nj = min(DT_CH, L - j0);
+          if (mod != cur_mod) {
+            if (cur_mod >= 0) flush();
+            cur_mod = mod;
+            m_run = -INFINITY;
+            l_run = 0.f;
+            cacc0 = cacc1 = 0.f;
+            const float* sp = S + (long long)n * ldS + mod * E;
+            const float* wp = p.w_att + mod * E;
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+              sreg[2 * k] = __ldcg(reinterpret_cast<const float4*>(sp + 8 * lane + 256 * k));
+              sreg[2 * k + 1] = __ldcg(reinterpret_cast<const float4*>(sp + 8 * lane + 256 * k + 4));
+              wreg[2 * k] = ld4(wp + 8 * lane + 256 * k);
+              wreg[2 * k + 1] = ld4(wp + 8 * lane + 256 * k + 4);
+            }
+            beta = p.beta_att[mod];
+          }
+          const uint32_t sH = q % DT_TSLOTS, rH = q / DT_TSLOTS;
+          const uint32_t sV = (q + 1) % DT_TSLOTS, rV = (q + 1) / DT_TSLOTS;
+          const uint8_t* Hs = gring + sH * DT_TSLOT;
+          const uint8_t* Vs = gring + sV * DT_TSLOT;
+          mbar_wait(&gfull[sH], rH & 1);
+          float* eb = ge + par * DT_CH;
+          if (gw < nj) {
+            const uint8_t* hp = Hs + gw * (E * 2);
+            float acc = 0.f;
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+              const uint4 hv = *reinterpret_cast<const uint4*>(hp + (8 * lane + 256 * k) * 2);
+              const float2 h0 = dt_bf2(hv.x), h1 = dt_bf2(hv.y), h2 = dt_bf2(hv.z), h3 = dt_bf2(hv.w);
+              const float4 s0 = sreg[2 * k], s1 = sreg[2 * k + 1], w0 = wreg[2 * k], w1 = wreg[2 * k + 1];
+              acc = fmaf(w0.x, tanh_fast<true>(h0.x + s0.x), acc);
+              acc = fmaf(w0.y, tanh_fast<true>(h0.y + s0.y), acc);
+              acc = fmaf(w0.z, tanh_fast<true>(h1.x + s0.z), acc);
+              acc = fmaf(w0.w, tanh_fast<true>(h1.y + s0.w), acc);
+              acc = fmaf(w1.x, tanh_fast<true>(h2.x + s1.x), acc);
+              acc = fmaf(w1.y, tanh_fast<true>(h2.y + s1.y), acc);
+              acc = fmaf(w1.z, tanh_fast<true>(h3.x + s1.z), acc);
+              acc = fmaf(w1.w, tanh_fast<true>(h3.y + s1.w), acc);
+            }
+            acc = warp_sum(acc) + beta;
+            if (lane == 0) {
+              eb[gw] = acc;
+              (mod ? al_tr : al_img)[(long long)n * L + j0 + gw] = acc;   // raw energy; normalised after the combine
+            }
+          } else if (lane == 0) {
+            eb[gw] = -INFINITY;
+          }
+          named_bar_sync(1 + grp, DT_GRP);
+          if (lane == 0) mbar_arrive(&gempty[sH]);        // every warp of the group is past its H reads
+          const float ej = lane < DT_CH ? eb[lane] : -INFINITY;
+          const float m_new = fmaxf(m_run, warp_max(ej));
+          const float scale = expf(m_run - m_new);
+          const float pj = expf(ej - m_new);
+          l_run = l_run * scale + warp_sum(pj);
+          m_run = m_new;
+          cacc0 *= scale;
+          cacc1 *= scale;
+          mbar_wait(&gfull[sV], rV & 1);
+          const uint8_t* vp = Vs + gt * 4;
+          if (nj == DT_CH) {
+#pragma unroll
+            for (int j = 0; j < DT_CH; j++) {
+              const float pr = __shfl_sync(FULL, pj, j);
+              const float2 v = dt_bf2(*reinterpret_cast<const uint32_t*>(vp + j * (E * 2)));
+              cacc0 = fmaf(pr, v.x, cacc0);
+              cacc1 = fmaf(pr, v.y, cacc1);
+            }
+          } else {
+            for (int j = 0; j < nj; j++) {
+              const float pr = __shfl_sync(FULL, pj, j);
+              const float2 v = dt_bf2(*reinterpret_cast<const uint32_t*>(vp + j * (E * 2)));
+              cacc0 = fmaf(pr, v.x, cacc0);
+              cacc1 = fmaf(pr, v.y, cacc1);
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&gempty[sV]);
+        }
+        if (cur_mod >= 0) flush();
+        named_bar_sync(3, DT_CONS);
+        // combine the (<= 2) partials of each modality; thread = column
+        {
+          const int x = tid;
+          float mm_[2], inv_[2];
+#pragma unroll
+          for (int mod = 0; mod < 2; mod++) {
+            float M = -INFINITY;
+#pragma unroll
+            for (int ps = 0; ps < 4; ps++)
+              if (pmod[ps] == mod && pml[2 * ps + 1] > 0.f) M = fmaxf(M, pml[2 * ps]);
+            float den = 0.f, cv = 0.f;
+#pragma unroll
+            for (int ps = 0; ps < 4; ps++)
+              if (pmod[ps] == mod && pml[2 * ps + 1] > 0.f) {
+                const float wgt = expf(pml[2 * ps] - M);
+                den = fmaf(pml[2 * ps + 1], wgt, den);
+                cv = fmaf(wgt, pacc[ps * E + x], cv);
+              }
+            const float inv = 1.0f / den;
+            cv *= inv;
+            if (mod) cv += p.b_tl[x];
+            cvec[mod * E + x] = cv;
+            C[((long long)n * 2 + mod) * E + x] = cv;
+            a.Cb[((long long)mod * Np + n) * E + x] = __float2bfloat16_rn(cv);
+            mm_[mod] = M;
+            inv_[mod] = inv;
+          }
+          // softmax weights for the backward pass / attention maps (raw energies were written by this CTA)
+          for (int j = tid; j < Li; j += DT_CONS) al_img[(long long)n * Li + j] = expf(al_img[(long long)n * Li + j] - mm_[0]) * inv_[0];
+          for (int j = tid; j < Lt; j += DT_CONS) al_tr[(long long)n * Lt + j] = expf(al_tr[(long long)n * Lt + j] - mm_[1]) * inv_[1];
+        }
+      }
+      tq += 2u * (uint32_t)(c_hi - c_lo);
+    }
+    stamp(t, 3);
+    dt_team_barrier(bar, c, epoch);
+    stamp(t, 4);
+    // ================================================================ P3: HC^T slice = We_mm_slice [c_img ; c_tr]^T
+    if (warp == 16) {
+      if (lane == 0) load_b(&mapC, n0, 2 * DT_KCH);          // chunks 0..7: image contexts, 8..15: trend contexts
+      __syncwarp();
+    } else if (warp == 17) {
+      if (lane == 0) issue(DT_R3, DT_NG, 2 * DT_KCH);
+      __syncwarp();
+    } else {
+      if (warp == 0) {
+        mbar_wait(mma_done, md & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int c0 = 0; c0 < 2 * DT_NG; c0 += 16) {
+          uint32_t v[16];
+          dt_tmem_ld16(tmem_d + (uint32_t)(DT_NG + c0), v);
+          if (lane < 8)
+#pragma unroll
+            for (int q = 0; q < 16; q++) stage5[lane * DT_P3 + c0 + q] = __uint_as_float(v[q]);
+        }
+        tc_fence_before();
+      }
+      md++;
+      named_bar_sync(3, DT_CONS);
+      {   // (row, modality) pair = tid / 4; 2 of the 8 columns per thread
+        const int pair = tid >> 2, qd = tid & 3, mod = pair >> 6, r = pair & 63;
+        if (n0 + r < N) {
+          const float2 v = make_float2(stage5[(2 * qd) * DT_P3 + pair], stage5[(2 * qd + 1) * DT_P3 + pair]);
+          *reinterpret_cast<float2*>(HC + ((long long)(n0 + r) * 2 + mod) * E + 8 * c + 2 * qd) = v;
+        }
+      }
+    }
+    stamp(t, 5);
+    dt_team_barrier(bar, c, epoch);
+    stamp(t, 6);
+    // ================================================================ P4: multimodal attention of the own row -> U ; closes step t-1
+    if (own) {
+      const int n = n_own, b = n / Wn;
+      float e[4] = {0.f, 0.f, 0.f, 0.f};
+      float mv[2][4], hv[2][4];
+      if (tid < DT_GRP) {
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+          const int x = tid + 256 * i;
+          const float sx = __ldcg(S + (long long)n * ldS + 2 * E + x), wx = p.w_att[2 * E + x];
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            const bool on = (mod_mask >> k) & 1;
+            float m_ = 0.f, h_ = 0.f;
+            if (on) {
+              if (k & 1) {
+                m_ = cvec[(k >> 1) * E + x];
+                h_ = __ldcg(HC + ((long long)n * 2 + (k >> 1)) * E + x);
+              } else {
+                m_ = p.Mst[((long long)b * 2 + (k >> 1)) * E + x];
+                h_ = p.HMst[((long long)b * 2 + (k >> 1)) * E + x];
+              }
+              e[k] = fmaf(wx, tanh_acc(h_ + sx), e[k]);
+            }
+            mv[i][k] = m_;
+            hv[i][k] = h_;
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) e[k] = warp_sum(e[k]);
+        if (lane == 0)
+#pragma unroll
+          for (int k = 0; k < 4; k++) red[warp * 4 + k] = e[k];
+      } else if (warp == 8 && t > 0) {
+        float yp = __ldcg(a.ypart + (long long)lane * Np + n) + __ldcg(a.ypart + (long long)(lane + 32) * Np + n);
+        yp = warp_sum(yp);
+        if (lane == 0) {
+          const float yh = yp + p.b_fc[0];
+          p.yhat[(long long)n * T + t - 1] = yh;
+          const int forced = mask_dev ? (int)((*mask_dev >> (t - 1)) & 1u) : (int)((p.tf_mask >> (t - 1)) & 1u);
+          p.xin[(long long)t * N + n] = (forced && p.y) ? p.y[(long long)n * T + t - 1] : yh;
+        }
+      }
+      __syncthreads();
+      if (tid < DT_GRP) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          float v = 0.f;
+#pragma unroll
+          for (int w = 0; w < 8; w++) v += red[w * 4 + k];
+          e[k] = v;
+        }
+        const float beta = p.beta_att[2];
+        float m = -INFINITY;
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+          if ((mod_mask >> k) & 1) {
+            e[k] += beta;
+            m = fmaxf(m, e[k]);
+          }
+        float sum = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          e[k] = ((mod_mask >> k) & 1) ? expf(e[k] - m) : 0.f;
+          sum += e[k];
+        }
+        const float inv = 1.0f / sum;
+#pragma unroll
+        for (int k = 0; k < 4; k++) e[k] *= inv;
+        if (tid == 0)
+#pragma unroll
+          for (int k = 0; k < 4; k++) p.alpha_mm[((long long)t * N + n) * 4 + k] = e[k];
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+          const int x = tid + 256 * i;
+          float u = 0.f;
+#pragma unroll
+          for (int k = 0; k < 4; k++)
+            if ((mod_mask >> k) & 1) u += mv[i][k] + e[k] * (byproj ? hv[i][k] : mv[i][k]);
+          U[(long long)n * E + x] = u;
+          a.Ub[(long long)n * E + x] = __float2bfloat16_rn(u);
+        }
+      }
+    }
+    stamp(t, 7);
+    dt_team_barrier(bar, c, epoch);
+    stamp(t, 8);
+    // ================================================================ P5: GI^T slice = W'_slice U^T ; GRU gates of the own hidden units
+    if (warp == 16) {
+      if (lane == 0) load_b(&mapU, n0, DT_KCH);
+      __syncwarp();
+    } else if (warp == 17) {
+      if (lane == 0) issue(DT_R5, 3 * DT_NG, DT_KCH);
+      __syncwarp();
+    } else {
+      if (warp == 0) {
+        mbar_wait(mma_done, md & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int c0 = 0; c0 < DT_NG; c0 += 16) {
+          uint32_t v[16];
+          dt_tmem_ld16(tmem_d + (uint32_t)(3 * DT_NG + c0), v);
+          if (lane < 24)
+#pragma unroll
+            for (int q = 0; q < 16; q++) stage5[lane * DT_P1 + c0 + q] = __uint_as_float(v[q]);
+        }
+        tc_fence_before();
+      }
+      md++;
+      named_bar_sync(3, DT_CONS);
+      float yp = 0.f;
+      if (gact) {
+        const int uu = 8 * c + gu;
+        const float x = __ldcg(p.xin + (long long)t * N + ng);
+        float gi[3], gh[3];
+#pragma unroll
+        for (int g3 = 0; g3 < 3; g3++) {
+          gi[g3] = stage5[(g3 * 8 + gu) * DT_P1 + nl] + a.bp[g3 * H + uu] + x * p.w_x[g3 * H + uu];
+          gh[g3] = stage1[(24 + g3 * 8 + gu) * DT_P1 + nl];
+        }
+        const float rg = sigmoid_full(gi[0] + gh[0]);
+        const float zg = sigmoid_full(gi[1] + gh[1]);
+        const float cg = tanh_full(gi[2] + rg * gh[2]);
+        const float hn = (1.f - zg) * cg + zg * hreg;
+        float* rzn = p.RZN + ((long long)t * N + ng) * 3 * H;
+        rzn[uu] = rg;
+        rzn[H + uu] = zg;
+        rzn[2 * H + uu] = cg;
+        p.h_all[((long long)(t + 1) * N + ng) * H + uu] = hn;
+        a.hb[(long long)ng * H + uu] = __float2bfloat16_rn(hn);
+        hreg = hn;
+        yp = p.w_fc[uu] * hn;
+      }
+      yp += __shfl_xor_sync(FULL, yp, 1);
+      yp += __shfl_xor_sync(FULL, yp, 2);
+      yp += __shfl_xor_sync(FULL, yp, 4);
+      if (gu == 0 && gact) a.ypart[(long long)c * Np + ng] = yp;
+    }
+    stamp(t, 9);
+    dt_team_barrier(bar, c, epoch);
+    stamp(t, 10);
+  }
+  // ------------------------------------------------------------------ close the last step: yhat_{T-1}
+  if (own && warp == 0) {
+    const int n = n_own;
+    float yp = __ldcg(a.ypart + (long long)lane * Np + n) + __ldcg(a.ypart + (long long)(lane + 32) * Np + n);
+    yp = warp_sum(yp);
+    if (lane == 0) {
+      const float yh = yp + p.b_fc[0];
+      p.yhat[(long long)n * T + T - 1] = yh;
+      const int forced = mask_dev ? (int)((*mask_dev >> (T - 1)) & 1u) : (int)((p.tf_mask >> (T - 1)) & 1u);
+      p.xin[(long long)T * N + n] = (forced && p.y) ? p.y[(long long)n * T + T - 1] : yh;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 17) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(DT_TMEM_COLS) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------ preparation kernels
+// the per-CTA weight slices, bf16, row-major [64 CTAs][80 rows][512]: rows 0..23 W' (gate g, unit 8c+u), 24..31
+// We_mm rows 8c.., 32..55 Wd_img | Wd_tr | Wd_mm rows 8c.., 56..79 W_hh (gate g, unit 8c+u)
+__global__ void dt_pack_weights_kernel(const float* __restrict__ Wp, const float* __restrict__ We_mm,
+                                       const float* __restrict__ Wcat, __nv_bfloat16* __restrict__ out) {
+  constexpr int E = DT_E;
+  const int row = blockIdx.x, c = row / DT_WROWS, r = row % DT_WROWS;
+  const float* src;
+  if (r < 24) src = Wp + (long long)((r >> 3) * E + 8 * c + (r & 7)) * E;
+  else if (r < 32) src = We_mm + (long long)(8 * c + r - 24) * E;
+  else src = Wcat + (long long)dt_col1(r - 32, c) * E;
+  for (int k = threadIdx.x * 4; k < E; k += blockDim.x * 4) {
+    const float4 v = ld4(src + k);
+    uint2 o;
+    o.x = dt_pack(v.x, v.y);
+    o.y = dt_pack(v.z, v.w);
+    *reinterpret_cast<uint2*>(out + (long long)row * E + k) = o;
+  }
+}
+
+static bool g_dt_enabled = true;
+static int g_dt_stamps = 0;
+
+static size_t dt_smem() {
+  return 1024 + (size_t)DT_WBYTES + DT_RING + sizeof(float) * (48 * DT_P1 + 24 * DT_P1 + 8 + 2 * DT_E + 4 * DT_E + 8 + 4 + 32 + 64) +
+         8 * (2 * DT_NBS + 4 * DT_TSLOTS + 2) + 16;
+}
+
+struct DtLayout {
+  long long bp, wpk, tiles, hb, cb, ub, ypart, bar, stamps, end;   // float offsets into team_ws
+};
+static DtLayout dt_layout(int N, int B, int T, int Li, int Lt) {
+  const long long Np = (long long)((N + DT_NG - 1) / DT_NG) * DT_NG;
+  DtLayout l;
+  long long o = 0;
+  auto take = [&](long long floats) { const long long at = o; o += (floats + 255) / 256 * 256; return at; };   // 1 KB aligned
+  l.bp = take(3 * DT_E);
+  l.wpk = take((long long)DT_CG * DT_WROWS * DT_E / 2);
+  l.tiles = take((long long)B * (2 * Li + 2 * Lt) * DT_E / 2);
+  l.hb = take(Np * DT_E / 2);
+  l.cb = take(2 * Np * DT_E / 2);
+  l.ub = take(Np * DT_E / 2);
+  l.ypart = take((long long)DT_CG * Np);
+  l.bar = take((long long)DT_MAXTEAMS * DT_BARW);
+  l.stamps = take(2LL * T * DT_STAMPS);
+  l.end = o;
+  return l;
+}
+
+long long decode_team_ws_floats(int N, int B, int T, int Li, int Lt) { return dt_layout(N, B, T, Li, Lt).end; }
+
+static bool dt_supported(const v2f_decode_params* p) {
+  if (!g_dt_enabled || !p->team_ws || !p->persist_ws) return false;
+  if (p->variant == 1 || p->T < 1 || p->precision == 0) return false;
+  if ((p->mod_mask & 0b1010) != 0b1010) return false;
+  if (p->E != DT_E || p->H != DT_E) return false;
+  if (p->N < 1 || p->N > DT_MAXTEAMS * DT_NG) return false;
+  if (p->Li < 1 || p->Lt < 1 || p->Li > 4096 || p->Lt > 4096) return false;
+  if (p->team_ws_floats < decode_team_ws_floats(p->N, p->B, p->T, p->Li, p->Lt)) return false;
+  int dev = 0, coop = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return false;
+  cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return coop && sms >= DT_MAXTEAMS * DT_CG;
+}
+
+// Returns V2F_ERR_UNSUPPORTED (and launches nothing) outside the envelope: the caller falls back to
+// decode_persist.cu / the step-per-launch path.
+int decode_team_fwd(const v2f_decode_params* p, cudaStream_t s) {
+  if (!dt_supported(p)) return V2F_ERR_UNSUPPORTED;
+  constexpr int E = DT_E, H = DT_E;
+  const int N = p->N, B = p->B, T = p->T, Li = p->Li, Lt = p->Lt;
+  const int teams = (N + DT_NG - 1) / DT_NG, Np = teams * DT_NG;
+  const DtLayout l = dt_layout(N, B, T, Li, Lt);
+  float* ws = p->team_ws;
+  // W' = W_ihc W_me [3H,E] (fp32, in persist_ws like decode_persist.cu), b' = W_ihc b_me + b_ih
+  float* Wp = p->persist_ws;
+  float* WmeT = Wp + (long long)3 * H * E + 3 * H;
+  float* bp = ws + l.bp;
+  V2F_TRY(v2f_transpose(E, E, p->W_me, E, 1, WmeT, E, 1, (void*)s));
+  V2F_TRY(v2f_gemm_tc(1, 3 * H, E, E, p->W_ihc, E, WmeT, E, Wp, E, nullptr, 0.f, 4, 1, (void*)s));
+  V2F_TRY(v2f_gemm_f32(0, 1, 1, 3 * H, E, p->b_me, E, 0, p->W_ihc, E, 0, bp, 3 * H, 0, 1, p->b_ih, 0.f, 0, (void*)s));
+  __nv_bfloat16* wpk = reinterpret_cast<__nv_bfloat16*>(ws + l.wpk);
+  dt_pack_weights_kernel<<<DT_CG * DT_WROWS, 128, 0, s>>>(Wp, p->We_mm, p->Wcat, wpk);
+  V2F_CHECK_LAUNCH();
+  // bf16 copies of the streamed tiles
+  __nv_bfloat16* tb = reinterpret_cast<__nv_bfloat16*>(ws + l.tiles);
+  const long long ni = (long long)B * Li * E, nt = (long long)B * Lt * E;
+  __nv_bfloat16 *Himg_b = tb, *Vimg_b = tb + ni, *Htr_b = tb + 2 * ni, *Ptr_b = tb + 2 * ni + nt;
+  V2F_TRY(v2f_cast_bf16(ni, p->Himg, Himg_b, (void*)s));
+  if (p->Vimg != p->Himg) V2F_TRY(v2f_cast_bf16(ni, p->Vimg, Vimg_b, (void*)s));
+  else Vimg_b = Himg_b;
+  V2F_TRY(v2f_cast_bf16(nt, p->Htr, Htr_b, (void*)s));
+  V2F_TRY(v2f_cast_bf16(nt, p->Ptr, Ptr_b, (void*)s));
+  DtArgs a;
+  a.p = *p;
+  a.bp = bp;
+  a.Himg = Himg_b;
+  a.Vimg = Vimg_b;
+  a.Htr = Htr_b;
+  a.Ptr = Ptr_b;
+  a.hb = reinterpret_cast<__nv_bfloat16*>(ws + l.hb);
+  a.Cb = reinterpret_cast<__nv_bfloat16*>(ws + l.cb);
+  a.Ub = reinterpret_cast<__nv_bfloat16*>(ws + l.ub);
+  a.ypart = ws + l.ypart;
+  a.bar = reinterpret_cast<unsigned*>(ws + l.bar);
+  a.stamps = g_dt_stamps ? reinterpret_cast<unsigned long long*>(ws + l.stamps) : nullptr;
+  a.Np = Np;
+  // pad rows of the B operands are zero; valid rows are rewritten every step
+  cudaMemsetAsync(ws + l.hb, 0, sizeof(float) * (size_t)(l.ypart - l.hb), s);
+  cudaMemsetAsync(a.bar, 0, sizeof(unsigned) * DT_MAXTEAMS * DT_BARW, s);
+  CUtensorMap mW, mH, mC, mU;
+  V2F_TRY(tc_make_map(&mW, 0, wpk, (long long)DT_CG * DT_WROWS, E, E, 1, 0, DT_WROWS));
+  V2F_TRY(tc_make_map(&mH, 0, a.hb, Np, E, E, 1, 0, DT_NG));
+  V2F_TRY(tc_make_map(&mC, 0, a.Cb, 2LL * Np, E, E, 1, 0, DT_NG));
+  V2F_TRY(tc_make_map(&mU, 0, a.Ub, Np, E, E, 1, 0, DT_NG));
+  static bool attr = false;
+  const size_t smem = dt_smem();
+  if (!attr) {
+    if (cudaFuncSetAttribute(decode_team_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+      return V2F_ERR_LAUNCH;
+    attr = true;
+  }
+  void* params[] = {(void*)&mW, (void*)&mH, (void*)&mC, (void*)&mU, (void*)&a};
+  prof_begin(V2F_K_DECODE_PERSIST_FWD, s);
+  const cudaError_t e = cudaLaunchCooperativeKernel((void*)decode_team_fwd_kernel, dim3(teams * DT_CG), dim3(DT_THREADS),
+                                                    params, smem, s);
+  prof_end(V2F_K_DECODE_PERSIST_FWD, s);
+  if (e == cudaErrorCooperativeLaunchTooLarge || e == cudaErrorLaunchOutOfResources) {
+    cudaGetLastError();
+    return V2F_ERR_UNSUPPORTED;
+  }
+  if (e != cudaSuccess) return V2F_ERR_LAUNCH;
+  ++g_v2f_launches;
+  // CTX = U W_me^T + b_me for all T*N rows (saved for the backward: dW_ihc = DGI^T CTX)
+  V2F_TRY(v2f_gemm_tc(1, T * N, E, E, p->U, E, p->W_me, E, p->CTX, E, p->b_me, 0.f, 4, 1, (void*)s));
+  return V2F_OK;
+}
+
+}  // namespace v2f
+
+extern "C" long long v2f_decode_team_ws_floats(int N, int B, int T, int Li, int Lt) {
+  if (N <= 0 || B <= 0 || T <= 0 || Li <= 0 || Lt <= 0) return 0;
+  return v2f::decode_team_ws_floats(N, B, T, Li, Lt);
+}
+// A/B switch (default 1): 0 routes the decoder through decode_persist.cu / the step-per-launch path again.
+extern "C" int v2f_decode_team_enable(int on) {
+  v2f::g_dt_enabled = on != 0;
+  return V2F_OK;
+}
+extern "C" int v2f_decode_team_stamps_enable(int on) {
+  v2f::g_dt_stamps = on != 0;
+  return V2F_OK;
+}
+// Byte offset of the stamp table [T, 16] (unsigned long long, ns) inside team_ws.
+extern "C" long long v2f_decode_team_stamps_offset(int N, int B, int T, int Li, int Lt) {
+  return (long long)sizeof(float) * v2f::dt_layout(N, B, T, Li, Lt).stamps;
+}

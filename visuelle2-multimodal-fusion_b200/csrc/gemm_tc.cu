@@ -12,72 +12,12 @@
 // lane issues tcgen05.mma for the CTA), warps 2..5 = epilogue (tcgen05.ld -> registers -> global;
 // warp w owns TMEM lanes 32*(w%4)..+31).  One 128 x BN output tile per CTA.
 // Every mbarrier wait is bounded: a protocol bug traps instead of hanging the GPU.
-#include <cuda.h>
-#include <cuda_bf16.h>
-
-#include "async.cuh"
+#include "tc.cuh"
 
 namespace v2f {
 
-constexpr int TC_BM = 128;           // UMMA_M
 constexpr int TC_STAGE_BYTES_K = 128;  // one 128-byte swizzle span of K per stage row
 constexpr int TC_THREADS = 192;
-
-__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
-                                            int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-// K-major operand tile, 128-byte swizzle: rows of 128 B, 8-row groups 1024 B apart (SBO), LBO unused.
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);          // start address  [0,14)
-  d |= (uint64_t)0 << 16;                           // leading byte offset (ignored for SW128 K-major)
-  d |= (uint64_t)(1024 >> 4) << 32;                 // stride byte offset [32,46)
-  d |= (uint64_t)1 << 46;                           // descriptor version (sm_100)
-  d |= (uint64_t)2 << 61;                           // layout type: SWIZZLE_128B
-  return d;
-}
-
-// instruction descriptor, kind::f16 (bf16 x bf16 -> f32) or kind::tf32, both operands K-major
-template <int KIND>
-__device__ __forceinline__ uint32_t umma_idesc(int n) {
-  uint32_t d = 0;
-  d |= 1u << 4;                                     // D format: F32
-  const uint32_t fmt = KIND == 0 ? 1u : 2u;         // kind::f16: 1 = BF16; kind::tf32: 2 = TF32
-  d |= fmt << 7;                                    // A format
-  d |= fmt << 10;                                   // B format
-  // bit 15 / 16: A / B major = 0 (K-major)
-  d |= (uint32_t)(n >> 3) << 17;                    // N >> 3
-  d |= (uint32_t)(TC_BM >> 4) << 24;                // M >> 4
-  return d;
-}
-
-template <int KIND>
-__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-  if (KIND == 0) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
-        : "memory");
-  } else {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
-        : "memory");
-  }
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
-}
 
 #ifdef V2F_GEMM_TIMELINE
 __device__ long long g_tl[16];
@@ -326,7 +266,7 @@ static EncodeTiledFn encode_fn() {
 
 // batch x row-major [rows, cols] (cols contiguous, row stride ld, batch stride bs, in elements),
 // box = [1, box_rows, 128 bytes]
-static int make_map(CUtensorMap* map, int kind, const void* ptr, long long rows, long long cols, long long ld,
+int tc_make_map(CUtensorMap* map, int kind, const void* ptr, long long rows, long long cols, long long ld,
                     long long batch, long long bs, int box_rows) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return V2F_ERR_UNSUPPORTED;
@@ -393,8 +333,8 @@ extern "C" int v2f_gemm_tc_batched(int kind, int M, int N, int K, const void* A,
   const int total_kb = (K + bk - 1) / bk;
   TcArgs a{M, N, K, C, ldc, bias, beta, act, (total_kb + splits - 1) / splits, splits > 1 ? 1 : 0, splits, sC};
   CUtensorMap mA, mB;
-  V2F_TRY(make_map(&mA, kind, A, M, K, lda, batch, sA, TC_BM));
-  V2F_TRY(make_map(&mB, kind, B, N, K, ldb, batch, sB, bn));
+  V2F_TRY(tc_make_map(&mA, kind, A, M, K, lda, batch, sA, TC_BM));
+  V2F_TRY(tc_make_map(&mB, kind, B, N, K, ldb, batch, sB, bn));
   cudaStream_t s = (cudaStream_t)stream;
   const int gz = batch * splits;
 #define DISPATCH(KIND_)                                      \

@@ -503,54 +503,72 @@ struct TileGradArgs {
   float *dH, *dV;       // [B,L,E]; dV may be NULL when byproj
 };
 
+// Thread = up to CPTG columns (x, x + 256, ...): the 13 tile values of each stay in registers for all T*W (step, row)
+// pairs of the item, so H is read once and dH / dV are written once.  The kernel is MUFU-bound, not HBM-bound
+// (B*L*E*T tanh evaluations): in tensor-core mode the single-instruction tanh.approx (the forward's choice there)
+// halves the MUFU work; the exact mode keeps the two-instruction form.
+template <bool APPROX, int CPTG>
 __global__ void __launch_bounds__(256)
 tilegrad_kernel(TileGradArgs a) {
-  __shared__ float al_sh[TG_J], de_sh[TG_J];
+  __shared__ float al_sh[2][TG_J], de_sh[2][TG_J];
   const int b = blockIdx.x, j0 = blockIdx.y * TG_J, E = a.E, L = a.L;
   const int nj = min(TG_J, L - j0);
-  for (int x0 = 0; x0 < E; x0 += blockDim.x) {
-    const int x = x0 + threadIdx.x;
-    const bool act = x < E;
-    float h[TG_J], accH[TG_J], accV[TG_J];
+  for (int x0 = 0; x0 < E; x0 += 256 * CPTG) {
+    float h[CPTG][TG_J], accH[CPTG][TG_J], accV[CPTG][TG_J], wx[CPTG];
+    bool act[CPTG];
 #pragma unroll
-    for (int jj = 0; jj < TG_J; jj++) {
-      h[jj] = (act && jj < nj) ? a.H[((long long)b * L + j0 + jj) * E + x] : 0.f;
-      accH[jj] = 0.f;
-      accV[jj] = 0.f;
-    }
-    const float wx = act ? a.w[x] : 0.f;
-    for (int t = 0; t < a.T; t++)
-      for (int wi = 0; wi < a.W; wi++) {
-        const int n = b * a.W + wi;
-        const long long tn = (long long)t * a.N + n;
-        __syncthreads();
-        if (threadIdx.x < TG_J) {
-          const int jj = threadIdx.x;
-          al_sh[jj] = jj < nj ? a.alpha[tn * L + j0 + jj] : 0.f;
-          de_sh[jj] = jj < nj ? a.DE[tn * L + j0 + jj] : 0.f;
-        }
-        __syncthreads();
-        if (act) {
-          const float s = a.S_all[tn * a.ldS + a.mod * E + x];
-          const float dc = a.DC_all[(tn * 2 + a.mod) * E + x];
+    for (int i = 0; i < CPTG; i++) {
+      const int x = x0 + threadIdx.x + 256 * i;
+      act[i] = x < E;
+      wx[i] = act[i] ? a.w[x] : 0.f;
 #pragma unroll
-          for (int jj = 0; jj < TG_J; jj++) {
-            const float q = tanh_acc(h[jj] + s);
-            accH[jj] = fmaf(de_sh[jj], 1.f - q * q, accH[jj]);
-            accV[jj] = fmaf(al_sh[jj], dc, accV[jj]);
-          }
-        }
+      for (int jj = 0; jj < TG_J; jj++) {
+        h[i][jj] = (act[i] && jj < nj) ? a.H[((long long)b * L + j0 + jj) * E + x] : 0.f;
+        accH[i][jj] = 0.f;
+        accV[i][jj] = 0.f;
       }
-    if (act) {
+    }
+    const int iters = a.T * a.W;
+    __syncthreads();                       // the previous x0 pass is done with the staging buffers
+    for (int it = 0; it < iters; it++) {
+      const int t = it / a.W, wi = it - t * a.W;
+      const long long tn = (long long)t * a.N + b * a.W + wi;
+      const int buf = it & 1;              // double-buffered scalars: one barrier per (step, row)
+      if (threadIdx.x < TG_J) {
+        const int jj = threadIdx.x;
+        al_sh[buf][jj] = jj < nj ? a.alpha[tn * L + j0 + jj] : 0.f;
+        de_sh[buf][jj] = jj < nj ? a.DE[tn * L + j0 + jj] : 0.f;
+      }
+      float s[CPTG], dc[CPTG];
+#pragma unroll
+      for (int i = 0; i < CPTG; i++) {
+        const int x = x0 + threadIdx.x + 256 * i;
+        s[i] = act[i] ? a.S_all[tn * a.ldS + a.mod * E + x] : 0.f;
+        dc[i] = act[i] ? a.DC_all[(tn * 2 + a.mod) * E + x] : 0.f;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < CPTG; i++)
+#pragma unroll
+        for (int jj = 0; jj < TG_J; jj++) {
+          const float q = tanh_fast<APPROX>(h[i][jj] + s[i]);
+          accH[i][jj] = fmaf(de_sh[buf][jj], fmaf(-q, q, 1.f), accH[i][jj]);
+          accV[i][jj] = fmaf(al_sh[buf][jj], dc[i], accV[i][jj]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < CPTG; i++) {
+      const int x = x0 + threadIdx.x + 256 * i;
+      if (!act[i]) continue;
 #pragma unroll
       for (int jj = 0; jj < TG_J; jj++)
         if (jj < nj) {
           const long long o = ((long long)b * L + j0 + jj) * E + x;
           if (a.byproj) {
-            a.dH[o] = accH[jj] * wx + accV[jj];
+            a.dH[o] = accH[i][jj] * wx[i] + accV[i][jj];
           } else {
-            a.dH[o] = accH[jj] * wx;
-            a.dV[o] = accV[jj];
+            a.dH[o] = accH[i][jj] * wx[i];
+            a.dV[o] = accV[i][jj];
           }
         }
     }
@@ -598,6 +616,7 @@ using namespace v2f;
 
 namespace v2f {
 int decode_persist_fwd(const v2f_decode_params* p, cudaStream_t s);   // decode_persist.cu
+int decode_team_fwd(const v2f_decode_params* p, cudaStream_t s);      // decode_team.cu
 }
 
 #define NT(M, N, K, A, lda, B, ldb, C, ldc, bias, beta) V2F_TRY(gemm_nt(gx, M, N, K, A, lda, B, ldb, C, ldc, bias, beta))
@@ -623,8 +642,11 @@ extern "C" int v2f_decode_fwd(const v2f_decode_params* p, void* st) {
     copy_kernel<<<(N + 255) / 256, 256, 0, s>>>(N, p->x0, p->xin);
     V2F_CHECK_LAUNCH();
   }
-  {   // the whole loop as one persistent cooperative launch when the configuration allows
-    const int rc = decode_persist_fwd(p, s);
+  {   // the whole loop as one persistent cooperative launch when the configuration allows: the row-team tcgen05
+      // kernel (decode_team.cu) at the default dims in tensor-core mode, else the column-split kernel (decode_persist.cu)
+    int rc = gru ? decode_team_fwd(p, s) : V2F_ERR_UNSUPPORTED;
+    if (rc != V2F_ERR_UNSUPPORTED) return rc;
+    rc = decode_persist_fwd(p, s);
     if (rc != V2F_ERR_UNSUPPORTED) return rc;
   }
   for (int t = 0; t < T; t++) {
@@ -781,7 +803,16 @@ extern "C" int v2f_decode_bwd(const v2f_decode_params* p, void* st) {
     // trend context always comes from Ptr (never from Htr), so byproj only affects the image tile
     if (mod) tg.byproj = 0;
     prof_begin(V2F_K_TILEGRAD, s);
-    tilegrad_kernel<<<dim3(B, (L + TG_J - 1) / TG_J), 256, 0, s>>>(tg);
+    {
+      const dim3 grid(B, (L + TG_J - 1) / TG_J);
+      if (p->precision != 0) {
+        if (E > 256) tilegrad_kernel<true, 2><<<grid, 256, 0, s>>>(tg);
+        else tilegrad_kernel<true, 1><<<grid, 256, 0, s>>>(tg);
+      } else {
+        if (E > 256) tilegrad_kernel<false, 2><<<grid, 256, 0, s>>>(tg);
+        else tilegrad_kernel<false, 1><<<grid, 256, 0, s>>>(tg);
+      }
+    }
     prof_end(V2F_K_TILEGRAD, s);
     V2F_CHECK_LAUNCH();
   }

@@ -475,25 +475,33 @@ STREAM_ATTENTION = True      # TMA-staged streaming attention kernels when the d
 # whole decode loop as one cooperative launch (csrc/decode_persist.cu) when the dims allow; V2F_PERSISTENT_DECODE=0 is
 # the A/B switch of bench.py / tools
 PERSISTENT_DECODE = os.environ.get("V2F_PERSISTENT_DECODE", "1") != "0"
+TEAM_DECODE = os.environ.get("V2F_TEAM_DECODE", "1") != "0"    # A/B switch: 0 keeps the decoder on decode_persist.cu
 
 
 KEEP_LAST_PERSIST_WS = False   # profiling: remember the persistent decoder's workspace (phase stamps live in it)
 _last_persist = []
 PERSIST_PHASES = ("P1 S-product", "P2 attention sweep", "P2b combine", "P3 HC-product", "P4 multimodal attention",
                   "P5/P6 embedder + GRU gates")
+TEAM_PHASES = ("P1 S-product", "P2 attention sweep", "P3 HC-product", "P4 multimodal attention", "P5 GI-product + GRU gates")
 
 
 def persist_phase_times():
     """Per-phase times (us, mean over the T steps, CTA 0's %globaltimer stamps) of the most recent persistent decode
-    forward run with v2f_decode_persist_stamps_enable(1) and KEEP_LAST_PERSIST_WS: {phase: (work_us, barrier_us)}."""
+    forward run with the stamps enabled and KEEP_LAST_PERSIST_WS: {phase: (work_us, barrier_us)}."""
     if not _last_persist:
         return None
-    ws, (N, E, H, T, Li, Lt) = _last_persist
-    off = _lib.lib().v2f_decode_persist_stamps_offset(N, E, H) // 4
+    team = len(_last_persist) == 3
+    ws, (N, E, H, T, Li, Lt) = _last_persist[:2]
+    if team:
+        off = _lib.lib().v2f_decode_team_stamps_offset(N, _last_persist[2], T, Li, Lt) // 4
+        names = TEAM_PHASES
+    else:
+        off = _lib.lib().v2f_decode_persist_stamps_offset(N, E, H) // 4
+        names = PERSIST_PHASES
     torch.cuda.synchronize()
     st = ws[off:off + 2 * T * 16].cpu().view(torch.int64).view(T, 16)
     out = {}
-    for k, name in enumerate(PERSIST_PHASES):
+    for k, name in enumerate(names):
         work = sum(int(st[t, 2 * k + 1]) - int(st[t, 2 * k]) for t in range(T)) / T / 1e3
         wait = sum(int(st[t, 2 * k + 2]) - int(st[t, 2 * k + 1]) for t in range(T)) / T / 1e3
         out[name] = (work, wait)
@@ -559,6 +567,12 @@ class _Decode(torch.autograd.Function):
                 keep["persist_ws"] = _f32(_lib.lib().v2f_decode_persist_ws_floats(N, E, H, T), device=dev)
                 if KEEP_LAST_PERSIST_WS:
                     _last_persist[:] = [keep["persist_ws"], (N, E, H, T, Li, Lt)]
+                # row-team tcgen05 kernel (csrc/decode_team.cu): default dims, tensor-core mode, <= 128 rows per launch
+                if TEAM_DECODE and prec and E == 512 and H == 512 and N <= 128 and full:
+                    p.team_ws_floats = _lib.lib().v2f_decode_team_ws_floats(N, B, T, Li, Lt)
+                    keep["team_ws"] = _f32(p.team_ws_floats, device=dev)
+                    if KEEP_LAST_PERSIST_WS:
+                        _last_persist[:] = [keep["team_ws"], (N, E, H, T, Li, Lt), B]
         for k, v in keep.items():
             setattr(p, k, ptr(v, allow_none=True))
         p.tf_mask_dev = ptr(tf_dev, torch.int32, allow_none=True)
