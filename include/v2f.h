@@ -158,6 +158,11 @@ int v2f_decode_fwd(const v2f_decode_params* p, void* stream);
 int v2f_decode_bwd(const v2f_decode_params* p, void* stream);
 long long v2f_decode_persist_ws_floats(int N, int E, int H, int T);
 long long v2f_decode_team_ws_floats(int N, int B, int T, int Li, int Lt);
+/* Backward of the row-team decoder: v2f_decode_bwd runs the whole BPTT loop as one cooperative launch when the forward
+ * took the row-team kernel (same params, team_ws still holding the forward's bf16 tiles) and the backward scratch `ws`
+ * has at least this many floats; 0 disables it (the step-per-launch loop runs instead). */
+long long v2f_decode_team_bwd_ws_floats(int N, int T);
+int v2f_decode_team_bwd_enable(int on);
 /* A/B switch (default 1): 0 keeps the decoder off the row-team kernel. */
 int v2f_decode_team_enable(int on);
 /* Profiling: CTA 0 of the row-team decoder stamps %globaltimer (ns), [T][16] unsigned long long at byte offset

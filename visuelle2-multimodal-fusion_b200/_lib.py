@@ -95,6 +95,9 @@ def _declare(lib):
     lib.v2f_decode_team_stamps_offset.argtypes = [c_int] * 5
     lib.v2f_decode_team_stamps_offset.restype = c_ll
     lib.v2f_decode_team_enable.argtypes = [c_int]
+    lib.v2f_decode_team_bwd_enable.argtypes = [c_int]
+    lib.v2f_decode_team_bwd_ws_floats.argtypes = [c_int, c_int]
+    lib.v2f_decode_team_bwd_ws_floats.restype = c_ll
     lib.v2f_decode_team_stamps_enable.argtypes = [c_int]
     lib.v2f_prof_read.argtypes = [c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(c_ll)]
     lib.v2f_prof_read_bytes.argtypes = [c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(c_ll),

@@ -18,9 +18,10 @@
 //     beyond the slice are don't-care) x X^T (B operand: the team's 64 activation rows, bf16, TMA-loaded in 64-wide
 //     K chunks through an 8-slot mbarrier ring), tcgen05.mma kind::f16 issued by one thread, fp32 accumulator in
 //     TMEM, read back with tcgen05.ld: 64 KB of activations per CTA per product instead of 256 KB;
-//   * the attention sweep of a row runs entirely inside its owner CTA (two 8-warp groups with a 4-slot bulk-copy
-//     ring each, bf16 tiles, online softmax, partials combined in shared memory): no combine phase, no partial
-//     traffic through L2, 304 KB per row and step instead of 608 KB;
+//   * the attention sweep of a row runs entirely inside its owner CTA, in two passes over bf16 tiles fed by one bulk-copy
+//     ring: energies (warp per position, no inter-warp dependency), softmax over the 152 stored energies, then the
+//     weighted sums (thread per column pair, plain FMAs): no online softmax, no combine phase, no partial traffic
+//     through L2, 304 KB per row and step instead of 608 KB;
 //   * barriers are per team (64 arrivals) and there are five per step.
 // GI = CTX W_ihc^T is re-associated to U (W_ihc W_me)^T (exact); CTX itself (saved for the backward) is one GEMM
 // over all T*N rows after the loop.  The GRU state, softmax, gates and all saved activations stay fp32; bf16 is
@@ -46,7 +47,6 @@ constexpr int DT_BSLOT = DT_NG * 128;        // 8 KB: 64 activation rows x 64 bf
 constexpr int DT_NBS = 8;
 constexpr int DT_CH = 8;                     // positions per attention chunk
 constexpr int DT_TSLOT = DT_CH * DT_E * 2;   // 8 KB: one operand (H or V) of one chunk, bf16
-constexpr int DT_TSLOTS = 4;                 // ring slots per group
 constexpr int DT_RING = DT_NBS * DT_BSLOT;   // 64 KB, shared by the B ring (products) and the tile rings (sweep)
 constexpr int DT_P1 = 65, DT_P3 = 129;       // staging pitches (odd: conflict-free transposed writes)
 constexpr int DT_NCTR = 8;
@@ -54,8 +54,9 @@ constexpr int DT_BARW = DT_NCTR * 32;        // unsigned words of barrier counte
 constexpr int DT_STAMPS = 16;
 constexpr uint32_t DT_TMEM_COLS = 256;       // D1: 0..63, D3: 64..191, D5: 192..255
 constexpr int DT_MAXTEAMS = 2;
+constexpr int DT_MAXL = 256;                 // positions per attention (image map 100, trends 52)
 
-static_assert(DT_RING == 2 * DT_TSLOTS * DT_TSLOT, "the two rings alias");
+static_assert(DT_RING == DT_NBS * DT_TSLOT, "the two rings alias");
 
 struct DtArgs {
   v2f_decode_params p;
@@ -146,16 +147,15 @@ decode_team_fwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_co
   float* stage1 = reinterpret_cast<float*>(ring + DT_RING);     // [48][65]: S columns and GH of the team's rows
   float* stage5 = stage1 + 48 * DT_P1;                          // [24][65] GI  (P3: [8][129] HC)
   float* cvec = stage5 + 24 * DT_P1 + 8;                        // [2][512] contexts of the own row
-  float* pacc = cvec + 2 * E;                                   // [4][512] attention partials
-  float* pml = pacc + 4 * E;                                    // [4][2] (m, l)
-  int* pmod = reinterpret_cast<int*>(pml + 8);                  // [4] modality of a partial, -1 = unused
-  float* e_sh = reinterpret_cast<float*>(pmod + 4);             // [2 groups][2][8]
-  float* red = e_sh + 32;                                       // [64]
+  float* pacc = cvec + 2 * E;                                   // [2 groups][2 modalities][512] partial contexts
+  float* e_all = pacc + 4 * E;                                  // [2][DT_MAXL] energies of the own row
+  float* al_all = e_all + 2 * DT_MAXL;                          // [2][DT_MAXL] softmax weights
+  float* red = al_all + 2 * DT_MAXL;                            // [64]
   uint64_t* bfull = reinterpret_cast<uint64_t*>(red + 64);      // [8] B ring
   uint64_t* bempty = bfull + DT_NBS;                            // [8]
-  uint64_t* tfull = bempty + DT_NBS;                            // [2][4] tile rings
-  uint64_t* tempty = tfull + 2 * DT_TSLOTS;                     // [2][4]
-  uint64_t* mma_done = tempty + 2 * DT_TSLOTS;
+  uint64_t* tfull = bempty + DT_NBS;                            // [8] tile ring (same 64 KB as the B ring)
+  uint64_t* tempty = tfull + DT_NBS;                            // [8]
+  uint64_t* mma_done = tempty + DT_NBS;
   uint64_t* wfull = mma_done + 1;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(wfull + 1);
 
@@ -165,7 +165,7 @@ decode_team_fwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_co
       mbar_init(&bfull[s], 1);
       mbar_init(&bempty[s], 1);
     }
-    for (int s = 0; s < 2 * DT_TSLOTS; s++) {
+    for (int s = 0; s < DT_NBS; s++) {
       mbar_init(&tfull[s], 1);
       mbar_init(&tempty[s], DT_GRP / 32);
     }
@@ -198,14 +198,8 @@ decode_team_fwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_co
   uint32_t md = 0;                 // completed waits on mma_done
   const int grp = warp < 8 ? 0 : (warp < 16 ? 1 : warp - 16);
   const int gt = tid & (DT_GRP - 1), gw = (tid >> 5) & 7;
-  uint8_t* gring = ring + grp * DT_TSLOTS * DT_TSLOT;
-  uint64_t* gfull = tfull + grp * DT_TSLOTS;
-  uint64_t* gempty = tempty + grp * DT_TSLOTS;
-  float* ge = e_sh + grp * 16;
-  uint32_t tq = 0;                 // tile-ring slots used by this group so far
+  uint32_t tq = 0;                 // tile-ring slots used so far (all steps)
   const int cpi = (Li + DT_CH - 1) / DT_CH, cpt = (Lt + DT_CH - 1) / DT_CH, ctot = cpi + cpt;
-  const int chalf = (ctot + 1) / 2;
-  const int c_lo = grp == 0 ? 0 : chalf, c_hi = grp == 0 ? chalf : ctot;
   const uint32_t idesc = umma_idesc<0>(DT_NG);
   auto stamp = [&](int t, int k) {
     if (a.stamps && blockIdx.x == 0 && tid == 0) a.stamps[t * DT_STAMPS + k] = dt_globaltimer();
@@ -298,162 +292,165 @@ decode_team_fwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_co
     dt_team_barrier(bar, c, epoch);
     stamp(t, 2);
     // ================================================================ P2: additive attention of the own row
+    // Two passes over the row's tiles, no inter-warp dependency inside a pass.  Pass 1 streams the H tiles: warp gw of
+    // group g computes the energy of position gw of the chunks g, g+2, ... on its own (no group barrier, the slot is
+    // released when its 8 warps have arrived).  Then the 152 energies are normalised (every warp redundantly, 5
+    // values per lane).  Pass 2 streams the V tiles: thread = 2 columns, c += alpha_j V_j, plain FMAs (the weights
+    // are final: no online-softmax rescaling).  The producer runs ahead through the 8-slot ring across both passes.
     if (own) {
       const int n = n_own, b = n / Wn;
-      if (warp >= 16) {
+      if (warp == 16) {
         if (lane == 0) {
           uint32_t q = tq;
-          for (int cc0 = c_lo; cc0 < c_hi; cc0++, q += 2) {
-            const int mod = cc0 >= cpi, cc = mod ? cc0 - cpi : cc0;
-            const int L = mod ? Lt : Li, j0 = cc * DT_CH, nj = min(DT_CH, L - j0);
-            const long long off = ((long long)b * L + j0) * E;
-            const uint32_t bytes = (uint32_t)nj * E * 2u;
-            const uint32_t sH = q % DT_TSLOTS, rH = q / DT_TSLOTS;
-            mbar_wait(&gempty[sH], (rH & 1) ^ 1);
-            mbar_expect_tx(&gfull[sH], bytes);
-            bulk_g2s(gring + sH * DT_TSLOT, (mod ? a.Htr : a.Himg) + off, bytes, &gfull[sH]);
-            const uint32_t sV = (q + 1) % DT_TSLOTS, rV = (q + 1) / DT_TSLOTS;
-            mbar_wait(&gempty[sV], (rV & 1) ^ 1);
-            mbar_expect_tx(&gfull[sV], bytes);
-            bulk_g2s(gring + sV * DT_TSLOT, (mod ? a.Ptr : Vimg_b) + off, bytes, &gfull[sV]);
-          }
+          for (int pass = 0; pass < 2; pass++)
+            for (int cc0 = 0; cc0 < ctot; cc0++, q++) {
+              const int mod = cc0 >= cpi, cc = mod ? cc0 - cpi : cc0;
+              const int L = mod ? Lt : Li, j0 = cc * DT_CH, nj = min(DT_CH, L - j0);
+              const long long off = ((long long)b * L + j0) * E;
+              const uint32_t bytes = (uint32_t)nj * E * 2u;
+              const uint32_t sl = q % DT_NBS, r = q / DT_NBS;
+              const __nv_bfloat16* src = pass == 0 ? (mod ? a.Htr : a.Himg) : (mod ? a.Ptr : Vimg_b);
+              mbar_wait(&tempty[sl], (r & 1) ^ 1);
+              mbar_expect_tx(&tfull[sl], bytes);
+              bulk_g2s(ring + sl * DT_TSLOT, src + off, bytes, &tfull[sl]);
+            }
         }
         __syncwarp();
-      } else {
-        float4 sreg[4], wreg[4];        // columns 8*lane + 256*k + [0,8) for k = 0,1: two float4 each
-        float cacc0 = 0.f, cacc1 = 0.f;
-        float m_run = -INFINITY, l_run = 0.f, beta = 0.f;
-        int cur_mod = -1, nseg = 0;
-        auto flush = [&]() {
-          const int ps = grp * 2 + nseg;
-          if (gt == 0) {
-            pml[2 * ps] = m_run;
-            pml[2 * ps + 1] = l_run;
-            pmod[ps] = cur_mod;
-          }
-          *reinterpret_cast<float2*>(pacc + ps * E + 2 * gt) = make_float2(cacc0, cacc1);
-          nseg++;
-        };
-        if (gt < 2) pmod[grp * 2 + gt] = -1;
-        uint32_t q = tq;
-        int par = 0;
-        for (int cc0 = c_lo; cc0 < c_hi; cc0++, q += 2, par ^= 1) {
-          const int mod = cc0 >= cpi, cc = mod ? cc0 - cpi : cc0;
-          const int L = mod ? Lt : Li, j0 = cc * DT_CH, nj = min(DT_CH, L - j0);
-          if (mod != cur_mod) {
-            if (cur_mod >= 0) flush();
-            cur_mod = mod;
-            m_run = -INFINITY;
-            l_run = 0.f;
-            cacc0 = cacc1 = 0.f;
-            const float* sp = S + (long long)n * ldS + mod * E;
-            const float* wp = p.w_att + mod * E;
-#pragma unroll
-            for (int k = 0; k < 2; k++) {
-              sreg[2 * k] = __ldcg(reinterpret_cast<const float4*>(sp + 8 * lane + 256 * k));
-              sreg[2 * k + 1] = __ldcg(reinterpret_cast<const float4*>(sp + 8 * lane + 256 * k + 4));
-              wreg[2 * k] = ld4(wp + 8 * lane + 256 * k);
-              wreg[2 * k + 1] = ld4(wp + 8 * lane + 256 * k + 4);
-            }
-            beta = p.beta_att[mod];
-          }
-          const uint32_t sH = q % DT_TSLOTS, rH = q / DT_TSLOTS;
-          const uint32_t sV = (q + 1) % DT_TSLOTS, rV = (q + 1) / DT_TSLOTS;
-          const uint8_t* Hs = gring + sH * DT_TSLOT;
-          const uint8_t* Vs = gring + sV * DT_TSLOT;
-          mbar_wait(&gfull[sH], rH & 1);
-          float* eb = ge + par * DT_CH;
-          if (gw < nj) {
-            const uint8_t* hp = Hs + gw * (E * 2);
-            float acc = 0.f;
-#pragma unroll
-            for (int k = 0; k < 2; k++) {
-              const uint4 hv = *reinterpret_cast<const uint4*>(hp + (8 * lane + 256 * k) * 2);
-              const float2 h0 = dt_bf2(hv.x), h1 = dt_bf2(hv.y), h2 = dt_bf2(hv.z), h3 = dt_bf2(hv.w);
-              const float4 s0 = sreg[2 * k], s1 = sreg[2 * k + 1], w0 = wreg[2 * k], w1 = wreg[2 * k + 1];
-              acc = fmaf(w0.x, tanh_fast<true>(h0.x + s0.x), acc);
-              acc = fmaf(w0.y, tanh_fast<true>(h0.y + s0.y), acc);
-              acc = fmaf(w0.z, tanh_fast<true>(h1.x + s0.z), acc);
-              acc = fmaf(w0.w, tanh_fast<true>(h1.y + s0.w), acc);
-              acc = fmaf(w1.x, tanh_fast<true>(h2.x + s1.x), acc);
-              acc = fmaf(w1.y, tanh_fast<true>(h2.y + s1.y), acc);
-              acc = fmaf(w1.z, tanh_fast<true>(h3.x + s1.z), acc);
-              acc = fmaf(w1.w, tanh_fast<true>(h3.y + s1.w), acc);
-            }
-            acc = warp_sum(acc) + beta;
-            if (lane == 0) {
-              eb[gw] = acc;
-              (mod ? al_tr : al_img)[(long long)n * L + j0 + gw] = acc;   // raw energy; normalised after the combine
-            }
-          } else if (lane == 0) {
-            eb[gw] = -INFINITY;
-          }
-          named_bar_sync(1 + grp, DT_GRP);
-          if (lane == 0) mbar_arrive(&gempty[sH]);        // every warp of the group is past its H reads
-          const float ej = lane < DT_CH ? eb[lane] : -INFINITY;
-          const float m_new = fmaxf(m_run, warp_max(ej));
-          const float scale = expf(m_run - m_new);
-          const float pj = expf(ej - m_new);
-          l_run = l_run * scale + warp_sum(pj);
-          m_run = m_new;
-          cacc0 *= scale;
-          cacc1 *= scale;
-          mbar_wait(&gfull[sV], rV & 1);
-          const uint8_t* vp = Vs + gt * 4;
-          if (nj == DT_CH) {
-#pragma unroll
-            for (int j = 0; j < DT_CH; j++) {
-              const float pr = __shfl_sync(FULL, pj, j);
-              const float2 v = dt_bf2(*reinterpret_cast<const uint32_t*>(vp + j * (E * 2)));
-              cacc0 = fmaf(pr, v.x, cacc0);
-              cacc1 = fmaf(pr, v.y, cacc1);
-            }
-          } else {
-            for (int j = 0; j < nj; j++) {
-              const float pr = __shfl_sync(FULL, pj, j);
-              const float2 v = dt_bf2(*reinterpret_cast<const uint32_t*>(vp + j * (E * 2)));
-              cacc0 = fmaf(pr, v.x, cacc0);
-              cacc1 = fmaf(pr, v.y, cacc1);
-            }
-          }
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&gempty[sV]);
-        }
-        if (cur_mod >= 0) flush();
-        named_bar_sync(3, DT_CONS);
-        // combine the (<= 2) partials of each modality; thread = column
+      } else if (warp < 16) {
+        // ---- pass 1: energies
         {
-          const int x = tid;
-          float mm_[2], inv_[2];
+          float4 sreg[4], wreg[4];        // columns 8*lane + 256*k + [0,8) for k = 0,1: two float4 each
+          float beta = 0.f;
+          int cur_mod = -1;
+          for (int cc0 = grp; cc0 < ctot; cc0 += 2) {
+            const int mod = cc0 >= cpi, cc = mod ? cc0 - cpi : cc0;
+            const int L = mod ? Lt : Li, j0 = cc * DT_CH, nj = min(DT_CH, L - j0);
+            if (mod != cur_mod) {
+              cur_mod = mod;
+              const float* sp = S + (long long)n * ldS + mod * E;
+              const float* wp = p.w_att + mod * E;
+#pragma unroll
+              for (int k = 0; k < 2; k++) {
+                sreg[2 * k] = __ldcg(reinterpret_cast<const float4*>(sp + 8 * lane + 256 * k));
+                sreg[2 * k + 1] = __ldcg(reinterpret_cast<const float4*>(sp + 8 * lane + 256 * k + 4));
+                wreg[2 * k] = ld4(wp + 8 * lane + 256 * k);
+                wreg[2 * k + 1] = ld4(wp + 8 * lane + 256 * k + 4);
+              }
+              beta = p.beta_att[mod];
+            }
+            const uint32_t q = tq + (uint32_t)cc0, sl = q % DT_NBS, r = q / DT_NBS;
+            mbar_wait(&tfull[sl], r & 1);
+            if (gw < nj) {
+              const uint8_t* hp = ring + sl * DT_TSLOT + gw * (E * 2);
+              float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+              for (int k = 0; k < 2; k++) {
+                const uint4 hv = *reinterpret_cast<const uint4*>(hp + (8 * lane + 256 * k) * 2);
+                const float2 h0 = dt_bf2(hv.x), h1 = dt_bf2(hv.y), h2 = dt_bf2(hv.z), h3 = dt_bf2(hv.w);
+                const float4 s0 = sreg[2 * k], s1 = sreg[2 * k + 1], w0 = wreg[2 * k], w1 = wreg[2 * k + 1];
+                acc0 = fmaf(w0.x, tanh_fast<true>(h0.x + s0.x), acc0);
+                acc1 = fmaf(w0.y, tanh_fast<true>(h0.y + s0.y), acc1);
+                acc0 = fmaf(w0.z, tanh_fast<true>(h1.x + s0.z), acc0);
+                acc1 = fmaf(w0.w, tanh_fast<true>(h1.y + s0.w), acc1);
+                acc0 = fmaf(w1.x, tanh_fast<true>(h2.x + s1.x), acc0);
+                acc1 = fmaf(w1.y, tanh_fast<true>(h2.y + s1.y), acc1);
+                acc0 = fmaf(w1.z, tanh_fast<true>(h3.x + s1.z), acc0);
+                acc1 = fmaf(w1.w, tanh_fast<true>(h3.y + s1.w), acc1);
+              }
+              const float e = warp_sum(acc0 + acc1) + beta;
+              if (lane == 0) e_all[mod * DT_MAXL + j0 + gw] = e;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[sl]);
+          }
+        }
+        stamp(t, 11);
+        named_bar_sync(3, DT_CONS);
+        stamp(t, 12);
+        // ---- softmax over the positions of each modality (every warp computes the statistics redundantly)
+        {
+          float mx0 = 0.f, mx1 = 0.f, inv0 = 0.f, inv1 = 0.f;
 #pragma unroll
           for (int mod = 0; mod < 2; mod++) {
-            float M = -INFINITY;
+            const int L = mod ? Lt : Li;
+            const float* ev = e_all + mod * DT_MAXL;
+            float m = -INFINITY;
+            for (int j = lane; j < L; j += 32) m = fmaxf(m, ev[j]);
+            m = warp_max(m);
+            float l = 0.f;
+            for (int j = lane; j < L; j += 32) l += expf(ev[j] - m);
+            l = warp_sum(l);
+            if (mod) {
+              mx1 = m;
+              inv1 = 1.0f / l;
+            } else {
+              mx0 = m;
+              inv0 = 1.0f / l;
+            }
+          }
+          for (int j = tid; j < Li + Lt; j += DT_CONS) {
+            const int mod = j >= Li, jj = mod ? j - Li : j;
+            const float al = expf(e_all[mod * DT_MAXL + jj] - (mod ? mx1 : mx0)) * (mod ? inv1 : inv0);
+            al_all[mod * DT_MAXL + jj] = al;
+            (mod ? al_tr + (long long)n * Lt : al_img + (long long)n * Li)[jj] = al;   // saved for the backward / attention maps
+          }
+        }
+        named_bar_sync(3, DT_CONS);
+        stamp(t, 13);
+        // ---- pass 2: contexts (thread = columns 2 gt, 2 gt + 1 of both modalities; group g takes chunks g, g+2, ...)
+        {
+          float ci0 = 0.f, ci1 = 0.f, ct0 = 0.f, ct1 = 0.f;
+          for (int cc0 = grp; cc0 < ctot; cc0 += 2) {
+            const int mod = cc0 >= cpi, cc = mod ? cc0 - cpi : cc0;
+            const int L = mod ? Lt : Li, j0 = cc * DT_CH, nj = min(DT_CH, L - j0);
+            const uint32_t q = tq + (uint32_t)(ctot + cc0), sl = q % DT_NBS, r = q / DT_NBS;
+            const float* alp = al_all + mod * DT_MAXL + j0;
+            mbar_wait(&tfull[sl], r & 1);
+            const uint8_t* vp = ring + sl * DT_TSLOT + gt * 4;
+            float x0 = 0.f, x1 = 0.f;
+            if (nj == DT_CH) {
 #pragma unroll
-            for (int ps = 0; ps < 4; ps++)
-              if (pmod[ps] == mod && pml[2 * ps + 1] > 0.f) M = fmaxf(M, pml[2 * ps]);
-            float den = 0.f, cv = 0.f;
-#pragma unroll
-            for (int ps = 0; ps < 4; ps++)
-              if (pmod[ps] == mod && pml[2 * ps + 1] > 0.f) {
-                const float wgt = expf(pml[2 * ps] - M);
-                den = fmaf(pml[2 * ps + 1], wgt, den);
-                cv = fmaf(wgt, pacc[ps * E + x], cv);
+              for (int j = 0; j < DT_CH; j++) {
+                const float2 v = dt_bf2(*reinterpret_cast<const uint32_t*>(vp + j * (E * 2)));
+                x0 = fmaf(alp[j], v.x, x0);
+                x1 = fmaf(alp[j], v.y, x1);
               }
-            const float inv = 1.0f / den;
-            cv *= inv;
+            } else {
+              for (int j = 0; j < nj; j++) {
+                const float2 v = dt_bf2(*reinterpret_cast<const uint32_t*>(vp + j * (E * 2)));
+                x0 = fmaf(alp[j], v.x, x0);
+                x1 = fmaf(alp[j], v.y, x1);
+              }
+            }
+            if (mod) {
+              ct0 += x0;
+              ct1 += x1;
+            } else {
+              ci0 += x0;
+              ci1 += x1;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[sl]);
+          }
+          // partial contexts of this group: pacc[grp][mod][512]
+          stamp(t, 14);
+          *reinterpret_cast<float2*>(pacc + (grp * 2 + 0) * E + 2 * gt) = make_float2(ci0, ci1);
+          *reinterpret_cast<float2*>(pacc + (grp * 2 + 1) * E + 2 * gt) = make_float2(ct0, ct1);
+        }
+        named_bar_sync(3, DT_CONS);
+        {
+          const int x = tid;
+#pragma unroll
+          for (int mod = 0; mod < 2; mod++) {
+            float cv = pacc[mod * E + x] + pacc[(2 + mod) * E + x];
             if (mod) cv += p.b_tl[x];
             cvec[mod * E + x] = cv;
             C[((long long)n * 2 + mod) * E + x] = cv;
             a.Cb[((long long)mod * Np + n) * E + x] = __float2bfloat16_rn(cv);
-            mm_[mod] = M;
-            inv_[mod] = inv;
           }
-          // softmax weights for the backward pass / attention maps (raw energies were written by this CTA)
-          for (int j = tid; j < Li; j += DT_CONS) al_img[(long long)n * Li + j] = expf(al_img[(long long)n * Li + j] - mm_[0]) * inv_[0];
-          for (int j = tid; j < Lt; j += DT_CONS) al_tr[(long long)n * Lt + j] = expf(al_tr[(long long)n * Lt + j] - mm_[1]) * inv_[1];
         }
       }
-      tq += 2u * (uint32_t)(c_hi - c_lo);
+      tq += 2u * (uint32_t)ctot;
     }
     stamp(t, 3);
     dt_team_barrier(bar, c, epoch);
@@ -678,8 +675,8 @@ static bool g_dt_enabled = true;
 static int g_dt_stamps = 0;
 
 static size_t dt_smem() {
-  return 1024 + (size_t)DT_WBYTES + DT_RING + sizeof(float) * (48 * DT_P1 + 24 * DT_P1 + 8 + 2 * DT_E + 4 * DT_E + 8 + 4 + 32 + 64) +
-         8 * (2 * DT_NBS + 4 * DT_TSLOTS + 2) + 16;
+  return 1024 + (size_t)DT_WBYTES + DT_RING + sizeof(float) * (48 * DT_P1 + 24 * DT_P1 + 8 + 2 * DT_E + 4 * DT_E + 4 * DT_MAXL + 64) +
+         8 * (4 * DT_NBS + 2) + 16;
 }
 
 struct DtLayout {
@@ -711,7 +708,7 @@ static bool dt_supported(const v2f_decode_params* p) {
   if ((p->mod_mask & 0b1010) != 0b1010) return false;
   if (p->E != DT_E || p->H != DT_E) return false;
   if (p->N < 1 || p->N > DT_MAXTEAMS * DT_NG) return false;
-  if (p->Li < 1 || p->Lt < 1 || p->Li > 4096 || p->Lt > 4096) return false;
+  if (p->Li < 1 || p->Lt < 1 || p->Li > DT_MAXL || p->Lt > DT_MAXL) return false;
   if (p->team_ws_floats < decode_team_ws_floats(p->N, p->B, p->T, p->Li, p->Lt)) return false;
   int dev = 0, coop = 0, sms = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return false;
@@ -793,6 +790,639 @@ int decode_team_fwd(const v2f_decode_params* p, cudaStream_t s) {
   return V2F_OK;
 }
 
+
+// ================================================================================================ backward
+// Row-team persistent BPTT: ONE cooperative launch walks the T steps backwards (CrossAttnRNN210.py:191-225 reversed).
+// Same teams / ownership as the forward.  The three per-step products are the transposed ones,
+//   dU  = DGI  W'                 [64 x 1536] x [1536 x 512]
+//   dC += DHC  We_mm              [128 x 512] x [512 x 512]
+//   dh += DS   Wcat               [64 x 3072] x [3072 x 512]
+// computed output-stationary: CTA c owns output columns 8c..8c+7 of each, i.e. 8 ROWS of W'^T | We_mm^T | Wcat^T
+// (8 x 5120 bf16 = 80 KB, resident for the whole launch as 80 swizzled [8 x 128 B] chunks).  The activations are the A
+// operand now (M = 128 tile: the team's 64 rows + 64 don't-care rows, TMA-loaded in 64-wide K chunks through the 8-slot
+// ring), the weight chunk the B operand (N = 16: 8 rows + 8 don't-care), accumulator [row, column] in TMEM: a thread
+// of warps 0/1 reads its row's 8 values directly.  Row-local phases (gate backward, multimodal-attention backward, the
+// attention backward sweep over the bf16 tiles of the forward) run in the row's owner CTA; dw_att / dMst / dHMst
+// accumulate in the owner's registers over all steps and are written once.  Saved per-step tensors (DScat, DGI, DHC,
+// DC, DE, DYH) are the ones the weight-gradient GEMMs and tilegrad_kernel after the loop consume (rnn_decode.cu).
+struct DtbArgs {
+  v2f_decode_params p;
+  const __nv_bfloat16 *Himg, *Vimg, *Htr, *Ptr;     // bf16 tiles left in team_ws by the forward
+  __nv_bfloat16 *DGIb, *DSb, *DHCb;                 // [2][Np,1536], [2][Np,3072] (double-buffered by step parity), [2 mod][Np,512]
+  float* dxpart;                                    // [64, Np] per-CTA partial d x_t
+  unsigned* bar;
+  unsigned long long* stamps;
+  int Np;
+};
+
+constexpr int DTB_KG = 3 * DT_E / 64, DTB_KC = DT_E / 64, DTB_KS = 6 * DT_E / 64;   // K chunks: 24, 8, 48
+constexpr int DTB_W2 = 0, DTB_W4 = DTB_KG, DTB_W6 = DTB_KG + DTB_KC;               // first weight chunk of each product
+constexpr int DTB_WCH = DTB_KG + DTB_KC + DTB_KS;                                   // 80 chunks of 1 KB
+constexpr uint32_t DTB_TMEM_COLS = 64;                                              // D2: 0, D4: 16 / 32, D6: 48
+
+__device__ __forceinline__ void dt_tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+template <int NV>
+__device__ __forceinline__ void dt_block_sum(float (&v)[NV], float* red, int tid) {   // over the 512 consumer threads
+  const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+  for (int i = 0; i < NV; i++) v[i] = warp_sum(v[i]);
+  named_bar_sync(3, DT_CONS);
+  if (lane == 0)
+#pragma unroll
+    for (int i = 0; i < NV; i++) red[warp * NV + i] = v[i];
+  named_bar_sync(3, DT_CONS);
+#pragma unroll
+  for (int i = 0; i < NV; i++) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < DT_CONS / 32; w++) t += red[w * NV + i];
+    v[i] = t;
+  }
+}
+
+__global__ void __launch_bounds__(DT_THREADS, 1)
+decode_team_bwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapG,
+                       const __grid_constant__ CUtensorMap mapS, const __grid_constant__ CUtensorMap mapD,
+                       const __grid_constant__ DtbArgs a) {
+  constexpr int E = DT_E, H = DT_E, ldS = 6 * DT_E;
+  extern __shared__ uint8_t raw[];
+  const v2f_decode_params& p = a.p;
+  const int N = p.N, T = p.T, Li = p.Li, Lt = p.Lt, Wn = p.W, Np = a.Np;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int team = blockIdx.x / DT_CG, c = blockIdx.x % DT_CG;
+  const int n0 = team * DT_NG;
+  const int n_own = n0 + c;
+  const bool own = n_own < N;
+
+  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* Wsm = sm;                                            // [80 chunks][8 rows][128 B]
+  uint8_t* ring = sm + DT_WBYTES;                               // A ring (products) / tile ring (sweep)
+  float* stage = reinterpret_cast<float*>(ring + DT_RING);      // [64][9] dh columns of the team's rows; 16 KB slack before it is read by MMA overrun
+  float* dcv = stage + 64 * 9 + 64;                             // [2][512] d contexts of the own row
+  float* pacc = dcv + 2 * E;                                    // [2 groups][2 modalities][2][512]: (sacc, wacc) partials
+  float* de_all = pacc + 8 * E;                                 // [2][DT_MAXL]
+  float* red = de_all + 2 * DT_MAXL;                            // [16 * 4]
+  uint64_t* bfull = reinterpret_cast<uint64_t*>(red + 64);
+  uint64_t* bempty = bfull + DT_NBS;
+  uint64_t* tfull = bempty + DT_NBS;
+  uint64_t* tempty = tfull + DT_NBS;
+  uint64_t* mma_done = tempty + DT_NBS;
+  uint64_t* wfull = mma_done + 1;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(wfull + 1);
+
+  if (tid == 0) {
+    for (int s = 0; s < DT_NBS; s++) {
+      mbar_init(&bfull[s], 1);
+      mbar_init(&bempty[s], 1);
+      mbar_init(&tfull[s], 1);
+      mbar_init(&tempty[s], DT_GRP / 32);
+    }
+    mbar_init(mma_done, 1);
+    mbar_init(wfull, 1);
+    mbar_fence_init();
+  }
+  if (warp == 17) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)),
+                 "r"(DTB_TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = *tmem_ptr;
+  if (warp == 16 && lane == 0) {                    // the transposed weight slice: 80 boxes of [8 rows x 128 B]
+    mbar_expect_tx(wfull, DT_WBYTES);
+    for (int kc = 0; kc < DTB_WCH; kc++) tma_load_3d(Wsm + kc * 1024, &mapW, wfull, kc * 64, c * 8, 0);
+  }
+
+  const __nv_bfloat16* Vimg_b = a.Vimg;
+  const bool byproj = p.variant == 2;
+  const int mod_mask = p.mod_mask;
+  const unsigned* mask_dev = p.y ? p.tf_mask_dev : nullptr;
+  unsigned* bar = a.bar + team * DT_BARW;
+  unsigned epoch = 0;
+  uint32_t bq = 0, md = 0, tq = 0;
+  const int grp = warp < 8 ? 0 : (warp < 16 ? 1 : warp - 16);
+  const int gt = tid & (DT_GRP - 1), gw = (tid >> 5) & 7;
+  const int cpi = (Li + DT_CH - 1) / DT_CH, cpt = (Lt + DT_CH - 1) / DT_CH, ctot = cpi + cpt;
+  const uint32_t idesc = umma_idesc<0>(16);
+  auto stamp = [&](int t, int k) {
+    if (a.stamps && blockIdx.x == 0 && tid == 0) a.stamps[t * DT_STAMPS + k] = dt_globaltimer();
+  };
+  auto load_a = [&](const CUtensorMap* map, int row0, int nch) {
+    dt_fence_async_global();
+    for (int i = 0; i < nch; i++, bq++) {
+      const uint32_t s = bq % DT_NBS, r = bq / DT_NBS;
+      mbar_wait(&bempty[s], (r & 1) ^ 1);
+      mbar_expect_tx(&bfull[s], DT_BSLOT);
+      tma_load_3d(ring + s * DT_BSLOT, map, &bfull[s], i * 64, row0, 0);
+    }
+  };
+  auto issue = [&](int wch0, uint32_t dcol, int nch, bool last) {
+    for (int i = 0; i < nch; i++, bq++) {
+      const uint32_t s = bq % DT_NBS, r = bq / DT_NBS;
+      mbar_wait(&bfull[s], r & 1);
+      tc_fence_after();
+      const uint64_t ad = umma_desc_sw128(smem_u32(ring + s * DT_BSLOT));
+      const uint64_t bd = umma_desc_sw128(smem_u32(Wsm + (wch0 + i) * 1024));
+#pragma unroll
+      for (int k = 0; k < 4; k++) umma<0>(tmem_d + dcol, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (i | k) ? 1u : 0u);
+      umma_commit(&bempty[s]);
+    }
+    if (last) umma_commit(mma_done);
+  };
+
+  // gate threads: (row nl of the team, hidden unit gu of this CTA); d h lives in a register across the steps
+  const int nl = tid >> 3, gu = tid & 7, ng = n0 + nl, uu = 8 * c + gu;
+  const bool gact = tid < DT_CONS && ng < N;
+  float dhreg = gact ? p.dh[(long long)ng * H + uu] : 0.f;
+  // owner accumulators over all steps (thread = column x of the own row)
+  float dw0 = 0.f, dw1 = 0.f, dw2 = 0.f, dM0 = 0.f, dM1 = 0.f, dHM0 = 0.f, dHM1 = 0.f;
+  if (warp == 17 && lane == 0) mbar_wait(wfull, 0);
+
+  for (int t = T - 1; t >= 0; t--) {
+    const int ts = T - 1 - t;                       // stamp row
+    const int par = t & 1;
+    const float* S = p.S_all + (long long)t * N * ldS;
+    float* DS = p.DScat + (long long)t * N * ldS;
+    float* DHC = p.DHC + (long long)t * N * 2 * E;
+    float* DC = p.DC + (long long)t * N * 2 * E;
+    __nv_bfloat16* DGIb = a.DGIb + (long long)par * Np * 3 * H;
+    __nv_bfloat16* DSb = a.DSb + (long long)par * Np * ldS;
+    stamp(ts, 0);
+    // ================================================================ A: GRU gate backward (own hidden units, the team's rows)
+    float dhdir = 0.f;
+    if (tid < DT_CONS) {
+      float dx = 0.f;
+      if (gact) {
+        const int forced = (t == T - 1) ? 1 : (mask_dev ? (int)((*mask_dev >> t) & 1u) : (int)((p.tf_mask >> t) & 1u));
+        const float dyh = p.dY[(long long)ng * T + t] + (forced ? 0.f : __ldcg(p.dxn + ng));
+        const float* rzn = p.RZN + ((long long)t * N + ng) * 3 * H;
+        const float r = rzn[uu], z = rzn[H + uu], cc = rzn[2 * H + uu];
+        const float hp = p.h_all[((long long)t * N + ng) * H + uu];
+        const float ghn = S[(long long)ng * ldS + 3 * E + 2 * H + uu];
+        const float dhp = dhreg + dyh * p.w_fc[uu];
+        const float dc_ = dhp * (1.f - z);
+        const float dz = dhp * (hp - cc);
+        const float dan = dc_ * (1.f - cc * cc);
+        const float dar = dan * ghn * r * (1.f - r);
+        const float daz = dz * z * (1.f - z);
+        float* dgi = p.DGI + ((long long)t * N + ng) * 3 * H;
+        dgi[uu] = dar;
+        dgi[H + uu] = daz;
+        dgi[2 * H + uu] = dan;
+        float* dgh = DS + (long long)ng * ldS + 3 * E;
+        dgh[uu] = dar;
+        dgh[H + uu] = daz;
+        dgh[2 * H + uu] = dan * r;
+        __nv_bfloat16* gb = DGIb + (long long)ng * 3 * H;
+        gb[uu] = __float2bfloat16_rn(dar);
+        gb[H + uu] = __float2bfloat16_rn(daz);
+        gb[2 * H + uu] = __float2bfloat16_rn(dan);
+        __nv_bfloat16* sb = DSb + (long long)ng * ldS + 3 * E;
+        sb[uu] = __float2bfloat16_rn(dar);
+        sb[H + uu] = __float2bfloat16_rn(daz);
+        sb[2 * H + uu] = __float2bfloat16_rn(dan * r);
+        dhdir = dhp * z;
+        dx = dar * p.w_x[uu] + daz * p.w_x[H + uu] + dan * p.w_x[2 * H + uu];
+        if (c == 0 && gu == 0) p.DYH[(long long)t * N + ng] = dyh;
+      }
+      dx += __shfl_xor_sync(FULL, dx, 1);
+      dx += __shfl_xor_sync(FULL, dx, 2);
+      dx += __shfl_xor_sync(FULL, dx, 4);
+      if (gu == 0 && gact) a.dxpart[(long long)c * Np + ng] = dx;
+    }
+    stamp(ts, 1);
+    dt_team_barrier(bar, c, epoch);
+    stamp(ts, 2);
+    // ================================================================ B: dU[:, 8c..8c+8) = DGI W'[:, 8c..]
+    if (warp == 16) {
+      if (lane == 0) load_a(&mapG, par * Np + n0, DTB_KG);
+      __syncwarp();
+    } else if (warp == 17) {
+      if (lane == 0) issue(DTB_W2, 0, DTB_KG, true);
+      __syncwarp();
+    } else {
+      if (warp < 2) {
+        mbar_wait(mma_done, md & 1);
+        tc_fence_after();
+        uint32_t v[8];
+        dt_tmem_ld8(tmem_d + ((uint32_t)(warp * 32) << 16), v);
+        tc_fence_before();
+        const int n = n0 + warp * 32 + lane;
+        if (n < N) {
+          float* dst = p.dU + (long long)n * E + 8 * c;
+          st4(dst, make_float4(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]), __uint_as_float(v[3])));
+          st4(dst + 4, make_float4(__uint_as_float(v[4]), __uint_as_float(v[5]), __uint_as_float(v[6]), __uint_as_float(v[7])));
+        }
+      }
+      md++;
+    }
+    stamp(ts, 3);
+    dt_team_barrier(bar, c, epoch);
+    stamp(ts, 4);
+    // ================================================================ C: multimodal attention backward of the own row
+    if (own && tid < DT_CONS) {
+      const int n = n_own, b = n / Wn, x = tid;
+      const float* Cc = p.C + ((long long)t * N + n) * 2 * E;
+      const float* HCc = p.HC + ((long long)t * N + n) * 2 * E;
+      float mk[4], hk[4], al[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const bool on = (mod_mask >> k) & 1;
+        mk[k] = !on ? 0.f : ((k & 1) ? Cc[(k >> 1) * E + x] : p.Mst[((long long)b * 2 + (k >> 1)) * E + x]);
+        hk[k] = !on ? 0.f : ((k & 1) ? HCc[(k >> 1) * E + x] : p.HMst[((long long)b * 2 + (k >> 1)) * E + x]);
+        al[k] = p.alpha_mm[((long long)t * N + n) * 4 + k];
+      }
+      const float d = __ldcg(p.dU + (long long)n * E + x);
+      float da[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) da[k] = ((mod_mask >> k) & 1) ? d * (byproj ? hk[k] : mk[k]) : 0.f;
+      dt_block_sum<4>(da, red, tid);
+      float dot = 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; k++) dot = fmaf(al[k], da[k], dot);
+      const float sx = S[(long long)n * ldS + 2 * E + x], wx = p.w_att[2 * E + x];
+      float ds = 0.f, dw = 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        float dhm = 0.f, dm = 0.f;
+        if ((mod_mask >> k) & 1) {
+          const float de = al[k] * (da[k] - dot);
+          const float q = tanh_acc(hk[k] + sx);
+          const float dpre = de * wx * (1.f - q * q);
+          ds += dpre;
+          dw = fmaf(de, q, dw);
+          dhm = dpre + (byproj ? al[k] * d : 0.f);
+          dm = byproj ? d : d * (1.f + al[k]);
+        }
+        if (k & 1) {
+          const long long dyn = ((long long)n * 2 + (k >> 1)) * E + x;
+          DHC[dyn] = dhm;
+          DC[dyn] = dm;
+          a.DHCb[((long long)(k >> 1) * Np + n) * E + x] = __float2bfloat16_rn(dhm);
+        } else if (k == 0) {
+          dHM0 += dhm;
+          dM0 += dm;
+        } else {
+          dHM1 += dhm;
+          dM1 += dm;
+        }
+      }
+      DS[(long long)n * ldS + 2 * E + x] = ds;
+      DSb[(long long)n * ldS + 2 * E + x] = __float2bfloat16_rn(ds);
+      dw2 += dw;
+      if (warp == 15) {       // d x_t of the own row = sum of the per-CTA partials (consumed by phase A of step t-1)
+        float v = __ldcg(a.dxpart + (long long)lane * Np + n) + __ldcg(a.dxpart + (long long)(lane + 32) * Np + n);
+        v = warp_sum(v);
+        if (lane == 0) p.dxn[n] = v;
+      }
+    }
+    stamp(ts, 5);
+    dt_team_barrier(bar, c, epoch);
+    stamp(ts, 6);
+    // ================================================================ D: dC[:, :, 8c..8c+8) += DHC We_mm[:, 8c..]
+    if (warp == 16) {
+      if (lane == 0) {
+        load_a(&mapD, n0, DTB_KC);
+        load_a(&mapD, Np + n0, DTB_KC);
+      }
+      __syncwarp();
+    } else if (warp == 17) {
+      if (lane == 0) {
+        issue(DTB_W4, 16, DTB_KC, false);
+        issue(DTB_W4, 32, DTB_KC, true);
+      }
+      __syncwarp();
+    } else {
+      if (warp < 2) {
+        mbar_wait(mma_done, md & 1);
+        tc_fence_after();
+        const int n = n0 + warp * 32 + lane;
+#pragma unroll
+        for (int mod = 0; mod < 2; mod++) {
+          uint32_t v[8];
+          dt_tmem_ld8(tmem_d + ((uint32_t)(warp * 32) << 16) + 16u * (mod + 1), v);
+          if (n < N) {
+            float* dst = DC + ((long long)n * 2 + mod) * E + 8 * c;
+            float4 o0 = __ldcg(reinterpret_cast<const float4*>(dst)), o1 = __ldcg(reinterpret_cast<const float4*>(dst + 4));
+            o0.x += __uint_as_float(v[0]);
+            o0.y += __uint_as_float(v[1]);
+            o0.z += __uint_as_float(v[2]);
+            o0.w += __uint_as_float(v[3]);
+            o1.x += __uint_as_float(v[4]);
+            o1.y += __uint_as_float(v[5]);
+            o1.z += __uint_as_float(v[6]);
+            o1.w += __uint_as_float(v[7]);
+            st4(dst, o0);
+            st4(dst + 4, o1);
+          }
+        }
+        tc_fence_before();
+      }
+      md++;
+    }
+    stamp(ts, 7);
+    dt_team_barrier(bar, c, epoch);
+    stamp(ts, 8);
+    // ================================================================ E: attention backward of the own row (two passes over the bf16 tiles)
+    if (own) {
+      const int n = n_own, b = n / Wn;
+      const float* al_img = p.alpha_img + ((long long)t * N + n) * Li;
+      const float* al_tr = p.alpha_tr + ((long long)t * N + n) * Lt;
+      if (warp == 16) {
+        if (lane == 0) {
+          uint32_t q = tq;
+          for (int pass = 0; pass < 2; pass++)
+            for (int cc0 = 0; cc0 < ctot; cc0++, q++) {
+              const int mod = cc0 >= cpi, cc = mod ? cc0 - cpi : cc0;
+              const int L = mod ? Lt : Li, j0 = cc * DT_CH, nj = min(DT_CH, L - j0);
+              const long long off = ((long long)b * L + j0) * E;
+              const uint32_t bytes = (uint32_t)nj * E * 2u;
+              const uint32_t sl = q % DT_NBS, r = q / DT_NBS;
+              const __nv_bfloat16* src = pass == 0 ? (mod ? a.Ptr : Vimg_b) : (mod ? a.Htr : a.Himg);
+              mbar_wait(&tempty[sl], (r & 1) ^ 1);
+              mbar_expect_tx(&tfull[sl], bytes);
+              bulk_g2s(ring + sl * DT_TSLOT, src + off, bytes, &tfull[sl]);
+            }
+        }
+        __syncwarp();
+      } else if (warp < 16) {
+        const int x = tid;
+        // d contexts of the own row (complete after phase D) and dot_m = dc_m . (c_m - b_tl)
+        float dots[2];
+        {
+          const float* Cc = p.C + ((long long)t * N + n) * 2 * E;
+#pragma unroll
+          for (int mod = 0; mod < 2; mod++) {
+            const float dcx = __ldcg(DC + ((long long)n * 2 + mod) * E + x);
+            dcv[mod * E + x] = dcx;
+            dots[mod] = dcx * (Cc[mod * E + x] - (mod ? p.b_tl[x] : 0.f));
+          }
+          dt_block_sum<2>(dots, red, tid);     // (its barriers also publish dcv)
+        }
+        // ---- pass 1 (V tiles): d alpha_j = V_j . dc ; de_j = alpha_j (d alpha_j - dot)
+        {
+          float4 dreg[4];
+          int cur_mod = -1;
+          for (int cc0 = grp; cc0 < ctot; cc0 += 2) {
+            const int mod = cc0 >= cpi, cc = mod ? cc0 - cpi : cc0;
+            const int L = mod ? Lt : Li, j0 = cc * DT_CH, nj = min(DT_CH, L - j0);
+            if (mod != cur_mod) {
+              cur_mod = mod;
+#pragma unroll
+              for (int k = 0; k < 2; k++) {
+                dreg[2 * k] = ld4(dcv + mod * E + 8 * lane + 256 * k);
+                dreg[2 * k + 1] = ld4(dcv + mod * E + 8 * lane + 256 * k + 4);
+              }
+            }
+            const uint32_t q = tq + (uint32_t)cc0, sl = q % DT_NBS, r = q / DT_NBS;
+            const float alv = gw < nj ? (mod ? al_tr : al_img)[j0 + gw] : 0.f;
+            mbar_wait(&tfull[sl], r & 1);
+            if (gw < nj) {
+              const uint8_t* vp = ring + sl * DT_TSLOT + gw * (E * 2);
+              float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+              for (int k = 0; k < 2; k++) {
+                const uint4 vv = *reinterpret_cast<const uint4*>(vp + (8 * lane + 256 * k) * 2);
+                const float2 v0 = dt_bf2(vv.x), v1 = dt_bf2(vv.y), v2 = dt_bf2(vv.z), v3 = dt_bf2(vv.w);
+                const float4 d0 = dreg[2 * k], d1 = dreg[2 * k + 1];
+                acc0 = fmaf(v0.x, d0.x, acc0);
+                acc1 = fmaf(v0.y, d0.y, acc1);
+                acc0 = fmaf(v1.x, d0.z, acc0);
+                acc1 = fmaf(v1.y, d0.w, acc1);
+                acc0 = fmaf(v2.x, d1.x, acc0);
+                acc1 = fmaf(v2.y, d1.y, acc1);
+                acc0 = fmaf(v3.x, d1.z, acc0);
+                acc1 = fmaf(v3.y, d1.w, acc1);
+              }
+              const float de = alv * (warp_sum(acc0 + acc1) - (mod ? dots[1] : dots[0]));
+              if (lane == 0) {
+                de_all[mod * DT_MAXL + j0 + gw] = de;
+                (mod ? p.DE_tr + ((long long)t * N + n) * Lt : p.DE_img + ((long long)t * N + n) * Li)[j0 + gw] = de;
+              }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[sl]);
+          }
+        }
+        named_bar_sync(3, DT_CONS);
+        // ---- pass 2 (H tiles): ds[x] = w[x] sum_j de_j (1 - q^2), dw[x] += sum_j de_j q, q = tanh(H_j[x] + s[x])
+        {
+          float sa_i0 = 0.f, sa_i1 = 0.f, wa_i0 = 0.f, wa_i1 = 0.f, sa_t0 = 0.f, sa_t1 = 0.f, wa_t0 = 0.f, wa_t1 = 0.f;
+          float s0 = 0.f, s1 = 0.f;
+          int cur_mod = -1;
+          for (int cc0 = grp; cc0 < ctot; cc0 += 2) {
+            const int mod = cc0 >= cpi, cc = mod ? cc0 - cpi : cc0;
+            const int L = mod ? Lt : Li, j0 = cc * DT_CH, nj = min(DT_CH, L - j0);
+            if (mod != cur_mod) {
+              cur_mod = mod;
+              const float2 sv = *reinterpret_cast<const float2*>(S + (long long)n * ldS + mod * E + 2 * gt);
+              s0 = sv.x;
+              s1 = sv.y;
+            }
+            const uint32_t q = tq + (uint32_t)(ctot + cc0), sl = q % DT_NBS, r = q / DT_NBS;
+            const float* dep = de_all + mod * DT_MAXL + j0;
+            mbar_wait(&tfull[sl], r & 1);
+            const uint8_t* hp = ring + sl * DT_TSLOT + gt * 4;
+            float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+            for (int j = 0; j < nj; j++) {
+              const float2 hv = dt_bf2(*reinterpret_cast<const uint32_t*>(hp + j * (E * 2)));
+              const float de = dep[j];
+              const float q0 = tanh_fast<true>(hv.x + s0), q1 = tanh_fast<true>(hv.y + s1);
+              a0 = fmaf(de, fmaf(-q0, q0, 1.f), a0);
+              a1 = fmaf(de, fmaf(-q1, q1, 1.f), a1);
+              b0 = fmaf(de, q0, b0);
+              b1 = fmaf(de, q1, b1);
+            }
+            if (mod) {
+              sa_t0 += a0;
+              sa_t1 += a1;
+              wa_t0 += b0;
+              wa_t1 += b1;
+            } else {
+              sa_i0 += a0;
+              sa_i1 += a1;
+              wa_i0 += b0;
+              wa_i1 += b1;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[sl]);
+          }
+          float* pp = pacc + grp * 4 * E;         // [mod][sacc | wacc][512]
+          *reinterpret_cast<float2*>(pp + 0 * E + 2 * gt) = make_float2(sa_i0, sa_i1);
+          *reinterpret_cast<float2*>(pp + 1 * E + 2 * gt) = make_float2(wa_i0, wa_i1);
+          *reinterpret_cast<float2*>(pp + 2 * E + 2 * gt) = make_float2(sa_t0, sa_t1);
+          *reinterpret_cast<float2*>(pp + 3 * E + 2 * gt) = make_float2(wa_t0, wa_t1);
+        }
+        named_bar_sync(3, DT_CONS);
+        {
+#pragma unroll
+          for (int mod = 0; mod < 2; mod++) {
+            const float sacc = pacc[(2 * mod) * E + x] + pacc[(4 + 2 * mod) * E + x];
+            const float wacc = pacc[(2 * mod + 1) * E + x] + pacc[(4 + 2 * mod + 1) * E + x];
+            const float ds = sacc * p.w_att[mod * E + x];
+            DS[(long long)n * ldS + mod * E + x] = ds;
+            DSb[(long long)n * ldS + mod * E + x] = __float2bfloat16_rn(ds);
+            if (mod) dw1 += wacc;
+            else dw0 += wacc;
+          }
+        }
+      }
+      tq += 2u * (uint32_t)ctot;
+    }
+    stamp(ts, 9);
+    dt_team_barrier(bar, c, epoch);
+    stamp(ts, 10);
+    // ================================================================ F: dh[:, 8c..8c+8) = z-path + DS Wcat[:, 8c..]
+    if (warp == 16) {
+      if (lane == 0) load_a(&mapS, par * Np + n0, DTB_KS);
+      __syncwarp();
+    } else if (warp == 17) {
+      if (lane == 0) issue(DTB_W6, 48, DTB_KS, true);
+      __syncwarp();
+    } else {
+      if (warp < 2) {
+        mbar_wait(mma_done, md & 1);
+        tc_fence_after();
+        uint32_t v[8];
+        dt_tmem_ld8(tmem_d + ((uint32_t)(warp * 32) << 16) + 48u, v);
+        tc_fence_before();
+        const int r = warp * 32 + lane;
+#pragma unroll
+        for (int i = 0; i < 8; i++) stage[r * 9 + i] = __uint_as_float(v[i]);
+      }
+      md++;
+      named_bar_sync(3, DT_CONS);
+      dhreg = dhdir + stage[nl * 9 + gu];
+      named_bar_sync(3, DT_CONS);          // stage is rewritten by the next step's phase F only, but keep the readers together
+    }
+    stamp(ts, 11);
+  }
+  // ------------------------------------------------------------------ outputs that accumulate over the steps
+  if (gact) p.dh[(long long)ng * H + uu] = dhreg;
+  if (own && tid < DT_CONS) {
+    const int n = n_own, x = tid;
+    p.dw_acc[((long long)n * 3 + 0) * E + x] = dw0;
+    p.dw_acc[((long long)n * 3 + 1) * E + x] = dw1;
+    p.dw_acc[((long long)n * 3 + 2) * E + x] = dw2;
+    p.dMst_acc[((long long)n * 2 + 0) * E + x] = dM0;
+    p.dMst_acc[((long long)n * 2 + 1) * E + x] = dM1;
+    p.dHMst_acc[((long long)n * 2 + 0) * E + x] = dHM0;
+    p.dHMst_acc[((long long)n * 2 + 1) * E + x] = dHM1;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 17) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(DTB_TMEM_COLS) : "memory");
+  }
+}
+
+// the per-CTA slices of the transposed weights, bf16, row-major [64 CTAs x 8 rows][5120]: row 8c+i holds column 8c+i of
+// W' (k < 1536), of We_mm (k < 2048) and of Wcat (rest).  32 x 32 tiles through shared memory: coalesced both ways.
+__global__ void dt_pack_weights_t_kernel(const float* __restrict__ Wp, const float* __restrict__ We_mm,
+                                         const float* __restrict__ Wcat, __nv_bfloat16* __restrict__ out) {
+  constexpr int E = DT_E, KT = 10 * DT_E;
+  __shared__ float tile[32][33];
+  const int k0 = blockIdx.x * 32, x0 = blockIdx.y * 32;      // source rows k0.., source columns x0..
+  const float* src = k0 < 3 * E ? Wp + (long long)k0 * E : (k0 < 4 * E ? We_mm + (long long)(k0 - 3 * E) * E : Wcat + (long long)(k0 - 4 * E) * E);
+  for (int i = threadIdx.y; i < 32; i += 8) tile[i][threadIdx.x] = src[(long long)i * E + x0 + threadIdx.x];
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) out[(long long)(x0 + i) * KT + k0 + threadIdx.x] = __float2bfloat16_rn(tile[threadIdx.x][i]);
+}
+
+static size_t dtb_smem() {
+  return 1024 + (size_t)DT_WBYTES + DT_RING + sizeof(float) * (64 * 9 + 64 + 2 * DT_E + 8 * DT_E + 2 * DT_MAXL + 64) +
+         8 * (4 * DT_NBS + 2) + 16;
+}
+
+struct DtbLayout {
+  long long wt, dgib, dsb, dhcb, dxpart, bar, stamps, end;   // float offsets into the backward scratch (p->ws)
+};
+static DtbLayout dtb_layout(int N, int T) {
+  const long long Np = (long long)((N + DT_NG - 1) / DT_NG) * DT_NG;
+  DtbLayout l;
+  long long o = 0;
+  auto take = [&](long long floats) { const long long at = o; o += (floats + 255) / 256 * 256; return at; };
+  l.wt = take((long long)DT_E * 10 * DT_E / 2);
+  l.dgib = take(2 * Np * 3 * DT_E / 2);
+  l.dsb = take(2 * Np * 6 * DT_E / 2);
+  l.dhcb = take(2 * Np * DT_E / 2);
+  l.dxpart = take((long long)DT_CG * Np);
+  l.bar = take((long long)DT_MAXTEAMS * DT_BARW);
+  l.stamps = take(2LL * T * DT_STAMPS);
+  l.end = o;
+  return l;
+}
+long long decode_team_bwd_ws_floats(int N, int T) { return dtb_layout(N, T).end; }
+
+static bool g_dtb_enabled = true;
+
+// The loop part of v2f_decode_bwd (rnn_decode.cu) as one launch; V2F_ERR_UNSUPPORTED outside the envelope.  Needs the
+// forward to have run through decode_team_fwd (the bf16 tiles and W' are taken from team_ws / persist_ws).
+int decode_team_bwd(const v2f_decode_params* p, float* bws, long long bws_floats, cudaStream_t s) {
+  if (!g_dtb_enabled || !dt_supported(p) || !bws) return V2F_ERR_UNSUPPORTED;
+  constexpr int E = DT_E, H = DT_E;
+  const int N = p->N, B = p->B, T = p->T, Li = p->Li, Lt = p->Lt;
+  const DtbLayout lb = dtb_layout(N, T);
+  if (bws_floats < lb.end) return V2F_ERR_UNSUPPORTED;
+  const int teams = (N + DT_NG - 1) / DT_NG, Np = teams * DT_NG;
+  const DtLayout l = dt_layout(N, B, T, Li, Lt);
+  const float* Wp = p->persist_ws;                       // W' = W_ihc W_me, left there by the forward
+  __nv_bfloat16* wt = reinterpret_cast<__nv_bfloat16*>(bws + lb.wt);
+  dt_pack_weights_t_kernel<<<dim3(10 * E / 32, E / 32), dim3(32, 8), 0, s>>>(Wp, p->We_mm, p->Wcat, wt);
+  V2F_CHECK_LAUNCH();
+  const __nv_bfloat16* tb = reinterpret_cast<const __nv_bfloat16*>(p->team_ws + l.tiles);
+  const long long ni = (long long)B * Li * E, nt = (long long)B * Lt * E;
+  DtbArgs a;
+  a.p = *p;
+  a.Himg = tb;
+  a.Vimg = p->Vimg != p->Himg ? tb + ni : tb;
+  a.Htr = tb + 2 * ni;
+  a.Ptr = tb + 2 * ni + nt;
+  a.DGIb = reinterpret_cast<__nv_bfloat16*>(bws + lb.dgib);
+  a.DSb = reinterpret_cast<__nv_bfloat16*>(bws + lb.dsb);
+  a.DHCb = reinterpret_cast<__nv_bfloat16*>(bws + lb.dhcb);
+  a.dxpart = bws + lb.dxpart;
+  a.bar = reinterpret_cast<unsigned*>(bws + lb.bar);
+  a.stamps = g_dt_stamps ? reinterpret_cast<unsigned long long*>(bws + lb.stamps) : nullptr;
+  a.Np = Np;
+  cudaMemsetAsync(bws + lb.dgib, 0, sizeof(float) * (size_t)(lb.dxpart - lb.dgib), s);   // pad rows of the A operands
+  cudaMemsetAsync(a.bar, 0, sizeof(unsigned) * DT_MAXTEAMS * DT_BARW, s);
+  CUtensorMap mW, mG, mS, mD;
+  V2F_TRY(tc_make_map(&mW, 0, wt, E, 10 * E, 10 * E, 1, 0, 8));
+  V2F_TRY(tc_make_map(&mG, 0, a.DGIb, 2LL * Np, 3 * H, 3 * H, 1, 0, DT_NG));
+  V2F_TRY(tc_make_map(&mS, 0, a.DSb, 2LL * Np, 6 * E, 6 * E, 1, 0, DT_NG));
+  V2F_TRY(tc_make_map(&mD, 0, a.DHCb, 2LL * Np, E, E, 1, 0, DT_NG));
+  static bool attr = false;
+  const size_t smem = dtb_smem();
+  if (!attr) {
+    if (cudaFuncSetAttribute(decode_team_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+      return V2F_ERR_LAUNCH;
+    attr = true;
+  }
+  void* params[] = {(void*)&mW, (void*)&mG, (void*)&mS, (void*)&mD, (void*)&a};
+  prof_begin(V2F_K_DECODE_PERSIST_BWD, s);
+  const cudaError_t e = cudaLaunchCooperativeKernel((void*)decode_team_bwd_kernel, dim3(teams * DT_CG), dim3(DT_THREADS),
+                                                    params, smem, s);
+  prof_end(V2F_K_DECODE_PERSIST_BWD, s);
+  if (e == cudaErrorCooperativeLaunchTooLarge || e == cudaErrorLaunchOutOfResources) {
+    cudaGetLastError();
+    return V2F_ERR_UNSUPPORTED;
+  }
+  if (e != cudaSuccess) return V2F_ERR_LAUNCH;
+  ++g_v2f_launches;
+  return V2F_OK;
+}
+
 }  // namespace v2f
 
 extern "C" long long v2f_decode_team_ws_floats(int N, int B, int T, int Li, int Lt) {
@@ -803,6 +1433,14 @@ extern "C" long long v2f_decode_team_ws_floats(int N, int B, int T, int Li, int 
 extern "C" int v2f_decode_team_enable(int on) {
   v2f::g_dt_enabled = on != 0;
   return V2F_OK;
+}
+extern "C" int v2f_decode_team_bwd_enable(int on) {
+  v2f::g_dtb_enabled = on != 0;
+  return V2F_OK;
+}
+extern "C" long long v2f_decode_team_bwd_ws_floats(int N, int T) {
+  if (N <= 0 || T <= 0) return 0;
+  return v2f::decode_team_bwd_ws_floats(N, T);
 }
 extern "C" int v2f_decode_team_stamps_enable(int on) {
   v2f::g_dt_stamps = on != 0;

@@ -617,6 +617,7 @@ using namespace v2f;
 namespace v2f {
 int decode_persist_fwd(const v2f_decode_params* p, cudaStream_t s);   // decode_persist.cu
 int decode_team_fwd(const v2f_decode_params* p, cudaStream_t s);      // decode_team.cu
+int decode_team_bwd(const v2f_decode_params* p, float* bws, long long bws_floats, cudaStream_t s);
 }
 
 #define NT(M, N, K, A, lda, B, ldb, C, ldc, bias, beta) V2F_TRY(gemm_nt(gx, M, N, K, A, lda, B, ldb, C, ldc, bias, beta))
@@ -717,7 +718,13 @@ extern "C" int v2f_decode_bwd(const v2f_decode_params* p, void* st) {
   const size_t smem = attn_smem(E, true);
   if (smem > 48 * 1024)
     cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  for (int t = T - 1; t >= 0; t--) {
+  // the whole BPTT loop as one persistent cooperative launch when the forward ran on the row-team kernel
+  // (decode_team.cu); dCTX = DGI W_ihc for all T*N rows is then one product after the loop
+  int team_rc = (gru && tc) ? decode_team_bwd(p, p->ws, p->ws_floats, s) : V2F_ERR_UNSUPPORTED;
+  if (team_rc != V2F_OK && team_rc != V2F_ERR_UNSUPPORTED) return team_rc;
+  if (team_rc == V2F_OK)
+    NN(T * N, E, 3 * H, p->DGI, 3 * H, p->W_ihc, E, W_ihcT, 3 * H, p->DCTX, E, 0.f);
+  for (int t = T - 1; t >= 0 && team_rc != V2F_OK; t--) {
     const float* h = p->h_all + (long long)t * N * H;
     const float* S = p->S_all + (long long)t * N * ldS;
     float* DS = p->DScat + (long long)t * N * ldS;

@@ -505,6 +505,11 @@ def persist_phase_times():
         work = sum(int(st[t, 2 * k + 1]) - int(st[t, 2 * k]) for t in range(T)) / T / 1e3
         wait = sum(int(st[t, 2 * k + 2]) - int(st[t, 2 * k + 1]) for t in range(T)) / T / 1e3
         out[name] = (work, wait)
+    if team:      # inside P2 (CTA 0, thread 0): pass 1 | wait for the other warps | softmax | pass 2 | tail (combine + writes)
+        marks = [2, 11, 12, 13, 14, 3]
+        names2 = ["P2.a energies pass", "P2.b barrier", "P2.c softmax", "P2.d context pass", "P2.e combine"]
+        for (a, b), name in zip(zip(marks[:-1], marks[1:]), names2):
+            out[name] = (sum(int(st[t, b]) - int(st[t, a]) for t in range(T)) / T / 1e3, 0.0)
     return out
 
 
@@ -617,6 +622,9 @@ class _Decode(torch.autograd.Function):
             ldS = 3 * E + G
             tn4, rows = (T * N + 3) // 4 * 4, (2 * T * N + 3) // 4 * 4
             ws_n = max((ldS + H) * tn4, (3 * H + E) * tn4, 2 * E * rows) + 64
+            if "team_ws" in keep:      # scratch of the row-team persistent backward (csrc/decode_team.cu)
+                ws_n = max(ws_n, _lib.lib().v2f_decode_team_bwd_ws_floats(N, T))
+                p.team_ws_floats = keep["team_ws"].numel()
             g.update(WcatT=_f32(H, ldS, device=dev), W_ihcT=_f32(E, H3, device=dev), W_meT=_f32(E, E, device=dev),
                      We_mmT=_f32(E, E, device=dev), ws=_f32(ws_n, device=dev))
             p.ws_floats = ws_n
