@@ -274,6 +274,17 @@ int v2f_bn1d_fwd(int B, int D, const float* x, const float* gamma, const float* 
 int v2f_bn1d_bwd(int B, int D, const float* x, const float* dy, const float* gamma,
                  const float* save_mean, const float* save_rstd, int training, float* dx,
                  float* dgamma, float* dbeta, void* stream);
+/* The same under batch sharding (data parallelism; the reference normalises over the WHOLE batch): per-channel
+ * sums of the local rows, sums[2,D] doubles = (sum x, sum x^2) resp. (sum dy, sum dy*xhat); the caller all-reduces
+ * them (NCCL, SUM) between the stats and the apply call and passes the global row count Btot. */
+int v2f_bn1d_stats(int B, int D, const float* x, double* sums, void* stream);
+int v2f_bn1d_apply(int B, int D, const float* x, const float* gamma, const float* beta, const double* sums,
+                   double Btot, float* run_mean, float* run_var, float momentum, float eps, float* y,
+                   float* save_mean, float* save_rstd, void* stream);
+int v2f_bn1d_bwd_stats(int B, int D, const float* x, const float* dy, const float* save_mean,
+                       const float* save_rstd, double* sums, float* dgamma, float* dbeta, void* stream);
+int v2f_bn1d_bwd_apply(int B, int D, const float* x, const float* dy, const float* gamma, const float* save_mean,
+                       const float* save_rstd, const double* sums, double Btot, float* dx, void* stream);
 /* Sigmoid gates: mode 0: out = x*sigmoid(g) (models/Proposed_model.py:217, _v2.py:598,682,
  * _v3.py:222-227); mode 1: out = x + x*sigmoid(g) (Proposed_model.py:154, _v2.py:635, _v4.py:186-192). */
 int v2f_gate_fwd(long long n, const float* x, const float* g, int mode, float* out, void* stream);

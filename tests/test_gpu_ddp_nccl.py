@@ -77,6 +77,84 @@ def _worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
+def _worker_gtm(rank, world, port, q):
+    """GTM_Visuelle2 (BatchNorm1d with batch statistics in its fusion network, GTM_Visuelle2.py:158) and
+    Proposed_model_v3: with ddp.sync_batchnorm1d, 2 ranks x 8 items == the 1-GPU batch of 16 items."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+    import visuelle2_multimodal_fusion_b200.synth as synth
+    from helpers import _restore_gtm_trunk, gtm_product_ctor
+    from oracle.refshim import zero_dropout
+    from visuelle2_multimodal_fusion_b200.ddp import GradReducer, shard_batch, sync_batchnorm1d
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(f"cuda:{rank}"))
+    try:
+        cat_d, col_d, fab_d = synth.label_dicts()
+        results = {}
+        for variant in ("gtm", "v3"):
+            torch.manual_seed(7)
+            try:
+                m = gtm_product_ctor(variant)(32, 64, 12, 4, 1, 1, 1, cat_d, col_d, fab_d, synth.STORE_N, 52, 3, 0)
+            finally:
+                _restore_gtm_trunk()
+            m = zero_dropout(m.cuda()).train()
+            B = 16
+            data, feat = synth.make_batch(B, demand=True, seed=5, feat_hw=3)
+            data = (data[0][:, :12].contiguous(),) + data[1:]
+            full = (tuple(t.cuda() for t in data), feat.cuda())
+            red = GradReducer(m, hooks=True)
+            state0 = {k: v.clone() for k, v in m.state_dict().items()}
+            # 1-GPU global batch, per-rank statistics == global statistics
+            loss = m.training_step(full, 0)
+            loss.backward()
+            red.finish()                                        # averages identical gradients: no-op
+            ref = {k: p.grad.detach().clone() for k, p in m.named_parameters() if p.grad is not None}
+            ref_stats = {k: v.clone() for k, v in m.state_dict().items() if "running" in k}
+            m.load_state_dict(state0)
+            for p in m.parameters():
+                p.grad = None
+            assert sync_batchnorm1d(m) >= 1
+            loss = m.training_step(shard_batch(full, rank, world), 0)
+            loss.backward()
+            red.finish()
+            worst = 0.0
+            for k, p in m.named_parameters():
+                if k not in ref:
+                    continue
+                d, sc = float((p.grad - ref[k]).abs().max()), float(ref[k].abs().max())
+                worst = max(worst, (d - 2e-7) / max(sc, 1e-6))
+            for k, v in m.state_dict().items():
+                if "running" in k:
+                    worst = max(worst, float((v - ref_stats[k]).abs().max()) / max(float(ref_stats[k].abs().max()), 1e-6))
+            results[variant] = worst
+            red.remove()
+        q.put((rank, results))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_gpu_sync_batchnorm1d_equals_global_batch():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() + 7) % 2000
+    procs = [ctx.Process(target=_worker_gtm, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = [q.get(timeout=600) for _ in procs]
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    for rank, res in out:
+        print(rank, res)
+        for variant, worst in res.items():
+            assert worst < 1e-4, (rank, variant, worst)
+
+
 def test_two_gpu_sharded_gradients_equal_global_batch_gradients():
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")

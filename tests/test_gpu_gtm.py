@@ -274,3 +274,50 @@ def test_cross_attention_pieces():
     assert _rel(o, ref) < 2e-5
     for a, b in zip(mine, [x.grad, mem.grad, mha.in_proj_weight.grad, mha.in_proj_bias.grad]):
         assert _rel(a, b) < 5e-5
+
+
+def test_sharded_batchnorm1d_kernels_equal_the_single_pass_kernel():
+    """stats -> (all-reduce) -> apply and its backward, fed the sums of two half-batches, equal v2f_bn1d_fwd/bwd on the
+    whole batch: the arithmetic of ddp.sync_batchnorm1d without the collective."""
+    from visuelle2_multimodal_fusion_b200 import _lib
+    from visuelle2_multimodal_fusion_b200._lib import check, ptr, stream
+    L = _lib.lib()
+    torch.manual_seed(2)
+    B, D = 48, 192
+    x = torch.randn(B, D, device="cuda") * 1.7 + 0.3
+    dy = torch.randn(B, D, device="cuda")
+    g, b = torch.rand(D, device="cuda") + 0.5, torch.randn(D, device="cuda")
+    rm, rv = torch.zeros(D, device="cuda"), torch.ones(D, device="cuda")
+    y0, m0, r0 = torch.empty_like(x), torch.empty(D, device="cuda"), torch.empty(D, device="cuda")
+    check(L.v2f_bn1d_fwd(B, D, ptr(x), ptr(g), ptr(b), ptr(rm), ptr(rv), 1, 0.1, 1e-5, ptr(y0), ptr(m0), ptr(r0), stream()), "fwd")
+    dx0, dg0, db0 = torch.empty_like(x), torch.empty(D, device="cuda"), torch.empty(D, device="cuda")
+    check(L.v2f_bn1d_bwd(B, D, ptr(x), ptr(dy), ptr(g), ptr(m0), ptr(r0), 1, ptr(dx0), ptr(dg0), ptr(db0), stream()), "bwd")
+    halves = [(x[:24].contiguous(), dy[:24].contiguous()), (x[24:].contiguous(), dy[24:].contiguous())]
+    sums = torch.zeros(2, D, device="cuda", dtype=torch.float64)
+    for xs, _ in halves:
+        part = torch.empty(2, D, device="cuda", dtype=torch.float64)
+        check(L.v2f_bn1d_stats(24, D, ptr(xs), part.data_ptr(), stream()), "stats")
+        sums += part
+    ys, bs, dgs, dbs = [], torch.zeros(2, D, device="cuda", dtype=torch.float64), 0, 0
+    saves = []
+    for xs, dys in halves:
+        rm1, rv1 = torch.zeros(D, device="cuda"), torch.ones(D, device="cuda")
+        y, m, r = torch.empty_like(xs), torch.empty(D, device="cuda"), torch.empty(D, device="cuda")
+        check(L.v2f_bn1d_apply(24, D, ptr(xs), ptr(g), ptr(b), sums.data_ptr(), float(B), ptr(rm1), ptr(rv1), 0.1, 1e-5,
+                               ptr(y), ptr(m), ptr(r), stream()), "apply")
+        ys.append(y)
+        saves.append((m, r))
+        part = torch.empty(2, D, device="cuda", dtype=torch.float64)
+        dg, db = torch.empty(D, device="cuda"), torch.empty(D, device="cuda")
+        check(L.v2f_bn1d_bwd_stats(24, D, ptr(xs), ptr(dys), ptr(m), ptr(r), part.data_ptr(), ptr(dg), ptr(db), stream()), "bs")
+        bs += part
+        dgs, dbs = dgs + dg, dbs + db
+    dxs = []
+    for (xs, dys), (m, r) in zip(halves, saves):
+        dx = torch.empty_like(xs)
+        check(L.v2f_bn1d_bwd_apply(24, D, ptr(xs), ptr(dys), ptr(g), ptr(m), ptr(r), bs.data_ptr(), float(B), ptr(dx), stream()), "ba")
+        dxs.append(dx)
+    rel = _rel
+    assert rel(torch.cat(ys), y0) < 2e-6 and rel(torch.cat(dxs), dx0) < 1e-5
+    assert rel(dgs, dg0) < 1e-5 and rel(dbs, db0) < 1e-5
+    assert rel(rm1, rm) < 1e-6 and rel(rv1, rv) < 1e-5

@@ -90,6 +90,12 @@ def _declare(lib):
     lib.v2f_decode_persist_ws_floats.restype = c_ll
     lib.v2f_decode_persist_stamps_offset.argtypes = [c_int, c_int, c_int]
     lib.v2f_decode_persist_stamps_offset.restype = c_ll
+    c_double = ctypes.c_double
+    lib.v2f_bn1d_stats.argtypes = [c_int, c_int, c_vp, c_vp, c_vp]
+    lib.v2f_bn1d_apply.argtypes = [c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_double, c_vp, c_vp, c_float, c_float, c_vp,
+                                   c_vp, c_vp, c_vp]
+    lib.v2f_bn1d_bwd_stats.argtypes = [c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]
+    lib.v2f_bn1d_bwd_apply.argtypes = [c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_double, c_vp, c_vp]
     lib.v2f_decode_team_ws_floats.argtypes = [c_int] * 5
     lib.v2f_decode_team_ws_floats.restype = c_ll
     lib.v2f_decode_team_stamps_offset.argtypes = [c_int] * 5

@@ -37,6 +37,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
   __trap();
 }
+// Warp-collective wait: lane 0 polls, the other lanes park at the warp barrier (512 threads spinning on try_wait keep
+// the shared-memory synchronisation unit busy while TMA is trying to complete transactions on the same barriers);
+// __syncwarp orders the lanes' later shared-memory reads after lane 0's acquire.
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity) {
+  if ((threadIdx.x & 31) == 0) mbar_wait(bar, parity);
+  __syncwarp();
+}
 // 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier (UBLKCP in SASS)
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile(

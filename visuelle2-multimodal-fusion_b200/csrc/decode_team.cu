@@ -37,7 +37,7 @@ constexpr int DT_NG = 64;                    // rows per team = MMA N
 constexpr int DT_CG = 64;                    // CTAs per team
 constexpr int DT_CONS = 512;                 // 16 consumer warps = 2 groups of 8
 constexpr int DT_GRP = 256;
-constexpr int DT_THREADS = DT_CONS + 64;     // + warp 16 (TMA / bulk-copy producer of group 0), warp 17 (MMA issuer / producer of group 1)
+constexpr int DT_THREADS = DT_CONS + 64;     // + warp 16 (weight TMA, bulk-copy producer of the sweep), warp 17 (TMEM owner; backward: MMA issuer)
 constexpr int DT_WROWS = 80;                 // resident weight rows per CTA: 24 W' | 8 We_mm | 48 Wcat
 constexpr int DT_R5 = 0, DT_R3 = 24, DT_R1 = 32;
 constexpr int DT_KCH = DT_E / 64;            // 8 K chunks of 64 bf16 (one 128-byte swizzle span)
@@ -45,18 +45,20 @@ constexpr int DT_WCHUNK = DT_WROWS * 128;    // bytes of one K chunk of the weig
 constexpr int DT_WBYTES = DT_KCH * DT_WCHUNK;
 constexpr int DT_BSLOT = DT_NG * 128;        // 8 KB: 64 activation rows x 64 bf16
 constexpr int DT_NBS = 8;
-constexpr int DT_CH = 8;                     // positions per attention chunk
+constexpr int DT_CH = 8;                     // positions per attention chunk = warps of a consumer group
 constexpr int DT_TSLOT = DT_CH * DT_E * 2;   // 8 KB: one operand (H or V) of one chunk, bf16
+constexpr int DT_NTS = 8;                    // tile-ring slots
 constexpr int DT_RING = DT_NBS * DT_BSLOT;   // 64 KB, shared by the B ring (products) and the tile rings (sweep)
 constexpr int DT_P1 = 65, DT_P3 = 129;       // staging pitches (odd: conflict-free transposed writes)
 constexpr int DT_NCTR = 8;
 constexpr int DT_BARW = DT_NCTR * 32;        // unsigned words of barrier counters per team
-constexpr int DT_STAMPS = 16;
-constexpr uint32_t DT_TMEM_COLS = 256;       // D1: 0..63, D3: 64..191, D5: 192..255
+constexpr int DT_STAMPS = 32;
+constexpr int DT_NI = 1;                      // MMA-issuing warps (consumer warps 8..11): a tcgen05 instruction costs its issuing thread ~85 cycles
+constexpr uint32_t DT_TMEM_COLS = 512;       // P1 / P5: 4 partial accumulators x 64 columns at 0; P3: 4 x 64 at 256
 constexpr int DT_MAXTEAMS = 2;
 constexpr int DT_MAXL = 256;                 // positions per attention (image map 100, trends 52)
 
-static_assert(DT_RING == DT_NBS * DT_TSLOT, "the two rings alias");
+static_assert(DT_RING == DT_NTS * DT_TSLOT, "the two rings alias");
 
 struct DtArgs {
   v2f_decode_params p;
@@ -67,6 +69,7 @@ struct DtArgs {
   unsigned* bar;                                    // [teams, DT_BARW] (zeroed before launch)
   unsigned long long* stamps;                       // optional [T, DT_STAMPS]
   int Np;                                           // teams * 64
+  int dbg;                                          // timing experiments only (results invalid): bit 0 skip the energy arithmetic, bit 1 skip the context arithmetic
 };
 
 __device__ __forceinline__ unsigned long long dt_globaltimer() {
@@ -78,7 +81,6 @@ __device__ __forceinline__ unsigned long long dt_globaltimer() {
 // Team barrier: 64 arrivals spread over DT_NCTR monotonic counters on separate 128-byte lines; lanes 0..7 of warp 0
 // poll one each (a sum of monotonic counters read one by one is a lower bound of the arrivals).  Bounded spin.
 __device__ __forceinline__ void dt_team_barrier(unsigned* ctr, int c, unsigned& epoch) {
-  asm volatile("fence.proxy.async.global;" ::: "memory");   // this thread's hb / Cb / Ub stores -> the next phase's TMA loads
   __syncthreads();
   ++epoch;
   if (threadIdx.x < 32) {
@@ -96,6 +98,10 @@ __device__ __forceinline__ void dt_team_barrier(unsigned* ctr, int c, unsigned& 
       if (v >= target) break;
       if (clock64() - t0 > (1LL << 31)) __trap();   // ~1 s: a protocol bug must not hang the device
     }
+    // the other CTAs' generic-proxy stores (hb / Cb / Ub / the backward's operand buffers) acquired above are read next
+    // by TMA (async proxy): one cross-proxy fence here, ordered before every issuing thread by the barrier below.
+    // (A fence in each of the 8 issuing threads serialised their copies: ~600 cycles apiece.)
+    if (threadIdx.x == 0) asm volatile("fence.proxy.async.global;" ::: "memory");
   }
   __syncthreads();
 }
@@ -110,9 +116,34 @@ __device__ __forceinline__ void dt_tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) 
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// Global data written through the generic proxy (st.global by this or another CTA) and then read by TMA (async proxy):
-// writers fence after their stores, the TMA-issuing thread fences after the team barrier's acquire.
-__device__ __forceinline__ void dt_fence_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
+__device__ __forceinline__ void dt_tmem_ld16_nowait(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void dt_tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void dt_tmem_ld8_nowait(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr));
+}
+// sum of NP partial accumulators (64 columns apart) of 8 columns of this warp's lanes
+template <int NP>
+__device__ __forceinline__ void dt_tmem_ld8_sum(uint32_t taddr, float (&out)[8]) {
+  uint32_t v[NP][8];
+#pragma unroll
+  for (int k = 0; k < NP; k++) dt_tmem_ld8_nowait(taddr + (uint32_t)(k * DT_NG), v[k]);
+  dt_tmem_wait_ld();
+#pragma unroll
+  for (int q = 0; q < 8; q++) {
+    float t = __uint_as_float(v[0][q]);
+#pragma unroll
+    for (int k = 1; k < NP; k++) t += __uint_as_float(v[k][q]);
+    out[q] = t;
+  }
+}
 
 __device__ __forceinline__ float2 dt_bf2(uint32_t w) {   // two packed bf16 -> two fp32
   return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
@@ -165,11 +196,11 @@ decode_team_fwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_co
       mbar_init(&bfull[s], 1);
       mbar_init(&bempty[s], 1);
     }
-    for (int s = 0; s < DT_NBS; s++) {
+    for (int s = 0; s < DT_NTS; s++) {
       mbar_init(&tfull[s], 1);
       mbar_init(&tempty[s], DT_GRP / 32);
     }
-    mbar_init(mma_done, 1);
+    mbar_init(mma_done, DT_NI);
     mbar_init(wfull, 1);
     mbar_fence_init();
   }
@@ -215,32 +246,36 @@ decode_team_fwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_co
     a.hb[(long long)ng * H + 8 * c + gu] = __float2bfloat16_rn(hreg);
   }
   // B ring helpers (warp 16 lane 0 produces, warp 17 lane 0 issues the MMAs)
-  auto load_b = [&](const CUtensorMap* map, int row0, int nch) {
-    dt_fence_async_global();
-    for (int i = 0; i < nch; i++, bq++) {
-      const uint32_t s = bq % DT_NBS, r = bq / DT_NBS;
-      mbar_wait(&bempty[s], (r & 1) ^ 1);
-      mbar_expect_tx(&bfull[s], DT_BSLOT);
-      tma_load_3d(ring + s * DT_BSLOT, map, &bfull[s], (i % DT_KCH) * 64, row0 + (i / DT_KCH) * Np, 0);
-    }
+  // A thread that issues TMA / bulk copies sustains one copy per ~600 cycles, whatever its size (tools/probes/
+  // bulk_probe.cu: 14 B/clk/SM from one issuer at 8 KB per copy, 76 B/clk/SM from eight) -- so copies are issued by MANY
+  // warps: chunk i of a product by lane 0 of consumer warp i % 8 (ring slot w is always filled by warp w, in order: a
+  // warp that skipped a use of its slot would see the mbarrier parity of two phases ago and overwrite live data), the
+  // tile chunks of the sweep by a warp of the group that will consume them.
+  auto load_chunk = [&](const CUtensorMap* map, int row0, int i, uint32_t q) {      // chunk i of a phase, ring sequence q
+    const uint32_t s = q % DT_NBS, r = q / DT_NBS;
+    mbar_wait(&bempty[s], (r & 1) ^ 1);
+    mbar_expect_tx(&bfull[s], DT_BSLOT);
+    tma_load_3d(ring + s * DT_BSLOT, map, &bfull[s], (i % DT_KCH) * 64, row0 + (i / DT_KCH) * Np, 0);
   };
-  auto issue = [&](int r0, uint32_t dcol, int nch) {      // nch = 8 per 64-column accumulator block
-    for (int i = 0; i < nch; i++, bq++) {
-      const uint32_t s = bq % DT_NBS, r = bq / DT_NBS;
+  // chunks [i0, i0 + n) of a product phase accumulate into the 64 columns at dcol (one of DT_NI partial accumulators,
+  // issued by DT_NI different warps in parallel: the sum is taken by the epilogue)
+  auto issue = [&](int r0, uint32_t dcol, int i0, int n, int t, int st0, bool last = true) {
+    for (int i = i0; i < i0 + n; i++) {
+      const uint32_t q = bq + (uint32_t)i, s = q % DT_NBS, r = q / DT_NBS;
       const int kc = i % DT_KCH;
       mbar_wait(&bfull[s], r & 1);
+      if (a.stamps && blockIdx.x == 0 && st0 && (i == i0 || i == i0 + n - 1)) a.stamps[t * DT_STAMPS + st0 + (i != i0)] = dt_globaltimer();
       tc_fence_after();
       const uint64_t ad = umma_desc_sw128(smem_u32(Wsm + kc * DT_WCHUNK + r0 * 128));
       const uint64_t bd = umma_desc_sw128(smem_u32(ring + s * DT_BSLOT));
 #pragma unroll
-      for (int k = 0; k < 4; k++)
-        umma<0>(tmem_d + dcol + (uint32_t)(i / DT_KCH) * DT_NG, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc,
-                (kc | k) ? 1u : 0u);
+      for (int k = 0; k < 4; k++) umma<0>(tmem_d + dcol, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, ((i - i0) | k) ? 1u : 0u);
       umma_commit(&bempty[s]);
     }
-    umma_commit(mma_done);
+    if (last) umma_commit(mma_done);
+    if (a.stamps && blockIdx.x == 0 && st0) a.stamps[t * DT_STAMPS + st0 + 2] = dt_globaltimer();
   };
-  if (warp == 17 && lane == 0) mbar_wait(wfull, 0);
+  if (warp >= 8 && warp < 8 + DT_NI && lane == 0) mbar_wait(wfull, 0);
   dt_team_barrier(bar, c, epoch);                  // hb of step 0 is complete
 
   for (int t = 0; t < T; t++) {
@@ -252,30 +287,36 @@ decode_team_fwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_co
     float* al_tr = p.alpha_tr + (long long)t * N * Lt;
     stamp(t, 0);
     // ================================================================ P1: S^T slice = Wcat_slice h^T (+ bcat)
-    if (warp == 16) {
-      if (lane == 0) load_b(&mapH, n0, DT_KCH);
-      __syncwarp();
-    } else if (warp == 17) {
-      if (lane == 0) issue(DT_R1, 0, DT_KCH);
-      __syncwarp();
-    } else {
+    if (warp < 16) {
+      if (warp < DT_KCH) {
+        if (lane == 0) load_chunk(&mapH, n0, warp, bq + (uint32_t)warp);
+        __syncwarp();
+      } else if (warp < 8 + DT_NI) {
+        const int k = warp - 8;
+        if (lane == 0) issue(DT_R1, (uint32_t)(k * DT_NG), k * (DT_KCH / DT_NI), DT_KCH / DT_NI, t, k == 0 ? 20 : 0);
+        __syncwarp();
+      }
+      stamp(t, 16);
       if (warp < 2) {
         mbar_wait(mma_done, md & 1);
+        stamp(t, 17);
         tc_fence_after();
         const int j = warp * 32 + lane;            // TMEM lane = weight row of the slice
         const float bias = j < 48 ? p.bcat[dt_col1(j, c)] : 0.f;
 #pragma unroll
-        for (int c0 = 0; c0 < DT_NG; c0 += 16) {
-          uint32_t v[16];
-          dt_tmem_ld16(tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+        for (int c0 = 0; c0 < DT_NG; c0 += 8) {
+          float v[8];
+          dt_tmem_ld8_sum<DT_NI>(tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
           if (j < 48)
 #pragma unroll
-            for (int q = 0; q < 16; q++) stage1[j * DT_P1 + c0 + q] = __uint_as_float(v[q]) + bias;
+            for (int q = 0; q < 8; q++) stage1[j * DT_P1 + c0 + q] = v[q] + bias;
         }
         tc_fence_before();
       }
       md++;
+      stamp(t, 18);
       named_bar_sync(3, DT_CONS);
+      stamp(t, 19);
       {   // 8 consecutive columns (32 B) per (row, segment): s_img | s_tr | s_mm | gh_r | gh_z | gh_n
         const int seg = tid & 7;
         if (seg < 6 && ng < N) {
@@ -288,6 +329,7 @@ decode_team_fwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_co
         }
       }
     }
+    bq += DT_KCH;
     stamp(t, 1);
     dt_team_barrier(bar, c, epoch);
     stamp(t, 2);
@@ -308,7 +350,7 @@ decode_team_fwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_co
               const int L = mod ? Lt : Li, j0 = cc * DT_CH, nj = min(DT_CH, L - j0);
               const long long off = ((long long)b * L + j0) * E;
               const uint32_t bytes = (uint32_t)nj * E * 2u;
-              const uint32_t sl = q % DT_NBS, r = q / DT_NBS;
+              const uint32_t sl = q % DT_NTS, r = q / DT_NTS;
               const __nv_bfloat16* src = pass == 0 ? (mod ? a.Htr : a.Himg) : (mod ? a.Ptr : Vimg_b);
               mbar_wait(&tempty[sl], (r & 1) ^ 1);
               mbar_expect_tx(&tfull[sl], bytes);
@@ -318,6 +360,7 @@ decode_team_fwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_co
         __syncwarp();
       } else if (warp < 16) {
         // ---- pass 1: energies
+        float wmax0 = -INFINITY, wmax1 = -INFINITY;      // running maxima of this warp's energies, per modality
         {
           float4 sreg[4], wreg[4];        // columns 8*lane + 256*k + [0,8) for k = 0,1: two float4 each
           float beta = 0.f;
@@ -359,43 +402,51 @@ decode_team_fwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_co
               }
               const float e = warp_sum(acc0 + acc1) + beta;
               if (lane == 0) e_all[mod * DT_MAXL + j0 + gw] = e;
+              if (mod) wmax1 = fmaxf(wmax1, e);
+              else wmax0 = fmaxf(wmax0, e);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[sl]);
           }
         }
+        if (lane == 0) {
+          red[warp] = wmax0;
+          red[16 + warp] = wmax1;
+        }
         stamp(t, 11);
         named_bar_sync(3, DT_CONS);
         stamp(t, 12);
-        // ---- softmax over the positions of each modality (every warp computes the statistics redundantly)
+        // ---- softmax: p_j = exp(e_j - max) in shared memory, 1 / sum per modality; thread j < 256: image position j,
+        // thread 256 + j: trend position j (warps 0..7 / 8..15); the maximum comes from the warps' running maxima
+        float inv0, inv1;
         {
-          float mx0 = 0.f, mx1 = 0.f, inv0 = 0.f, inv1 = 0.f;
+          float m0 = red[lane & 15], m1 = red[16 + (lane & 15)];
 #pragma unroll
-          for (int mod = 0; mod < 2; mod++) {
-            const int L = mod ? Lt : Li;
-            const float* ev = e_all + mod * DT_MAXL;
-            float m = -INFINITY;
-            for (int j = lane; j < L; j += 32) m = fmaxf(m, ev[j]);
-            m = warp_max(m);
-            float l = 0.f;
-            for (int j = lane; j < L; j += 32) l += expf(ev[j] - m);
-            l = warp_sum(l);
-            if (mod) {
-              mx1 = m;
-              inv1 = 1.0f / l;
-            } else {
-              mx0 = m;
-              inv0 = 1.0f / l;
-            }
+          for (int o = 8; o > 0; o >>= 1) {
+            m0 = fmaxf(m0, __shfl_xor_sync(FULL, m0, o));
+            m1 = fmaxf(m1, __shfl_xor_sync(FULL, m1, o));
           }
-          for (int j = tid; j < Li + Lt; j += DT_CONS) {
-            const int mod = j >= Li, jj = mod ? j - Li : j;
-            const float al = expf(e_all[mod * DT_MAXL + jj] - (mod ? mx1 : mx0)) * (mod ? inv1 : inv0);
-            al_all[mod * DT_MAXL + jj] = al;
-            (mod ? al_tr + (long long)n * Lt : al_img + (long long)n * Li)[jj] = al;   // saved for the backward / attention maps
+          const int mod = tid >> 8, jj = tid & 255;
+          float pj = 0.f;
+          if (jj < (mod ? Lt : Li)) {
+            pj = __expf(e_all[mod * DT_MAXL + jj] - (mod ? m1 : m0));
+            al_all[mod * DT_MAXL + jj] = pj;
           }
+          pj = warp_sum(pj);
+          if (lane == 0) red[32 + warp] = pj;
+          named_bar_sync(3, DT_CONS);
+          float l0 = red[32 + (lane & 7)], l1 = red[40 + (lane & 7)];
+#pragma unroll
+          for (int o = 4; o > 0; o >>= 1) {
+            l0 += __shfl_xor_sync(FULL, l0, o);
+            l1 += __shfl_xor_sync(FULL, l1, o);
+          }
+          inv0 = 1.0f / l0;
+          inv1 = 1.0f / l1;
+          // softmax weights saved for the backward pass / returned as attention maps
+          if (jj < (mod ? Lt : Li))
+            (mod ? al_tr + (long long)n * Lt : al_img + (long long)n * Li)[jj] = al_all[mod * DT_MAXL + jj] * (mod ? inv1 : inv0);
         }
-        named_bar_sync(3, DT_CONS);
         stamp(t, 13);
         // ---- pass 2: contexts (thread = columns 2 gt, 2 gt + 1 of both modalities; group g takes chunks g, g+2, ...)
         {
@@ -434,8 +485,8 @@ decode_team_fwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_co
           }
           // partial contexts of this group: pacc[grp][mod][512]
           stamp(t, 14);
-          *reinterpret_cast<float2*>(pacc + (grp * 2 + 0) * E + 2 * gt) = make_float2(ci0, ci1);
-          *reinterpret_cast<float2*>(pacc + (grp * 2 + 1) * E + 2 * gt) = make_float2(ct0, ct1);
+          *reinterpret_cast<float2*>(pacc + (grp * 2 + 0) * E + 2 * gt) = make_float2(ci0 * inv0, ci1 * inv0);
+          *reinterpret_cast<float2*>(pacc + (grp * 2 + 1) * E + 2 * gt) = make_float2(ct0 * inv1, ct1 * inv1);
         }
         named_bar_sync(3, DT_CONS);
         {
@@ -456,23 +507,37 @@ decode_team_fwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_co
     dt_team_barrier(bar, c, epoch);
     stamp(t, 4);
     // ================================================================ P3: HC^T slice = We_mm_slice [c_img ; c_tr]^T
-    if (warp == 16) {
-      if (lane == 0) load_b(&mapC, n0, 2 * DT_KCH);          // chunks 0..7: image contexts, 8..15: trend contexts
-      __syncwarp();
-    } else if (warp == 17) {
-      if (lane == 0) issue(DT_R3, DT_NG, 2 * DT_KCH);
-      __syncwarp();
-    } else {
+    if (warp < 16) {
+      if (warp >= 8 && warp < 8 + DT_NI) {       // issuer k: modality k / PP, K part k % PP -> accumulator 256 + 64 k
+        const int k = warp - 8;
+        if (lane == 0) {
+          if (DT_NI == 1) {
+            issue(DT_R3, 256u, 0, DT_KCH, t, 0, false);
+            issue(DT_R3, 256u + DT_NG, DT_KCH, DT_KCH, t, 0, true);
+          } else {
+            issue(DT_R3, (uint32_t)(256 + k * DT_NG), k * (2 * DT_KCH / DT_NI), 2 * DT_KCH / DT_NI, t, 0);
+          }
+        }
+        __syncwarp();
+      }
+      if (warp < DT_KCH) {             // chunks 0..7: image contexts, 8..15: trend contexts; slot w always from warp w
+        if (lane == 0) {
+          load_chunk(&mapC, n0, warp, bq + (uint32_t)warp);
+          load_chunk(&mapC, n0, warp + DT_KCH, bq + (uint32_t)(warp + DT_KCH));
+        }
+        __syncwarp();
+      }
       if (warp == 0) {
         mbar_wait(mma_done, md & 1);
         tc_fence_after();
 #pragma unroll
-        for (int c0 = 0; c0 < 2 * DT_NG; c0 += 16) {
-          uint32_t v[16];
-          dt_tmem_ld16(tmem_d + (uint32_t)(DT_NG + c0), v);
+        for (int c0 = 0; c0 < 2 * DT_NG; c0 += 8) {         // column c0 = modality * 64 + row: PP = DT_NI / 2 partials at 256 + 64 PP mod + 64 j
+          float v[8];
+          constexpr int PP = DT_NI >= 2 ? DT_NI / 2 : 1;
+          dt_tmem_ld8_sum<PP>(tmem_d + (uint32_t)(256 + (c0 / DT_NG) * PP * DT_NG + (c0 % DT_NG)), v);
           if (lane < 8)
 #pragma unroll
-            for (int q = 0; q < 16; q++) stage5[lane * DT_P3 + c0 + q] = __uint_as_float(v[q]);
+            for (int q = 0; q < 8; q++) stage5[lane * DT_P3 + c0 + q] = v[q];
         }
         tc_fence_before();
       }
@@ -486,6 +551,7 @@ decode_team_fwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_co
         }
       }
     }
+    bq += 2 * DT_KCH;
     stamp(t, 5);
     dt_team_barrier(bar, c, epoch);
     stamp(t, 6);
@@ -577,23 +643,25 @@ decode_team_fwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_co
     dt_team_barrier(bar, c, epoch);
     stamp(t, 8);
     // ================================================================ P5: GI^T slice = W'_slice U^T ; GRU gates of the own hidden units
-    if (warp == 16) {
-      if (lane == 0) load_b(&mapU, n0, DT_KCH);
-      __syncwarp();
-    } else if (warp == 17) {
-      if (lane == 0) issue(DT_R5, 3 * DT_NG, DT_KCH);
-      __syncwarp();
-    } else {
+    if (warp < 16) {
+      if (warp < DT_KCH) {
+        if (lane == 0) load_chunk(&mapU, n0, warp, bq + (uint32_t)warp);
+        __syncwarp();
+      } else if (warp < 8 + DT_NI) {
+        const int k = warp - 8;
+        if (lane == 0) issue(DT_R5, (uint32_t)(k * DT_NG), k * (DT_KCH / DT_NI), DT_KCH / DT_NI, t, 0);
+        __syncwarp();
+      }
       if (warp == 0) {
         mbar_wait(mma_done, md & 1);
         tc_fence_after();
 #pragma unroll
-        for (int c0 = 0; c0 < DT_NG; c0 += 16) {
-          uint32_t v[16];
-          dt_tmem_ld16(tmem_d + (uint32_t)(3 * DT_NG + c0), v);
+        for (int c0 = 0; c0 < DT_NG; c0 += 8) {
+          float v[8];
+          dt_tmem_ld8_sum<DT_NI>(tmem_d + (uint32_t)c0, v);
           if (lane < 24)
 #pragma unroll
-            for (int q = 0; q < 16; q++) stage5[lane * DT_P1 + c0 + q] = __uint_as_float(v[q]);
+            for (int q = 0; q < 8; q++) stage5[lane * DT_P1 + c0 + q] = v[q];
         }
         tc_fence_before();
       }
@@ -627,6 +695,7 @@ decode_team_fwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_co
       yp += __shfl_xor_sync(FULL, yp, 4);
       if (gu == 0 && gact) a.ypart[(long long)c * Np + ng] = yp;
     }
+    bq += DT_KCH;
     stamp(t, 9);
     dt_team_barrier(bar, c, epoch);
     stamp(t, 10);
@@ -759,6 +828,14 @@ int decode_team_fwd(const v2f_decode_params* p, cudaStream_t s) {
   a.bar = reinterpret_cast<unsigned*>(ws + l.bar);
   a.stamps = g_dt_stamps ? reinterpret_cast<unsigned long long*>(ws + l.stamps) : nullptr;
   a.Np = Np;
+  {
+    static int dbg = -1;
+    if (dbg < 0) {
+      const char* e = getenv("V2F_TEAM_DEBUG");
+      dbg = e ? atoi(e) : 0;
+    }
+    a.dbg = dbg;
+  }
   // pad rows of the B operands are zero; valid rows are rewritten every step
   cudaMemsetAsync(ws + l.hb, 0, sizeof(float) * (size_t)(l.ypart - l.hb), s);
   cudaMemsetAsync(a.bar, 0, sizeof(unsigned) * DT_MAXTEAMS * DT_BARW, s);
@@ -916,18 +993,17 @@ decode_team_bwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_co
   auto stamp = [&](int t, int k) {
     if (a.stamps && blockIdx.x == 0 && tid == 0) a.stamps[t * DT_STAMPS + k] = dt_globaltimer();
   };
-  auto load_a = [&](const CUtensorMap* map, int row0, int nch) {
-    dt_fence_async_global();
-    for (int i = 0; i < nch; i++, bq++) {
-      const uint32_t s = bq % DT_NBS, r = bq / DT_NBS;
-      mbar_wait(&bempty[s], (r & 1) ^ 1);
-      mbar_expect_tx(&bfull[s], DT_BSLOT);
-      tma_load_3d(ring + s * DT_BSLOT, map, &bfull[s], i * 64, row0, 0);
-    }
+  // chunk i of a product phase (ring sequence q = bq + i) is issued by lane 0 of consumer warp i % 8 = its ring slot (one
+  // issuing thread sustains only one copy per ~600 cycles; see the forward kernel)
+  auto load_chunk = [&](const CUtensorMap* map, int row0, int kc, uint32_t q) {
+    const uint32_t s = q % DT_NBS, r = q / DT_NBS;
+    mbar_wait(&bempty[s], (r & 1) ^ 1);
+    mbar_expect_tx(&bfull[s], DT_BSLOT);
+    tma_load_3d(ring + s * DT_BSLOT, map, &bfull[s], kc * 64, row0, 0);
   };
-  auto issue = [&](int wch0, uint32_t dcol, int nch, bool last) {
-    for (int i = 0; i < nch; i++, bq++) {
-      const uint32_t s = bq % DT_NBS, r = bq / DT_NBS;
+  auto issue = [&](int wch0, uint32_t dcol, int nch, uint32_t q0, bool last) {
+    for (int i = 0; i < nch; i++) {
+      const uint32_t q = q0 + (uint32_t)i, s = q % DT_NBS, r = q / DT_NBS;
       mbar_wait(&bfull[s], r & 1);
       tc_fence_after();
       const uint64_t ad = umma_desc_sw128(smem_u32(ring + s * DT_BSLOT));
@@ -1003,13 +1079,15 @@ decode_team_bwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_co
     dt_team_barrier(bar, c, epoch);
     stamp(ts, 2);
     // ================================================================ B: dU[:, 8c..8c+8) = DGI W'[:, 8c..]
-    if (warp == 16) {
-      if (lane == 0) load_a(&mapG, par * Np + n0, DTB_KG);
+    if (warp == 17) {
+      if (lane == 0) issue(DTB_W2, 0, DTB_KG, bq, true);
       __syncwarp();
-    } else if (warp == 17) {
-      if (lane == 0) issue(DTB_W2, 0, DTB_KG, true);
-      __syncwarp();
-    } else {
+    } else if (warp < 16) {
+      if (warp < DT_NBS) {
+        if (lane == 0)
+          for (int i = warp; i < DTB_KG; i += DT_NBS) load_chunk(&mapG, par * Np + n0, i, bq + (uint32_t)i);
+        __syncwarp();
+      }
       if (warp < 2) {
         mbar_wait(mma_done, md & 1);
         tc_fence_after();
@@ -1025,6 +1103,7 @@ decode_team_bwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_co
       }
       md++;
     }
+    bq += DTB_KG;
     stamp(ts, 3);
     dt_team_barrier(bar, c, epoch);
     stamp(ts, 4);
@@ -1089,19 +1168,20 @@ decode_team_bwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_co
     dt_team_barrier(bar, c, epoch);
     stamp(ts, 6);
     // ================================================================ D: dC[:, :, 8c..8c+8) += DHC We_mm[:, 8c..]
-    if (warp == 16) {
+    if (warp == 17) {
       if (lane == 0) {
-        load_a(&mapD, n0, DTB_KC);
-        load_a(&mapD, Np + n0, DTB_KC);
+        issue(DTB_W4, 16, DTB_KC, bq, false);
+        issue(DTB_W4, 32, DTB_KC, bq + DTB_KC, true);
       }
       __syncwarp();
-    } else if (warp == 17) {
-      if (lane == 0) {
-        issue(DTB_W4, 16, DTB_KC, false);
-        issue(DTB_W4, 32, DTB_KC, true);
+    } else if (warp < 16) {
+      if (warp < DT_NBS) {             // 8 image + 8 trend chunks
+        if (lane == 0) {
+          load_chunk(&mapD, n0, warp, bq + (uint32_t)warp);
+          load_chunk(&mapD, Np + n0, warp, bq + (uint32_t)(warp + DTB_KC));
+        }
+        __syncwarp();
       }
-      __syncwarp();
-    } else {
       if (warp < 2) {
         mbar_wait(mma_done, md & 1);
         tc_fence_after();
@@ -1129,6 +1209,7 @@ decode_team_bwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_co
       }
       md++;
     }
+    bq += 2 * DTB_KC;
     stamp(ts, 7);
     dt_team_barrier(bar, c, epoch);
     stamp(ts, 8);
@@ -1146,7 +1227,7 @@ decode_team_bwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_co
               const int L = mod ? Lt : Li, j0 = cc * DT_CH, nj = min(DT_CH, L - j0);
               const long long off = ((long long)b * L + j0) * E;
               const uint32_t bytes = (uint32_t)nj * E * 2u;
-              const uint32_t sl = q % DT_NBS, r = q / DT_NBS;
+              const uint32_t sl = q % DT_NTS, r = q / DT_NTS;
               const __nv_bfloat16* src = pass == 0 ? (mod ? a.Ptr : Vimg_b) : (mod ? a.Htr : a.Himg);
               mbar_wait(&tempty[sl], (r & 1) ^ 1);
               mbar_expect_tx(&tfull[sl], bytes);
@@ -1282,13 +1363,15 @@ decode_team_bwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_co
     dt_team_barrier(bar, c, epoch);
     stamp(ts, 10);
     // ================================================================ F: dh[:, 8c..8c+8) = z-path + DS Wcat[:, 8c..]
-    if (warp == 16) {
-      if (lane == 0) load_a(&mapS, par * Np + n0, DTB_KS);
+    if (warp == 17) {
+      if (lane == 0) issue(DTB_W6, 48, DTB_KS, bq, true);
       __syncwarp();
-    } else if (warp == 17) {
-      if (lane == 0) issue(DTB_W6, 48, DTB_KS, true);
-      __syncwarp();
-    } else {
+    } else if (warp < 16) {
+      if (warp < DT_NBS) {
+        if (lane == 0)
+          for (int i = warp; i < DTB_KS; i += DT_NBS) load_chunk(&mapS, par * Np + n0, i, bq + (uint32_t)i);
+        __syncwarp();
+      }
       if (warp < 2) {
         mbar_wait(mma_done, md & 1);
         tc_fence_after();
@@ -1304,6 +1387,7 @@ decode_team_bwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_co
       dhreg = dhdir + stage[nl * 9 + gu];
       named_bar_sync(3, DT_CONS);          // stage is rewritten by the next step's phase F only, but keep the readers together
     }
+    bq += DTB_KS;
     stamp(ts, 11);
   }
   // ------------------------------------------------------------------ outputs that accumulate over the steps

@@ -226,6 +226,108 @@ bn1d_bwd_kernel(int B, int D, const float* __restrict__ x, const float* __restri
   }
 }
 
+// ------------------------------------------------------------------ BatchNorm1d with batch statistics over a SHARDED batch
+// (data parallelism: every rank holds B_local rows of the global batch).  The reference normalises with the statistics
+// of the whole batch (models/GTM_Visuelle2.py:158, Proposed_model_v3.py:166), so under batch sharding the per-channel
+// sums are exchanged: stats kernel -> all-reduce of [2,D] doubles (host side, NCCL) -> apply kernel; same for the two
+// reductions of the backward pass.  Sums are kept in double so that E[x^2] - mean^2 stays at the fp32 rounding level.
+__device__ __forceinline__ double col_reduce_d(double v, double (*red)[33]) {
+  red[threadIdx.y][threadIdx.x] = v;
+  __syncthreads();
+  double t = 0.0;
+  if (threadIdx.y == 0)
+    for (int i = 0; i < 32; i++) t += red[i][threadIdx.x];
+  __syncthreads();
+  return t;
+}
+
+// out[0,c] = sum_b x[b,c], out[1,c] = sum_b x[b,c]^2
+__global__ void __launch_bounds__(1024)
+bn1d_stats_kernel(int B, int D, const float* __restrict__ x, double* __restrict__ out) {
+  __shared__ double red[32][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const bool ok = c < D;
+  double s = 0.0, q = 0.0;
+  if (ok) for (int b = threadIdx.y; b < B; b += 32) {
+    const double v = x[(long long)b * D + c];
+    s += v;
+    q += v * v;
+  }
+  s = col_reduce_d(s, red);
+  q = col_reduce_d(q, red);
+  if (ok && threadIdx.y == 0) {
+    out[c] = s;
+    out[D + c] = q;
+  }
+}
+
+// sums = all-reduced [2,D]; Btot = rows of the global batch
+__global__ void __launch_bounds__(1024)
+bn1d_apply_kernel(int B, int D, const float* __restrict__ x, const float* __restrict__ gamma,
+                  const float* __restrict__ beta, const double* __restrict__ sums, double Btot,
+                  float* __restrict__ run_mean, float* __restrict__ run_var, float momentum, float eps,
+                  float* __restrict__ y, float* __restrict__ save_mean, float* __restrict__ save_rstd) {
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  if (c >= D) return;
+  const double m = sums[c] / Btot;
+  double v = sums[D + c] / Btot - m * m;
+  if (v < 0.0) v = 0.0;
+  const float mean = (float)m, var = (float)v;
+  const float r = 1.0f / sqrtf(var + eps);
+  if (threadIdx.y == 0) {
+    const float unb = Btot > 1.0 ? (float)(v * Btot / (Btot - 1.0)) : var;
+    run_mean[c] = (1.f - momentum) * run_mean[c] + momentum * mean;
+    run_var[c] = (1.f - momentum) * run_var[c] + momentum * unb;
+    save_mean[c] = mean;
+    save_rstd[c] = r;
+  }
+  const float g = gamma[c], bt = beta[c];
+  for (int b = threadIdx.y; b < B; b += 32)
+    y[(long long)b * D + c] = fmaf((x[(long long)b * D + c] - mean) * r, g, bt);
+}
+
+// out[0,c] = sum_b dy, out[1,c] = sum_b dy * xhat   (local rows); dgamma / dbeta = the local sums
+__global__ void __launch_bounds__(1024)
+bn1d_bwd_stats_kernel(int B, int D, const float* __restrict__ x, const float* __restrict__ dy,
+                      const float* __restrict__ save_mean, const float* __restrict__ save_rstd,
+                      double* __restrict__ out, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  __shared__ double red[32][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const bool ok = c < D;
+  const float mean = ok ? save_mean[c] : 0.f, r = ok ? save_rstd[c] : 0.f;
+  double s1 = 0.0, s2 = 0.0;
+  if (ok) for (int b = threadIdx.y; b < B; b += 32) {
+    const float d = dy[(long long)b * D + c];
+    s1 += d;
+    s2 += (double)d * (double)((x[(long long)b * D + c] - mean) * r);
+  }
+  s1 = col_reduce_d(s1, red);
+  s2 = col_reduce_d(s2, red);
+  if (ok && threadIdx.y == 0) {
+    out[c] = s1;
+    out[D + c] = s2;
+    dbeta[c] = (float)s1;
+    dgamma[c] = (float)s2;
+  }
+}
+
+__global__ void __launch_bounds__(1024)
+bn1d_bwd_apply_kernel(int B, int D, const float* __restrict__ x, const float* __restrict__ dy,
+                      const float* __restrict__ gamma, const float* __restrict__ save_mean,
+                      const float* __restrict__ save_rstd, const double* __restrict__ sums, double Btot,
+                      float* __restrict__ dx) {
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  if (c >= D) return;
+  const float mean = save_mean[c], r = save_rstd[c];
+  const float g = gamma[c] * r;
+  const float m1 = (float)(sums[c] / Btot), m2 = (float)(sums[D + c] / Btot);
+  for (int b = threadIdx.y; b < B; b += 32) {
+    const float d = dy[(long long)b * D + c];
+    const float xh = (x[(long long)b * D + c] - mean) * r;
+    dx[(long long)b * D + c] = g * (d - m1 - xh * m2);
+  }
+}
+
 // ------------------------------------------------------------------ elementwise
 __global__ void gate_fwd_kernel(long long n, const float* __restrict__ x, const float* __restrict__ g,
                                 int mode, float* __restrict__ out) {
@@ -463,6 +565,40 @@ extern "C" int v2f_bn1d_bwd(int B, int D, const float* x, const float* dy, const
               V2F_ERR_BAD_ARG);
   bn1d_bwd_kernel<<<(D + 31) / 32, dim3(32, 32), 0, (cudaStream_t)st>>>(B, D, x, dy, gamma, save_mean, save_rstd,
                                                                         training, dx, dgamma, dbeta);
+  V2F_CHECK_LAUNCH();
+  return V2F_OK;
+}
+
+extern "C" int v2f_bn1d_stats(int B, int D, const float* x, double* sums, void* st) {
+  V2F_REQUIRE(B > 0 && D > 0 && x && sums, V2F_ERR_BAD_ARG);
+  bn1d_stats_kernel<<<(D + 31) / 32, dim3(32, 32), 0, (cudaStream_t)st>>>(B, D, x, sums);
+  V2F_CHECK_LAUNCH();
+  return V2F_OK;
+}
+extern "C" int v2f_bn1d_apply(int B, int D, const float* x, const float* gamma, const float* beta, const double* sums,
+                              double Btot, float* run_mean, float* run_var, float momentum, float eps, float* y,
+                              float* save_mean, float* save_rstd, void* st) {
+  V2F_REQUIRE(B > 0 && D > 0 && Btot >= B && x && gamma && beta && sums && run_mean && run_var && y && save_mean && save_rstd,
+              V2F_ERR_BAD_ARG);
+  bn1d_apply_kernel<<<(D + 31) / 32, dim3(32, 32), 0, (cudaStream_t)st>>>(B, D, x, gamma, beta, sums, Btot, run_mean,
+                                                                          run_var, momentum, eps, y, save_mean, save_rstd);
+  V2F_CHECK_LAUNCH();
+  return V2F_OK;
+}
+extern "C" int v2f_bn1d_bwd_stats(int B, int D, const float* x, const float* dy, const float* save_mean,
+                                  const float* save_rstd, double* sums, float* dgamma, float* dbeta, void* st) {
+  V2F_REQUIRE(B > 0 && D > 0 && x && dy && save_mean && save_rstd && sums && dgamma && dbeta, V2F_ERR_BAD_ARG);
+  bn1d_bwd_stats_kernel<<<(D + 31) / 32, dim3(32, 32), 0, (cudaStream_t)st>>>(B, D, x, dy, save_mean, save_rstd, sums,
+                                                                              dgamma, dbeta);
+  V2F_CHECK_LAUNCH();
+  return V2F_OK;
+}
+extern "C" int v2f_bn1d_bwd_apply(int B, int D, const float* x, const float* dy, const float* gamma,
+                                  const float* save_mean, const float* save_rstd, const double* sums, double Btot,
+                                  float* dx, void* st) {
+  V2F_REQUIRE(B > 0 && D > 0 && Btot >= B && x && dy && gamma && save_mean && save_rstd && sums && dx, V2F_ERR_BAD_ARG);
+  bn1d_bwd_apply_kernel<<<(D + 31) / 32, dim3(32, 32), 0, (cudaStream_t)st>>>(B, D, x, dy, gamma, save_mean, save_rstd,
+                                                                              sums, Btot, dx);
   V2F_CHECK_LAUNCH();
   return V2F_OK;
 }

@@ -32,6 +32,20 @@ def shard_batch(batch, rank, world):
     return tuple(cut(t) for t in data), cut(images)
 
 
+def sync_batchnorm1d(module, group=None):
+    """Mark every nn.BatchNorm1d of ``module`` (GTM_Visuelle2 / Proposed_model_v3 / M4FT fusion networks) so that its
+    train-mode statistics are those of the GLOBAL batch: (sum, sum of squares) and the two backward sums are all-reduced
+    across ``group`` (functional_gtm._BatchNorm1dSync).  With it, N ranks x B/N items reproduce the reference's
+    single-process batch of B items; without it each rank normalises with its own shard's statistics (what
+    DistributedDataParallel does by default).  The ResNet trunk's BatchNorm2d stays per-rank.  Returns the count."""
+    n = 0
+    for m in module.modules():
+        if isinstance(m, torch.nn.BatchNorm1d):
+            m.v2f_sync_group = "world" if group is None else group
+            n += 1
+    return n
+
+
 class GradReducer:
     def __init__(self, module, bucket_bytes=25 << 20, group=None, hooks=True, broadcast=True):
         self.group = group

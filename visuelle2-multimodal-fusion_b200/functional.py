@@ -499,7 +499,8 @@ def persist_phase_times():
         off = _lib.lib().v2f_decode_persist_stamps_offset(N, E, H) // 4
         names = PERSIST_PHASES
     torch.cuda.synchronize()
-    st = ws[off:off + 2 * T * 16].cpu().view(torch.int64).view(T, 16)
+    ns = 32 if team else 16
+    st = ws[off:off + 2 * T * ns].cpu().view(torch.int64).view(T, ns)
     out = {}
     for k, name in enumerate(names):
         work = sum(int(st[t, 2 * k + 1]) - int(st[t, 2 * k]) for t in range(T)) / T / 1e3
@@ -509,6 +510,13 @@ def persist_phase_times():
         marks = [2, 11, 12, 13, 14, 3]
         names2 = ["P2.a energies pass", "P2.b barrier", "P2.c softmax", "P2.d context pass", "P2.e combine"]
         for (a, b), name in zip(zip(marks[:-1], marks[1:]), names2):
+            out[name] = (sum(int(st[t, b]) - int(st[t, a]) for t in range(T)) / T / 1e3, 0.0)
+        for a_, b_, name in ((0, 20, "P1.m first chunk landed (MMA thread)"), (20, 21, "P1.m last chunk landed"),
+                             (21, 22, "P1.m MMAs issued + commits"), (22, 17, "P1.m commit -> epilogue sees mma_done")):
+            out[name] = (sum(int(st[t, b_]) - int(st[t, a_]) for t in range(T)) / T / 1e3, 0.0)
+        marks = [0, 16, 17, 18, 19, 1]
+        names1 = ["P1.a TMA issue", "P1.b loads + MMA", "P1.c TMEM -> smem", "P1.d barrier", "P1.e S stores"]
+        for (a, b), name in zip(zip(marks[:-1], marks[1:]), names1):
             out[name] = (sum(int(st[t, b]) - int(st[t, a]) for t in range(T)) / T / 1e3, 0.0)
     return out
 

@@ -86,11 +86,69 @@ class _BatchNorm1d(torch.autograd.Function):
         return dx, dg, db, None, None, None, None, None
 
 
+class _BatchNorm1dSync(torch.autograd.Function):
+    """Train-mode BatchNorm1d over a batch SHARDED across the ranks of ``group``: the statistics are those of the global
+    batch, as in the reference's single-process run (BatchNorm1d under batch sharding).  Two tiny
+    all-reduces of [2,D] doubles per direction; every rank must call it (same count, same order)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, run_mean, run_var, momentum, eps, group):
+        import torch.distributed as dist
+        x = _c(x)
+        B, D = x.shape
+        dev = x.device
+        sums = torch.empty(2, D, device=dev, dtype=torch.float64)
+        check(_L().v2f_bn1d_stats(B, D, ptr(x), sums.data_ptr(), stream()), "v2f_bn1d_stats")
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
+        btot = float(B * dist.get_world_size(group))       # equal shards (ddp.shard_batch raises otherwise)
+        y = torch.empty_like(x)
+        mean, rstd = _f32(D, device=dev), _f32(D, device=dev)
+        check(_L().v2f_bn1d_apply(B, D, ptr(x), ptr(gamma), ptr(beta), sums.data_ptr(), btot, ptr(run_mean),
+                                  ptr(run_var), float(momentum), float(eps), ptr(y), ptr(mean), ptr(rstd), stream()),
+              "v2f_bn1d_apply")
+        ctx.save_for_backward(x, gamma, mean, rstd)
+        ctx.group, ctx.btot = group, btot
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        import torch.distributed as dist
+        x, gamma, mean, rstd = ctx.saved_tensors
+        dy = _c(dy)
+        B, D = x.shape
+        dev = x.device
+        sums = torch.empty(2, D, device=dev, dtype=torch.float64)
+        dg, db = _f32(D, device=dev), _f32(D, device=dev)
+        check(_L().v2f_bn1d_bwd_stats(B, D, ptr(x), ptr(dy), ptr(mean), ptr(rstd), sums.data_ptr(), ptr(dg), ptr(db),
+                                      stream()), "v2f_bn1d_bwd_stats")
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=ctx.group)
+        dx = torch.empty_like(x)
+        check(_L().v2f_bn1d_bwd_apply(B, D, ptr(x), ptr(dy), ptr(gamma), ptr(mean), ptr(rstd), sums.data_ptr(),
+                                      ctx.btot, ptr(dx), stream()), "v2f_bn1d_bwd_apply")
+        return dx, dg, db, None, None, None, None, None
+
+
+def _sync_group(bn):
+    """The process group a BatchNorm1d was marked with by ddp.sync_batchnorm1d (None: per-rank statistics)."""
+    g = getattr(bn, "v2f_sync_group", None)
+    if g is None:
+        return None
+    import torch.distributed as dist
+    if not dist.is_initialized():
+        return None
+    group = None if g == "world" else g
+    return g if dist.get_world_size(group) > 1 else None
+
+
 def batch_norm1d(x, bn, training):
     """``bn``: an nn.BatchNorm1d used as parameter / buffer container (running stats updated in place)."""
     if training and bn.track_running_stats and bn.num_batches_tracked is not None:
         bn.num_batches_tracked.add_(1)
     mom = 0.1 if bn.momentum is None else bn.momentum
+    g = _sync_group(bn) if training else None
+    if g is not None:
+        return _BatchNorm1dSync.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, mom, bn.eps,
+                                      None if g == "world" else g)
     return _BatchNorm1d.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, training, mom, bn.eps)
 
 
