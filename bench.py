@@ -435,11 +435,34 @@ class _Runner:
         self.zero()
 
     def head_ms(self, steps):
+        """Head-only step (feature maps in, gradient w.r.t. them out) replayed from a CUDA graph like the full step:
+        the eager pass is ~700 launches issued by one host thread, and its figure followed the box's host jitter
+        (4.7 ... 60 ms from box to box for the same kernels); the eager median is kept beside it."""
+        from visuelle2_multimodal_fusion_b200.graphs import GraphedTrainStep
         for i in range(3):
             self.step_head(i)
-        self.timed(self.step_head, steps, "head_only")
-        hs = sorted(self.step_ms["head_only"])
-        return hs[len(hs) // 2]                # median step: this eager, launch-bound pass is jitter-prone
+        self.timed(self.step_head, steps, "head_only_eager")
+        hs = sorted(self.step_ms["head_only_eager"])
+        self.head_eager_ms = hs[len(hs) // 2]
+        if not self.use_graph:
+            self.step_ms["head_only"] = self.step_ms["head_only_eager"]
+            return self.head_eager_ms
+        torch.manual_seed(98)
+        batches = [(d, f) for (d, _), f in zip(self.resident, self.feats)]
+        g = GraphedTrainStep(self.model, batches[0], reducer=self.reducer if self.graph_nccl else None, image_grad=True)
+
+        def step(i):
+            torch.manual_seed(1234 + i)
+            g(batches[i & 1])
+            if self.reducer and not self.graph_nccl:
+                self.reducer.reduce_now()
+
+        for i in range(3):
+            step(i)
+        ms = self.timed(step, steps, "head_only")
+        del g
+        self.zero()
+        return ms / steps
 
     def close(self):
         if self.reducer is not None:
@@ -493,7 +516,12 @@ def _roofline_passes(r, args, nsteps):
             _lib.lib().v2f_decode_team_stamps_enable(0)
     peak, peak_src = _peaks()
     N, T = r.B, 10
-    tile_bytes = N * 4 * (2 * LI + 2 * LT) * E
+    team = bool(phases) and len([k for k in phases if k.startswith("P") and "." not in k]) == 5
+    # SURVEY 8(d) per-step byte model: every row streams its image and trend tiles (H and V: 2 x (100 + 52) positions x E)
+    # once per step, plus the row's small vectors.  The row-team kernel streams bf16 copies of the tiles (2 B / element);
+    # the fp32-tile figure of the survey's formula is reported beside it so that rounds stay comparable.
+    tile_bytes_fp32 = N * 4 * (2 * LI + 2 * LT) * E
+    tile_bytes = tile_bytes_fp32 // 2 if team else tile_bytes_fp32
     small = N * 4 * (5 * H + LI + LT + 4)
     timing = ("CUDA events on the launching stream around each launch, separate eager pass with the host running ahead "
               "of the GPU (spin kernel before forward / backward)")
@@ -515,6 +543,17 @@ def _roofline_passes(r, args, nsteps):
                       "traffic": traffic, "traffic_source": tsrc, "kernel": name, "avg_launch_us": avg_ms * 1e3,
                       "launches_per_step": n / nprof, "algorithmic_bytes_per_launch": bytes_per_launch,
                       "peak_source": peak_src, "timing": timing}
+    for kname in ("decode_persist_fwd_kernel", "decode_persist_bwd_kernel"):
+        if kname in roof and team:
+            rr = roof[kname]
+            rr["tile_storage"] = "bf16 copies of the tiles (csrc/decode_team.cu)"
+            fp32_bytes = T * (tile_bytes_fp32 + small)
+            rr["algorithmic_bytes_per_launch_fp32_tiles"] = fp32_bytes
+            rr["frac_fp32_tile_bytes"] = fp32_bytes / (rr["avg_launch_us"] * 1e-6) / 1e9 / peak
+            rr["note_bound"] = ("the bf16 tiles of all rows (40 MB) stay resident in the 126 MB L2 for the whole launch: DRAM traffic "
+                                "(`traffic`) is a fraction of the algorithmic bytes, so HBM is not what bounds this kernel -- "
+                                "the per-step chain of five team barriers, tcgen05 issue (~85 cycles per instruction in the "
+                                "issuing thread) and L2 -> SM tile delivery is (profiles/r02_summary.md)")
     if "decode_persist_fwd_kernel" in roof and phases:
         rr = roof["decode_persist_fwd_kernel"]
         rr["phases_us_per_step"] = {k: {"work": round(w, 2), "barrier_wait": round(b, 2)} for k, (w, b) in phases.items()}
@@ -683,7 +722,9 @@ def run_product(args):
     r.to_eager()
     r.head_setup()
     head_ms = r.head_ms(args.steps)
+    head_eager_ms = r.head_eager_ms
     step_ms["head_only"] = r.step_ms["head_only"]
+    step_ms["head_only_eager"] = r.step_ms["head_only_eager"]
     roof = _roofline_passes(r, args, args.steps)
     r.head_restore()
     _bn_passes(r, roof)
@@ -713,7 +754,8 @@ def run_product(args):
                            "e2e": {"value": tot / (m2 * 1e-3), "unit": "samples/s", "ms_per_step": m2 / k_other,
                                    "h2d_bytes_per_step": ro.h2d, "d2h_bytes_per_step": 4},
                            "head_only": {"ms_per_step": hm, "value": B * world / (hm * 1e-3), "unit": "samples/s",
-                                         "note": "feature maps in, eager launches, median step"},
+                                         "eager_median_ms": ro.head_eager_ms,
+                                         "note": "feature maps in, gradient w.r.t. them out; CUDA-graph replay"},
                            "gpu_launches_per_step": lp,
                            "cpu_baseline": _cpu_sample(name, 16, threads, n_it=1) if want_cpu else None}
             ro.close()
@@ -758,7 +800,10 @@ def run_product(args):
             "gpu_launches": launches, "gpu_launches_per_step": launches / args.steps,
             "clocks": clk, "step_ms": step_ms,
             "head_only": {"value": B * world / (head_ms * 1e-3), "unit": "samples/s", "ms_per_step": head_ms,
-                          "note": "feature maps [B,2048,10,10] in; everything libv2f_b200 covers; eager launches, median step"},
+                          "eager_median_ms": head_eager_ms,
+                          "note": "feature maps [B,2048,10,10] in, gradient w.r.t. them out; everything libv2f_b200 covers; "
+                                  "CUDA-graph replay like the full step (eager_median_ms: the same step issued eagerly, "
+                                  "~700 launches from one host thread -- follows the box's host jitter)"},
             "roofline": roof.get(roof_main),
             "roofline_other": {k: v for k, v in roof.items() if k != roof_main},
             "cpu_baseline": cpu,

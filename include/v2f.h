@@ -285,6 +285,10 @@ int v2f_bn1d_bwd_stats(int B, int D, const float* x, const float* dy, const floa
                        const float* save_rstd, double* sums, float* dgamma, float* dbeta, void* stream);
 int v2f_bn1d_bwd_apply(int B, int D, const float* x, const float* dy, const float* gamma, const float* save_mean,
                        const float* save_rstd, const double* sums, double Btot, float* dx, void* stream);
+/* nn.Dropout (models/CrossAttnRNN210.py:72 and every encoder / fusion network): out = x * keep / (1 - p) with the keep
+ * decisions generated inside the kernel (Philox4x32-10, counter = element index / 4, key = key[0], key[1] read from
+ * DEVICE memory).  Calling it again on the incoming gradient with the same key is the backward pass: no mask tensor. */
+int v2f_dropout(long long n, const float* x, const unsigned long long* key, float p, float* out, void* stream);
 /* Sigmoid gates: mode 0: out = x*sigmoid(g) (models/Proposed_model.py:217, _v2.py:598,682,
  * _v3.py:222-227); mode 1: out = x + x*sigmoid(g) (Proposed_model.py:154, _v2.py:635, _v4.py:186-192). */
 int v2f_gate_fwd(long long n, const float* x, const float* g, int mode, float* out, void* stream);

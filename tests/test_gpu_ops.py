@@ -217,3 +217,24 @@ def test_persistent_gru_equals_per_step_path(N, L, I, H, prec):
             _lib.lib().v2f_gru_persistent_enable(1)
     for a, b in zip(res[1], res[0]):
         assert _rel(a, b) < (2e-5 if prec == "fp32" else 5e-3)     # tf32 (rounded vs truncated operands) in bf16 mode
+
+
+def test_fused_dropout_statistics_and_backward_replays_the_mask():
+    """v2f_dropout: keep rate 1 - p, kept values scaled by 1 / (1 - p), decisions a function of (key, index) only --
+    the backward pass regenerates exactly the forward's mask; a different key gives a different mask."""
+    import visuelle2_multimodal_fusion_b200.functional as Fv
+    torch.manual_seed(3)
+    x = (torch.rand(257, 1031, device="cuda") + 0.5).requires_grad_(True)       # odd sizes: tail elements
+    for p in (0.1, 0.2, 0.5):
+        y = Fv.dropout(x, p, True)
+        kept = y != 0
+        rate = float(kept.float().mean())
+        assert abs(rate - (1 - p)) < 4 * (p * (1 - p) / x.numel()) ** 0.5 + 1e-4, (p, rate)
+        assert torch.allclose(y[kept], x.detach()[kept] / (1 - p), rtol=1e-6)
+        (g,) = torch.autograd.grad(y, x, torch.ones_like(y))
+        assert torch.equal(g != 0, kept) and torch.allclose(g[kept], torch.full_like(g[kept], 1 / (1 - p)))
+        y2 = Fv.dropout(x, p, True)
+        assert float(((y2 != 0) != kept).float().mean()) > 0.05          # fresh key, fresh mask
+        # no run of identical decisions along rows / columns (counter layout sanity)
+        assert abs(float((kept[:, 1:] & kept[:, :-1]).float().mean()) - (1 - p) ** 2) < 0.01
+    assert Fv.dropout(x, 0.3, False) is x

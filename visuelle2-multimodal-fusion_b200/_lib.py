@@ -116,6 +116,7 @@ def _declare(lib):
     lib.v2f_bn1d_fwd.argtypes = [c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_float, c_float, c_vp, c_vp,
                                  c_vp, c_vp]
     lib.v2f_bn1d_bwd.argtypes = [c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_vp]
+    lib.v2f_dropout.argtypes = [c_ll, c_vp, c_vp, c_float, c_vp, c_vp]
     lib.v2f_gate_fwd.argtypes = [c_ll, c_vp, c_vp, c_int, c_vp, c_vp]
     lib.v2f_gate_bwd.argtypes = [c_ll, c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_vp]
     lib.v2f_add_f32.argtypes = [c_ll, c_vp, c_vp, c_vp, c_vp]

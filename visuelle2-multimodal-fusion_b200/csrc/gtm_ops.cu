@@ -328,6 +328,54 @@ bn1d_bwd_apply_kernel(int B, int D, const float* __restrict__ x, const float* __
   }
 }
 
+// ------------------------------------------------------------------ dropout with the keep decisions drawn IN the kernel
+// out = x * keep / (1 - p), keep ~ Bernoulli(1 - p) from Philox4x32-10 keyed by two 64-bit words in DEVICE memory (drawn
+// by the caller from torch's CUDA generator: graph-safe, fresh per replay).  The backward regenerates the same decisions
+// from the same key, so no mask is ever materialised (the reference's nn.Dropout after ImageEncoder.fc alone was a
+// 26 MB fp32 mask written by four elementwise launches and read back twice).  Thread = 4 consecutive elements = one
+// Philox counter.
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                                              uint32_t (&out)[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0;
+    c1 = lo1;
+    c2 = n2;
+    c3 = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  out[0] = c0;
+  out[1] = c1;
+  out[2] = c2;
+  out[3] = c3;
+}
+
+__global__ void dropout_kernel(long long n, const float* __restrict__ x, const unsigned long long* __restrict__ key,
+                               float p, float* __restrict__ out) {
+  const long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long i = i4 * 4;
+  if (i >= n) return;
+  const unsigned long long k = key[0], sq = key[1];
+  uint32_t r[4];
+  philox4x32_10((uint32_t)i4, (uint32_t)(i4 >> 32), (uint32_t)sq, (uint32_t)(sq >> 32), (uint32_t)k, (uint32_t)(k >> 32), r);
+  const float scale = 1.0f / (1.0f - p);
+  const uint32_t thr = (uint32_t)fminf(p * 4294967296.0f, 4294967295.0f);      // keep iff r >= thr
+  if (i + 3 < n) {
+    float4 v = ld4(x + i);
+    v.x = r[0] >= thr ? v.x * scale : 0.f;
+    v.y = r[1] >= thr ? v.y * scale : 0.f;
+    v.z = r[2] >= thr ? v.z * scale : 0.f;
+    v.w = r[3] >= thr ? v.w * scale : 0.f;
+    st4(out + i, v);
+  } else {
+    for (int j = 0; j < 4 && i + j < n; j++) out[i + j] = r[j] >= thr ? x[i + j] * scale : 0.f;
+  }
+}
+
 // ------------------------------------------------------------------ elementwise
 __global__ void gate_fwd_kernel(long long n, const float* __restrict__ x, const float* __restrict__ g,
                                 int mode, float* __restrict__ out) {
@@ -599,6 +647,15 @@ extern "C" int v2f_bn1d_bwd_apply(int B, int D, const float* x, const float* dy,
   V2F_REQUIRE(B > 0 && D > 0 && Btot >= B && x && dy && gamma && save_mean && save_rstd && sums && dx, V2F_ERR_BAD_ARG);
   bn1d_bwd_apply_kernel<<<(D + 31) / 32, dim3(32, 32), 0, (cudaStream_t)st>>>(B, D, x, dy, gamma, save_mean, save_rstd,
                                                                               sums, Btot, dx);
+  V2F_CHECK_LAUNCH();
+  return V2F_OK;
+}
+
+extern "C" int v2f_dropout(long long n, const float* x, const unsigned long long* key, float p, float* out, void* st) {
+  V2F_REQUIRE(n >= 0 && x && key && out && p >= 0.f && p < 1.f, V2F_ERR_BAD_ARG);
+  if (n == 0) return V2F_OK;
+  V2F_REQUIRE(aligned16(x) && aligned16(out), V2F_ERR_ALIGN);
+  dropout_kernel<<<blocks_for((n + 3) / 4), 256, 0, (cudaStream_t)st>>>(n, x, key, p, out);
   V2F_CHECK_LAUNCH();
   return V2F_OK;
 }

@@ -229,9 +229,33 @@ def keep_mask(shape, p, training, device):
     return (torch.rand(shape, device=device) >= p).float().div_(1.0 - p)
 
 
+class _Dropout(torch.autograd.Function):
+    """nn.Dropout with the Bernoulli decisions generated inside the kernel from a 128-bit key in device memory (two
+    int64 drawn from torch's CUDA generator: one tiny launch, graph-safe); the backward replays the same key."""
+
+    @staticmethod
+    def forward(ctx, x, key, p):
+        x = _c(x)
+        out = torch.empty_like(x)
+        check(_lib.lib().v2f_dropout(x.numel(), ptr(x), key.data_ptr(), float(p), ptr(out), stream()), "v2f_dropout")
+        ctx.save_for_backward(key)
+        ctx.p = p
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (key,) = ctx.saved_tensors
+        g = _c(g)
+        out = torch.empty_like(g)
+        check(_lib.lib().v2f_dropout(g.numel(), ptr(g), key.data_ptr(), float(ctx.p), ptr(out), stream()), "v2f_dropout")
+        return out, None, None
+
+
 def dropout(x, p, training):
-    m = keep_mask(x.shape, p, training, x.device)
-    return x if m is None else MaskMul.apply(x, m)
+    if not training or p <= 0.0:
+        return x
+    key = torch.randint(-(1 << 62), 1 << 62, (2,), device=x.device, dtype=torch.int64)
+    return _Dropout.apply(x, key, p)
 
 
 # --------------------------------------------------------------------------- trend_linear re-association

@@ -85,15 +85,22 @@ class GraphedTrainStep:
     """``step = GraphedTrainStep(model, example_batch); loss = step(batch)`` -- same arithmetic as
     ``loss = model.training_step(batch, i); loss.backward()`` with gradients in ``p.grad``."""
 
-    def __init__(self, model, example_batch, warmup=3, reducer=None):
+    def __init__(self, model, example_batch, warmup=3, reducer=None, image_grad=False):
         """``reducer``: a ``ddp.GradReducer`` built with hooks: its bucketed NCCL all-reduces are captured INSIDE
         the graph, on its side stream, so they overlap the rest of the backward exactly as in the eager loop
-        (gradients in ``p.grad`` are already averaged when the replay returns)."""
+        (gradients in ``p.grad`` are already averaged when the replay returns).
+        ``image_grad``: also produce the gradient w.r.t. the batch's image tensor (``self.static_batch[1].grad``) --
+        for callers that feed precomputed feature maps and run the trunk's backward themselves.
+
+        The capture runs on a private stream; the parameters' AccumulateGrad nodes must be created there too, so no
+        autograd graph of an earlier eager step may still be alive (``del loss`` before constructing this)."""
         self.model = model
         self.reducer = reducer
         dev = next(model.parameters()).device
         self.device = dev
         self.static_batch = _tree_map(lambda t: t.to(dev, copy=True), example_batch)
+        if image_grad:
+            self.static_batch[1].requires_grad_(True)
         self.has_tf = hasattr(model, "draw_tf_mask")
         self._tf = _TfWord(dev) if self.has_tf else None      # owned here, not by the module
         self.params = [p for p in model.parameters() if p.requires_grad]
@@ -108,6 +115,8 @@ class GraphedTrainStep:
                     reducer.finish()
                 for p in self.params:
                     p.grad = None
+                if image_grad:
+                    self.static_batch[1].grad = None
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         from . import _lib
@@ -127,7 +136,8 @@ class GraphedTrainStep:
             self._tf.set(self.model.draw_tf_mask(True))
 
     def __call__(self, batch):
-        _tree_copy(self.static_batch, batch)              # device->device (or pinned host->device) into the graph's inputs
+        with torch.no_grad():
+            _tree_copy(self.static_batch, batch)          # device->device (or pinned host->device) into the graph's inputs
         self._refresh_tf()
         self.graph.replay()
         return self.static_loss
