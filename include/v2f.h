@@ -31,7 +31,7 @@ long long v2f_launch_count(void);
 /* Kernel ids for the optional event timing below. */
 enum { V2F_K_ATTN_FWD = 0, V2F_K_ATTN_BWD = 1, V2F_K_TILEGRAD = 2, V2F_K_BN_STATS = 3, V2F_K_BN_APPLY = 4,
        V2F_K_BN_BWD_REDUCE = 5, V2F_K_BN_BWD_ELEMT = 6, V2F_K_DECODE_PERSIST_FWD = 7,
-       V2F_K_DECODE_PERSIST_BWD = 8, V2F_K_COUNT = 9 };
+       V2F_K_DECODE_PERSIST_BWD = 8, V2F_K_STEM_CONV = 9, V2F_K_COUNT = 10 };
 /* Per-kernel CUDA-event timing on the launching stream (bench.py roofline leg).  Off by default.
  * v2f_prof_read sums the spans recorded for one kernel id since the previous read.            */
 int v2f_prof_enable(int on);
@@ -356,6 +356,24 @@ int v2f_bn2d_relu_maxpool_fwd(int N, int H, int W, int C, const void* x, const f
                               const float* beta, float* run_mean, float* run_var, int training,
                               float momentum, float eps, void* y, float* save_mean, float* save_rstd,
                               float* scale_shift, float* part, void* stream);
+/* Same, with the batch statistics already reduced to `part_blocks` partial rows [part_blocks,2,C] (sum, sum of
+ * squares over disjoint row sets) by the producer of x -- the epilogue of v2f_stem_conv_fwd -- so no statistics
+ * sweep over x runs here (training != 0 only). */
+int v2f_bn2d_relu_maxpool_fwd_parts(int N, int H, int W, int C, const void* x, const float* gamma,
+                                    const float* beta, float* run_mean, float* run_var, float momentum, float eps,
+                                    void* y, float* save_mean, float* save_rstd, float* scale_shift,
+                                    const float* part, int part_blocks, void* stream);
+/* Stem convolution conv1 = Conv2d(3, 64, 7, stride 2, padding 3, bias=False) of the torchvision ResNet trunk
+ * (models/CrossAttnRNN210.py:58-65: frozen, forward only) as an implicit GEMM on tcgen05 (csrc/stem_conv.cu).
+ * x: [N,H,W,3] NHWC (a channels_last [N,3,H,W] tensor) or, with x_nchw, plain [N,3,H,W]; fp32 or bf16 (x_bf16); wpk: bf16 [64,192], the weight packed
+ * as wpk[o, kh*24 + kw*3 + c] = w[o,c,kh,kw], zero elsewhere; y: bf16 [N,OH,OW,64] NHWC with OH=(H-1)/2+1,
+ * OW=(W-1)/2+1 (values: fp32 accumulation of bf16 products, rounded to bf16 -- what a bf16 library convolution
+ * returns).  part (optional): [v2f_stem_conv_blocks(...), 2, 64] floats, per-CTA sum / sum of squares of the stored
+ * (rounded) outputs for v2f_bn2d_relu_maxpool_fwd_parts.  v2f_stem_conv_blocks returns 0 for unsupported shapes
+ * (OW < 128 or 3 W > 1024): keep the library convolution there. */
+int v2f_stem_conv_blocks(int N, int H, int W, int x_bf16, int x_nchw);
+int v2f_stem_conv_fwd(int N, int H, int W, const void* x, int x_bf16, int x_nchw, const void* wpk, void* y,
+                      float* part, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Device side of the image transform of dataset_fusion.py:50-65 (ToTensor + Normalize; decode and Resize stay on

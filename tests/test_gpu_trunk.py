@@ -315,3 +315,83 @@ def test_eval_forward_sees_optimizer_updates_of_trainable_trunk_weights():
     assert torch.equal(trunk_params[-1].detach(), w_before)
     assert float((f1 - f2).abs().max()) == 0.0, "eval forward depends on a stale weight cache"
     assert float((f1 - f0).abs().max()) > 0.0, "eval output did not change after three optimizer steps"
+
+
+# ------------------------------------------------------------------ stem convolution on tcgen05 (csrc/stem_conv.cu)
+@pytest.mark.parametrize("nchw", [False, True])
+@pytest.mark.parametrize("N,H,W,in_bf16", [(3, 299, 299, False), (2, 299, 299, True), (2, 300, 300, False),
+                                           (5, 256, 272, False), (1, 261, 341, True)])
+def test_stem_conv_tcgen05_matches_exact_convolution(N, H, W, in_bf16, nchw):
+    """conv1 (7x7, stride 2, pad 3, 3 -> 64) as the tcgen05 implicit GEMM: every output equals the exact (fp64)
+    convolution of the bf16-rounded operands to within one bf16 rounding of the output, and the per-CTA partial
+    statistics of the epilogue are the sums of the STORED values.  Odd / even sizes, partial last tile (N*OH*OW not a
+    multiple of 128), image boundaries inside a tile, fp32 and bf16 inputs."""
+    from visuelle2_multimodal_fusion_b200 import _lib, trunk
+    torch.manual_seed(N * H + W)
+    conv = nn.Conv2d(3, 64, 7, 2, 3, bias=False).cuda()
+    x = torch.randn(N, 3, H, W, device="cuda") * 1.3 + 0.2
+    if not nchw:
+        x = x.contiguous(memory_format=CL)
+    if in_bf16:
+        x = x.bfloat16()
+    assert x.is_contiguous() if nchw else x.is_contiguous(memory_format=CL)
+    nblk = _lib.lib().v2f_stem_conv_blocks(N, H, W, 1 if in_bf16 else 0, 1 if nchw else 0)
+    assert nblk > 0
+    OH, OW = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    y = torch.empty((N, 64, OH, OW), device="cuda", dtype=torch.bfloat16, memory_format=CL)
+    part = torch.full((nblk, 2, 64), float("nan"), device="cuda")
+    pk = trunk._stem_packed_weight(conv)
+    _lib.check(_lib.lib().v2f_stem_conv_fwd(N, H, W, x.data_ptr(), 1 if in_bf16 else 0, 1 if nchw else 0, pk.data_ptr(),
+                                            y.data_ptr(), part.data_ptr(), _lib.stream()), "v2f_stem_conv_fwd")
+    ref = torch.nn.functional.conv2d(x.bfloat16().double(), conv.weight.detach().bfloat16().double(), None, 2, 3)
+    err = (y.double() - ref).abs()
+    tol = ref.abs() * 2.0 ** -8 + 1e-3          # half an ulp of bf16 + fp32 accumulation noise near zero
+    assert bool((err <= tol).all()), float((err - tol).max())
+    s = y.double().sum((0, 2, 3))
+    q = (y.double() ** 2).sum((0, 2, 3))
+    ps = part.double().sum(0)
+    assert _rel(ps[0], s) < 1e-5 and _rel(ps[1], q) < 1e-5
+    # without statistics (eval): same outputs
+    y2 = torch.empty_like(y)
+    _lib.check(_lib.lib().v2f_stem_conv_fwd(N, H, W, x.data_ptr(), 1 if in_bf16 else 0, 1 if nchw else 0, pk.data_ptr(),
+                                            y2.data_ptr(), None, _lib.stream()), "v2f_stem_conv_fwd")
+    assert torch.equal(y, y2)
+
+
+def test_stem_conv_unsupported_shapes_keep_the_library_convolution():
+    from visuelle2_multimodal_fusion_b200 import _lib
+    assert _lib.lib().v2f_stem_conv_blocks(4, 64, 64, 0, 0) == 0          # OW < 128
+    assert _lib.lib().v2f_stem_conv_blocks(4, 299, 400, 0, 1) == 0        # 3 W > 1024
+
+
+@pytest.mark.parametrize("training", [True, False])
+def test_stem_with_tcgen05_conv_equals_stem_with_library_conv(training):
+    """trunk.stem (conv1 -> bn1 -> relu -> maxpool) with conv1 on csrc/stem_conv.cu + statistics from its epilogue vs
+    the same stem with the library convolution + statistics sweep: outputs within bf16 rounding, running statistics
+    equal to fp32 noise."""
+    import torchvision
+    from visuelle2_multimodal_fusion_b200 import trunk
+    torch.manual_seed(11)
+    net = torchvision.models.resnet101(weights=None).cuda().train(training)
+    for p in net.parameters():
+        p.requires_grad_(False)
+    with torch.no_grad():
+        net.bn1.running_mean.uniform_(-0.2, 0.2)
+        net.bn1.running_var.uniform_(0.5, 1.5)
+    x = torch.randn(6, 3, 299, 299, device="cuda")          # NCHW, as a DataLoader collates it
+    outs, stats = [], []
+    state = copy.deepcopy(net.bn1.state_dict())
+    for flag in (True, False):
+        net.bn1.load_state_dict(state)
+        trunk.STEM_CONV_TC = flag
+        trunk._w16 = trunk._bf16_weights([net.conv1])
+        try:
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                outs.append(trunk.stem(net.conv1, net.bn1, net.maxpool, x).float())
+        finally:
+            trunk._w16 = None
+            trunk.STEM_CONV_TC = True
+        stats.append((net.bn1.running_mean.clone(), net.bn1.running_var.clone(), int(net.bn1.num_batches_tracked)))
+    assert outs[0].shape == outs[1].shape == (6, 64, 75, 75)
+    assert _rel(outs[0], outs[1]) < 1.6e-2 and _cos(outs[0], outs[1]) > 0.99999
+    assert _rel(stats[0][0], stats[1][0]) < 1e-4 and _rel(stats[0][1], stats[1][1]) < 1e-4 and stats[0][2] == stats[1][2]

@@ -140,7 +140,12 @@ def _declare(lib):
                                      c_vp, c_vp, c_vp, c_vp, c_vp]
     lib.v2f_bn2d_relu_maxpool_fwd.argtypes = [c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_float,
                                               c_float, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]
-    for name in ("v2f_bn2d_blocks", "v2f_bn2d_act_fwd", "v2f_bn2d_act_bwd", "v2f_bn2d_relu_maxpool_fwd"):
+    lib.v2f_bn2d_relu_maxpool_fwd_parts.argtypes = [c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_float,
+                                                    c_float, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp]
+    lib.v2f_stem_conv_blocks.argtypes = [c_int, c_int, c_int, c_int, c_int]
+    lib.v2f_stem_conv_fwd.argtypes = [c_int, c_int, c_int, c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_vp]
+    for name in ("v2f_bn2d_blocks", "v2f_bn2d_act_fwd", "v2f_bn2d_act_bwd", "v2f_bn2d_relu_maxpool_fwd",
+                 "v2f_bn2d_relu_maxpool_fwd_parts", "v2f_stem_conv_blocks", "v2f_stem_conv_fwd"):
         getattr(lib, name).restype = c_int
     for name in ("v2f_add_ln_fwd", "v2f_add_ln_bwd_blocks", "v2f_add_ln_bwd", "v2f_bn1d_fwd", "v2f_bn1d_bwd",
                  "v2f_gate_fwd", "v2f_gate_bwd", "v2f_add_f32", "v2f_relu_bwd", "v2f_relu_fwd", "v2f_add_bcast", "v2f_copy2d",

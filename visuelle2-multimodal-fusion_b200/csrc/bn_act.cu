@@ -582,20 +582,17 @@ extern "C" int v2f_bn2d_act_bwd(long long R, int C, const void* dy, const void* 
 
 // Stem of the trunk: y = maxpool3x3/2(relu(BN(x))), x bf16 [N,H,W,C], y bf16 [N,OH,OW,C] with
 // OH = (H-1)/2+1, OW = (W-1)/2+1.  Forward only (the stem is frozen in the reference).
-extern "C" int v2f_bn2d_relu_maxpool_fwd(int N, int H, int W, int C, const void* x, const float* gamma,
-                                         const float* beta, float* run_mean, float* run_var, int training,
-                                         float momentum, float eps, void* y, float* save_mean,
-                                         float* save_rstd, float* scale_shift, float* part, void* st) {
-  V2F_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && (C & 7) == 0, V2F_ERR_BAD_ARG);
-  V2F_REQUIRE(x && gamma && beta && y && save_mean && save_rstd && scale_shift && part, V2F_ERR_BAD_ARG);
-  V2F_REQUIRE(training || (run_mean && run_var), V2F_ERR_BAD_ARG);
-  V2F_REQUIRE(aligned16(x) && aligned16(y), V2F_ERR_ALIGN);
-  cudaStream_t s = (cudaStream_t)st;
+// part_blocks > 0: the statistics arrive as that many partial rows from the producer of x (stem_conv.cu).
+static int stem_bn_pool(int N, int H, int W, int C, const void* x, const float* gamma, const float* beta,
+                        float* run_mean, float* run_var, int training, float momentum, float eps, void* y,
+                        float* save_mean, float* save_rstd, float* scale_shift, float* part, int part_blocks,
+                        cudaStream_t s) {
   const long long R = (long long)N * H * W;
   const Geo g = make_geo(C);
-  const int nblk = sweep_blocks(R, C);
-  const size_t smem = sizeof(float) * (size_t)g.RB * 2 * g.CVB * 8;
-  if (training) {
+  int nblk = part_blocks;
+  if (training && part_blocks <= 0) {
+    nblk = sweep_blocks(R, C);
+    const size_t smem = sizeof(float) * (size_t)g.RB * 2 * g.CVB * 8;
     bn_stats_kernel<<<nblk, BN_THREADS, smem, s>>>(R, C, (const uint4*)x, part);
     V2F_CHECK_LAUNCH();
   }
@@ -609,4 +606,27 @@ extern "C" int v2f_bn2d_relu_maxpool_fwd(int N, int H, int W, int C, const void*
       N, H, W, C, OH, OW, (const uint4*)x, scale_shift, scale_shift + C, (uint4*)y);
   V2F_CHECK_LAUNCH();
   return V2F_OK;
+}
+
+extern "C" int v2f_bn2d_relu_maxpool_fwd(int N, int H, int W, int C, const void* x, const float* gamma,
+                                         const float* beta, float* run_mean, float* run_var, int training,
+                                         float momentum, float eps, void* y, float* save_mean,
+                                         float* save_rstd, float* scale_shift, float* part, void* st) {
+  V2F_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && (C & 7) == 0, V2F_ERR_BAD_ARG);
+  V2F_REQUIRE(x && gamma && beta && y && save_mean && save_rstd && scale_shift && part, V2F_ERR_BAD_ARG);
+  V2F_REQUIRE(training || (run_mean && run_var), V2F_ERR_BAD_ARG);
+  V2F_REQUIRE(aligned16(x) && aligned16(y), V2F_ERR_ALIGN);
+  return stem_bn_pool(N, H, W, C, x, gamma, beta, run_mean, run_var, training, momentum, eps, y, save_mean, save_rstd,
+                      scale_shift, part, 0, (cudaStream_t)st);
+}
+
+extern "C" int v2f_bn2d_relu_maxpool_fwd_parts(int N, int H, int W, int C, const void* x, const float* gamma,
+                                               const float* beta, float* run_mean, float* run_var, float momentum,
+                                               float eps, void* y, float* save_mean, float* save_rstd,
+                                               float* scale_shift, const float* part, int part_blocks, void* st) {
+  V2F_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && (C & 7) == 0 && part_blocks > 0, V2F_ERR_BAD_ARG);
+  V2F_REQUIRE(x && gamma && beta && y && save_mean && save_rstd && scale_shift && part, V2F_ERR_BAD_ARG);
+  V2F_REQUIRE(aligned16(x) && aligned16(y), V2F_ERR_ALIGN);
+  return stem_bn_pool(N, H, W, C, x, gamma, beta, run_mean, run_var, 1, momentum, eps, y, save_mean, save_rstd,
+                      scale_shift, const_cast<float*>(part), part_blocks, (cudaStream_t)st);
 }

@@ -50,23 +50,88 @@ def _stem_fusable(conv, bn, pool, x):
         dl == (1, 1) and not pool.ceil_mode and not pool.return_indices
 
 
+STEM_CONV_TC = os.environ.get("V2F_STEM_CONV", "1") != "0"      # A/B switch: 0 keeps conv1 on the library convolution
+_stem_pack_cache = WeakTensorKeyDictionary()                       # conv1.weight -> (version, data_ptr, packed bf16 [64,192])
+
+
+def _stem_packed_weight(conv):
+    """conv1.weight [64,3,7,7] as the K-major operand of csrc/stem_conv.cu: wpk[o, kh*24 + kw*3 + c], zero-padded to
+    [64,192] bf16.  Cached while the (frozen) weight is unchanged."""
+    w = conv.weight
+    hit = _stem_pack_cache.get(w)
+    if hit is not None and hit[0] == w._version and hit[1] == w.data_ptr():
+        return hit[2]
+    with torch.no_grad():
+        k = w.detach().to(torch.bfloat16).permute(0, 2, 3, 1).reshape(64, 7, 21)      # [o, kh, kw*3 + c]
+        pk = torch.zeros(64, 192, device=w.device, dtype=torch.bfloat16)
+        pk[:, :168].view(64, 7, 24)[:, :, :21] = k
+    _stem_pack_cache[w] = (w._version, w.data_ptr(), pk)
+    return pk
+
+
+def _stem_conv_blocks(conv, x):
+    """(CTAs, nchw flag) of the tcgen05 stem convolution for this input; 0 CTAs when conv1 / the input are not what it
+    covers.  The kernel reads the images as they are: fp32 or bf16, channels_last or plain NCHW."""
+    if not (STEM_CONV_TC and x.is_cuda and x.dim() == 4 and x.shape[1] == 3 and conv.bias is None):
+        return 0, 0
+    if (conv.in_channels, conv.out_channels, conv.kernel_size, conv.stride, conv.padding, conv.dilation, conv.groups,
+            conv.padding_mode) != (3, 64, (7, 7), (2, 2), (3, 3), (1, 1), 1, "zeros"):
+        return 0, 0
+    if x.dtype not in (torch.float32, torch.bfloat16):
+        return 0, 0
+    if x.is_contiguous(memory_format=_CL):
+        nchw = 0
+    elif x.is_contiguous():
+        nchw = 1
+    else:
+        return 0, 0
+    N, _, H, W = x.shape
+    return _lib.lib().v2f_stem_conv_blocks(N, H, W, 1 if x.dtype == torch.bfloat16 else 0, nchw), nchw
+
+
 def stem(conv, bn, pool, x):
     """maxpool(relu(bn(conv(x)))) with BN + ReLU + max-pool in one sweep when no gradient flows through the
-    stem (it is frozen in the reference); otherwise BN+ReLU fused and torch's max-pool."""
-    c = _conv(conv, x.to(torch.bfloat16) if (_w16 is not None and conv in _w16) else x)
-    if not _stem_fusable(conv, bn, pool, x) or c.dtype != torch.bfloat16:
-        return pool(bn_act(c, bn, relu=True))
-    c = c.detach()
-    if not c.is_contiguous(memory_format=_CL):
-        c = c.contiguous(memory_format=_CL)
+    stem (it is frozen in the reference); otherwise BN+ReLU fused and torch's max-pool.  At the reference's image
+    size the frozen conv1 itself runs on csrc/stem_conv.cu (tcgen05 implicit GEMM reading the fp32 images directly,
+    batch statistics from its epilogue): no image cast, no statistics sweep."""
+    bf16_mode = _w16 is not None and conv in _w16
+    fusable = _stem_fusable(conv, bn, pool, x)
+    nblk, nchw = _stem_conv_blocks(conv, x) if (bf16_mode and fusable) else (0, 0)
+    use_batch = bn.training or bn.running_mean is None
+    part = None
+    if nblk > 0:
+        N, _, H, W = x.shape
+        OHc, OWc = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+        c = torch.empty((N, 64, OHc, OWc), device=x.device, dtype=torch.bfloat16, memory_format=_CL)
+        part = _f32(nblk * 2 * 64, device=x.device) if use_batch else None
+        xd = x.detach()
+        check(_lib.lib().v2f_stem_conv_fwd(N, H, W, xd.data_ptr(), 1 if xd.dtype == torch.bfloat16 else 0, nchw,
+                                           _stem_packed_weight(conv).data_ptr(), c.data_ptr(),
+                                           ptr(part) if part is not None else None, stream()), "v2f_stem_conv_fwd")
+    else:
+        if not x.is_contiguous(memory_format=_CL):
+            x = x.contiguous(memory_format=_CL)
+        c = _conv(conv, x.to(torch.bfloat16) if bf16_mode else x)
+        if not fusable or c.dtype != torch.bfloat16:
+            return pool(bn_act(c, bn, relu=True))
+        c = c.detach()
+        if not c.is_contiguous(memory_format=_CL):
+            c = c.contiguous(memory_format=_CL)
     N, C, H, W = c.shape
     OH, OW = (H - 1) // 2 + 1, (W - 1) // 2 + 1
     dev = c.device
-    use_batch = bn.training or bn.running_mean is None
     y = torch.empty((N, C, OH, OW), device=dev, dtype=torch.bfloat16, memory_format=_CL)
     mean, rstd, ss = _f32(C, device=dev), _f32(C, device=dev), _f32(2, C, device=dev)
-    part = _f32(max(_lib.lib().v2f_bn2d_blocks(N * H * W, C), 1) * 2 * C, device=dev)
     mom = _count_batch(bn, use_batch, bn.momentum)
+    if part is not None:
+        check(_lib.lib().v2f_bn2d_relu_maxpool_fwd_parts(N, H, W, C, c.data_ptr(), ptr(bn.weight), ptr(bn.bias),
+                                                         ptr(bn.running_mean, allow_none=True),
+                                                         ptr(bn.running_var, allow_none=True),
+                                                         float(mom if mom is not None else 0.0), float(bn.eps),
+                                                         y.data_ptr(), ptr(mean), ptr(rstd), ptr(ss), ptr(part), nblk,
+                                                         stream()), "v2f_bn2d_relu_maxpool_fwd_parts")
+        return y
+    part = _f32(max(_lib.lib().v2f_bn2d_blocks(N * H * W, C), 1) * 2 * C, device=dev)
     check(_lib.lib().v2f_bn2d_relu_maxpool_fwd(N, H, W, C, c.data_ptr(), ptr(bn.weight), ptr(bn.bias),
                                                ptr(bn.running_mean, allow_none=True),
                                                ptr(bn.running_var, allow_none=True), 1 if use_batch else 0,
@@ -308,7 +373,7 @@ def forward(cnn, images):
     """images [B,3,H,W] fp32 (any memory format) -> feature map [B,2048,h,w] bf16 channels_last."""
     global _pending_counters, _w16
     mods = list(cnn.children())
-    x = images.contiguous(memory_format=_CL)
+    x = images                   # the stem reads the images as collated (NCHW or channels_last, fp32 or bf16)
     _pending_counters = []
     blocks = [blk for layer in mods[4:] for blk in layer]
     try:
