@@ -374,6 +374,9 @@ int v2f_bn2d_relu_maxpool_fwd_parts(int N, int H, int W, int C, const void* x, c
 int v2f_stem_conv_blocks(int N, int H, int W, int x_bf16, int x_nchw);
 int v2f_stem_conv_fwd(int N, int H, int W, const void* x, int x_bf16, int x_nchw, const void* wpk, void* y,
                       float* part, void* stream);
+/* Diagnostics: registers, dynamic shared memory and the CTAs/SM the runtime's occupancy calculator reports for the
+ * stem kernel at image width W (it reports 1; the launch uses 2 per SM, which the hardware co-schedules). */
+int v2f_stem_conv_occupancy(int W, int* regs, int* smem_bytes, int* per_sm);
 
 /* ------------------------------------------------------------------------------------------
  * Device side of the image transform of dataset_fusion.py:50-65 (ToTensor + Normalize; decode and Resize stay on

@@ -64,21 +64,6 @@ __device__ __forceinline__ uint32_t sc_swz(int r, int j) {
   return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((j ^ (r & 7)) << 4));
 }
 
-// first / last global input row (g = n * H + ih, source row of the NHWC tensor) a tile reads
-__device__ __forceinline__ void sc_tile_rows(const ScArgs& a, long long t, long long& g_lo, long long& g_hi) {
-  const long long p0 = t * 128;
-  long long p1 = p0 + 127;
-  if (p1 > a.P - 1) p1 = a.P - 1;
-  const long long ra = p0 / a.OW, rb = p1 / a.OW;
-  const long long na = ra / a.OH, nb = rb / a.OH;
-  const int oha = (int)(ra - na * a.OH), ohb = (int)(rb - nb * a.OH);
-  int lo = 2 * oha - 3, hi = 2 * ohb + 3;
-  if (lo < 0) lo = 0;
-  if (hi > a.H - 1) hi = a.H - 1;
-  g_lo = na * a.H + lo;
-  g_hi = nb * a.H + hi;
-}
-
 template <bool IN_BF16>
 __device__ __forceinline__ float sc_load(const void* x, long long idx) {
   if (IN_BF16) return __bfloat162float(__ldg(reinterpret_cast<const __nv_bfloat16*>(x) + idx));
@@ -92,12 +77,39 @@ struct ScLane {
   int off[SC_PF_J];      // source offset inside the row (NHWC) or plane offset c * H * W + iw (NCHW); -1: none
   int pos[SC_PF_J];      // staged position (without the + 9 shift)
 };
+// element offset of input row (n, ih): NHWC: the row's 3 W contiguous values; NCHW: row ih of the image's first plane
 template <bool NCHW>
-__device__ __forceinline__ long long sc_row_base(const ScArgs& a, long long g) {
-  if (!NCHW) return g * (3LL * a.W);
-  const long long n = g / a.H;
-  const int ih = (int)(g - n * a.H);
-  return (n * 3 * a.H + ih) * (long long)a.W;
+__device__ __forceinline__ long long sc_row_base(const ScArgs& a, int n, int ih) {
+  if (!NCHW) return ((long long)n * a.H + ih) * (3LL * a.W);
+  return ((long long)n * 3 * a.H + ih) * (long long)a.W;
+}
+__device__ __forceinline__ void sc_row_adv(const ScArgs& a, int& g, int& n, int& ih) {
+  ++g;
+  if (++ih == a.H) {
+    ih = 0;
+    ++n;
+  }
+}
+
+struct ScPix {
+  int n, oh, ow;
+};
+__device__ __forceinline__ void sc_pix_init(const ScArgs& a, int p, ScPix& px) {
+  const unsigned orow = (unsigned)p / (unsigned)a.OW;
+  px.ow = p - (int)orow * a.OW;
+  px.n = (int)(orow / (unsigned)a.OH);
+  px.oh = (int)orow - px.n * a.OH;
+}
+// + 128 pixels (OW >= 128: at most one output-row wrap)
+__device__ __forceinline__ void sc_pix_adv(const ScArgs& a, ScPix& px) {
+  px.ow += 128;
+  if (px.ow >= a.OW) {
+    px.ow -= a.OW;
+    if (++px.oh >= a.OH) {
+      px.oh = 0;
+      ++px.n;
+    }
+  }
 }
 
 template <bool IN_BF16, bool NCHW>
@@ -108,8 +120,7 @@ __global__ void __launch_bounds__(SC_THREADS, 2) stem_conv_kernel(const ScArgs a
   uint8_t* sB = smem + SC_A_BYTES;
   __nv_bfloat16* rows = reinterpret_cast<__nv_bfloat16*>(smem + SC_A_BYTES + SC_B_BYTES);   // [SC_NSLOT + 1][rowlen]
   const int rowlen = a.rowlen;
-  __nv_bfloat16* zrow = rows + SC_NSLOT * rowlen;
-  uint8_t* tail = reinterpret_cast<uint8_t*>(rows + (SC_NSLOT + 1) * rowlen);
+  uint8_t* tail = reinterpret_cast<uint8_t*>(rows + (SC_NSLOT + 1) * rowlen);      // slot SC_NSLOT stays zero
   tail = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tail) + 15) & ~(uintptr_t)15);
   uint64_t* bar = reinterpret_cast<uint64_t*>(tail);
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tail + 8);
@@ -164,79 +175,86 @@ __global__ void __launch_bounds__(SC_THREADS, 2) stem_conv_kernel(const ScArgs a
   const uint32_t tmem_d = *tmem_ptr;
   const uint32_t idesc = umma_idesc<0>(SC_COUT);
 
-  const long long t0 = (long long)blockIdx.x * a.ntiles / gridDim.x;
-  const long long t1 = (long long)(blockIdx.x + 1) * a.ntiles / gridDim.x;
+  const int t0 = (int)((long long)blockIdx.x * a.ntiles / gridDim.x);
+  const int t1 = (int)((long long)(blockIdx.x + 1) * a.ntiles / gridDim.x);
   float sacc = 0.f, qacc = 0.f;        // lane l of warp (q, half): channel half * 32 + l over the rows of quarter q
   uint32_t phase = 0;
+  const int P = (int)a.P;              // < 2^31 (checked by the host): all index arithmetic below is 32-bit
+  const int ntiles = (int)a.ntiles;
 
-  long long staged_hi = 0;             // rows [.., staged_hi) of this CTA's range are staged
+  // pixel cursors (n, oh, ow), advanced by 128 pixels per tile without divisions (OW >= 128: at most one row wrap):
+  // the tile's first and last pixel (-> the input rows it needs) and this thread's own gather pixel
+  ScPix pxa, pxb, pxr;
+  // staging cursor: the next input row (g = n * H + ih) this CTA has not fetched yet
+  int cur_g = 0, cur_n = 0, cur_ih = 0;
   float pf[SC_PF_ROWS][SC_PF_J];
-  long long pf_g0 = 0;
-  int pf_n = 0;
+  int pf_g0 = 0, pf_n = 0;
   if (t0 < t1) {
-    long long glo, ghi;
-    sc_tile_rows(a, t0, glo, ghi);
-    staged_hi = glo;
+    sc_pix_init(a, t0 * 128, pxa);
+    sc_pix_init(a, min(t0 * 128 + 127, P - 1), pxb);
+    sc_pix_init(a, min(t0 * 128 + (tid & 127), P - 1), pxr);
+    cur_n = pxa.n;
+    cur_ih = max(2 * pxa.oh - 3, 0);
+    cur_g = cur_n * a.H + cur_ih;
   }
 
-  for (long long t = t0; t < t1; t++) {
-    long long glo, ghi;
-    sc_tile_rows(a, t, glo, ghi);
+  for (int t = t0; t < t1; t++) {
+    const int ghi = pxb.n * a.H + min(2 * pxb.oh + 3, a.H - 1);
     // ---- stage the rows this tile adds: the prefetched ones from registers, any others synchronously
     if (pf_n > 0) {
 #pragma unroll
       for (int i = 0; i < SC_PF_ROWS; i++) {
         if (i < pf_n) {
-          __nv_bfloat16* dst = rows + (int)((pf_g0 + i) % SC_NSLOT) * rowlen + 9;
+          __nv_bfloat16* dst = rows + ((pf_g0 + i) & (SC_NSLOT - 1)) * rowlen + 9;
 #pragma unroll
           for (int j = 0; j < SC_PF_J; j++)
             if (ln.off[j] >= 0) dst[ln.pos[j]] = __float2bfloat16_rn(pf[i][j]);
         }
       }
-      staged_hi = pf_g0 + pf_n;
       pf_n = 0;
     }
-    for (long long g = staged_hi; g <= ghi; g++) {
-      __nv_bfloat16* dst = rows + (int)(g % SC_NSLOT) * rowlen + 9;
-      const long long src = sc_row_base<NCHW>(a, g);
+    while (cur_g <= ghi) {
+      __nv_bfloat16* dst = rows + (cur_g & (SC_NSLOT - 1)) * rowlen + 9;
+      const long long src = sc_row_base<NCHW>(a, cur_n, cur_ih);
 #pragma unroll
       for (int j = 0; j < SC_PF_J; j++)
         if (ln.off[j] >= 0) dst[ln.pos[j]] = __float2bfloat16_rn(sc_load<IN_BF16>(a.x, src + ln.off[j]));
+      sc_row_adv(a, cur_g, cur_n, cur_ih);
     }
-    if (staged_hi < ghi + 1) staged_hi = ghi + 1;
     __syncthreads();
 
     // ---- gather the A tile: thread = (pixel r, half of the 21 chunks)
     {
       const int r = tid & 127, hf = tid >> 7;
-      const long long p = t * 128 + r;
-      if (p < a.P) {
-        const long long orow = p / a.OW;
-        const int ow = (int)(p - orow * a.OW);
-        const long long n = orow / a.OH;
-        const int oh = (int)(orow - n * a.OH);
+      if (t * 128 + r < P) {
         const int kc0 = hf ? 11 : 0, kc1 = hf ? SC_CHUNKS : 11;
+        const int gbase = pxr.n * a.H + 2 * pxr.oh - 3;
+        const int ih0 = 2 * pxr.oh - 3;
+        const __nv_bfloat16* colbase = rows + 6 * pxr.ow;
+        int kh = hf ? 3 : 0, c = hf ? 2 : 0;               // chunk 11 = (kh 3, c 2)
         for (int kc = kc0; kc < kc1; kc++) {
-          const int kh = kc / 3, c = kc - kh * 3;
-          const int ih = 2 * oh - 3 + kh;
-          const __nv_bfloat16* srow =
-              (ih < 0 || ih >= a.H) ? zrow : rows + (int)((n * a.H + ih) % SC_NSLOT) * rowlen;
-          const uint32_t* s32 = reinterpret_cast<const uint32_t*>(srow + 6 * ow + 8 * c);
+          const int ih = ih0 + kh;
+          const int slot = (ih < 0 || ih >= a.H) ? SC_NSLOT : ((gbase + kh) & (SC_NSLOT - 1));
+          const uint32_t* s32 = reinterpret_cast<const uint32_t*>(colbase + slot * rowlen + 8 * c);
           uint4 v;
           v.x = s32[0];
           v.y = s32[1];
           v.z = s32[2];
           v.w = s32[3];
           *reinterpret_cast<uint4*>(sA + (kc >> 3) * SC_A_ATOM + sc_swz(r, kc & 7)) = v;
+          if (++c == 3) {
+            c = 0;
+            ++kh;
+          }
         }
       }
     }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    tc_fence_before();
     __syncthreads();
 
-    // ---- multiply: one thread, 11 k-steps; the rows of the next tile are fetched meanwhile
+    // ---- multiply: one thread publishes the tile to the async proxy and issues the 11 k-steps; the rows of the next
+    // tile are fetched into registers meanwhile
     if (tid == 0) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       tc_fence_after();
 #pragma unroll
       for (int ks = 0; ks < SC_KSTEPS; ks++) {
@@ -246,20 +264,24 @@ __global__ void __launch_bounds__(SC_THREADS, 2) stem_conv_kernel(const ScArgs a
       }
       umma_commit(bar);
     }
+    sc_pix_adv(a, pxa);
+    sc_pix_adv(a, pxb);
+    sc_pix_adv(a, pxr);
     if (t + 1 < t1) {
-      long long nlo, nhi;
-      sc_tile_rows(a, t + 1, nlo, nhi);
-      long long cnt = nhi + 1 - staged_hi;
+      if (t + 2 == ntiles && (t + 1) * 128 + 127 >= P) sc_pix_init(a, P - 1, pxb);      // partial last tile
+      const int nhi = pxb.n * a.H + min(2 * pxb.oh + 3, a.H - 1);
+      int cnt = nhi + 1 - cur_g;
       if (cnt > SC_PF_ROWS) cnt = SC_PF_ROWS;
       if (cnt > 0) {
-        pf_g0 = staged_hi;
-        pf_n = (int)cnt;
+        pf_g0 = cur_g;
+        pf_n = cnt;
 #pragma unroll
         for (int i = 0; i < SC_PF_ROWS; i++) {
           if (i < pf_n) {
-            const long long src = sc_row_base<NCHW>(a, pf_g0 + i);
+            const long long src = sc_row_base<NCHW>(a, cur_n, cur_ih);
 #pragma unroll
             for (int j = 0; j < SC_PF_J; j++) pf[i][j] = ln.off[j] >= 0 ? sc_load<IN_BF16>(a.x, src + ln.off[j]) : 0.f;
+            sc_row_adv(a, cur_g, cur_n, cur_ih);
           }
         }
       }
@@ -271,8 +293,8 @@ __global__ void __launch_bounds__(SC_THREADS, 2) stem_conv_kernel(const ScArgs a
     tc_fence_after();
     {
       const int q = warp & 3, half = warp >> 2;
-      const long long p = t * 128 + q * 32 + lane;
-      const bool ok = p < a.P;
+      const int p = t * 128 + q * 32 + lane;
+      const bool ok = p < P;
       uint32_t v[32];
       const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 32);
 #pragma unroll
@@ -296,7 +318,7 @@ __global__ void __launch_bounds__(SC_THREADS, 2) stem_conv_kernel(const ScArgs a
         f[2 * i + 1] = ok ? fb.y : 0.f;
       }
       if (ok) {
-        uint4* dst = reinterpret_cast<uint4*>(a.y + p * SC_COUT + half * 32);
+        uint4* dst = reinterpret_cast<uint4*>(a.y + (long long)p * SC_COUT + half * 32);
 #pragma unroll
         for (int i = 0; i < 4; i++) dst[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
       }
@@ -360,10 +382,12 @@ static int sc_grid(size_t smem) {
   if (cached_smem == (int)smem) return cached;
   auto kern = stem_conv_kernel<IN_BF16, NCHW>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
-  int per_sm = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, SC_THREADS, smem) != cudaSuccess || per_sm < 1)
-    return 0;
-  if (per_sm > 2) per_sm = 2;
+  // two CTAs per SM need the full shared-memory carve-out (2 x 108 KB at W = 299)
+  cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  // residency by the real limits (<= 128 registers x 256 threads, shared memory incl. the 1 KB the system reserves per
+  // CTA, 64 of 512 TMEM columns): the runtime's occupancy calculator reports 1 CTA/SM for this kernel at any
+  // shared-memory size, the hardware co-schedules two
+  const int per_sm = 2 * (smem + 1024) <= 228 * 1024 ? 2 : 1;
   int dev = 0, sms = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -382,6 +406,7 @@ extern "C" int v2f_stem_conv_blocks(int N, int H, int W, int x_bf16, int x_nchw)
   if (N <= 0 || H < 7 || W < 7) return 0;
   const int OW = (W - 1) / 2 + 1, OH = (H - 1) / 2 + 1;
   if (OW < 128 || 3 * W > SC_PF_J * SC_THREADS) return 0;      // a tile spans at most two output rows; register prefetch
+  if ((long long)N * OH * OW + 128 >= (1LL << 31) || (long long)N * H >= (1LL << 31)) return 0;   // 32-bit index arithmetic
   const size_t smem = sc_smem(sc_rowlen(W, OW));
   if (smem > 227 * 1024) return 0;
   const long long ntiles = ((long long)N * OH * OW + 127) / 128;
@@ -389,6 +414,23 @@ extern "C" int v2f_stem_conv_blocks(int N, int H, int W, int x_bf16, int x_nchw)
                        : (x_nchw ? sc_grid<false, true>(smem) : sc_grid<false, false>(smem));
   if (g > ntiles) g = ntiles;
   return (int)g;
+}
+
+// diagnostics (tools/stem_probe.py): occupancy the runtime reports for the fp32-NCHW instantiation
+extern "C" int v2f_stem_conv_occupancy(int W, int* regs, int* smem_bytes, int* per_sm) {
+  auto kern = stem_conv_kernel<false, true>;
+  const int OW = (W - 1) / 2 + 1;
+  const size_t smem = sc_smem(sc_rowlen(W, OW));
+  cudaFuncAttributes fa;
+  if (cudaFuncGetAttributes(&fa, kern) != cudaSuccess) return V2F_ERR_LAUNCH;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  int n = 0;
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, SC_THREADS, smem);
+  *regs = fa.numRegs;
+  *smem_bytes = (int)smem + (int)fa.sharedSizeBytes;
+  *per_sm = e == cudaSuccess ? n : -(int)e;
+  return V2F_OK;
 }
 
 extern "C" int v2f_stem_conv_fwd(int N, int H, int W, const void* x, int x_bf16, int x_nchw, const void* wpk, void* y,
