@@ -589,13 +589,15 @@ def _bn_passes(r, roof):
     torch.cuda.synchronize()
     _lib.prof_enable(False)
     for name, kid in (("bn_stats_kernel", _lib.K_BN_STATS), ("bn_apply_kernel", _lib.K_BN_APPLY),
-                      ("bn_bwd_reduce_kernel", _lib.K_BN_BWD_REDUCE), ("bn_bwd_elemt_kernel", _lib.K_BN_BWD_ELEMT)):
+                      ("bn_bwd_reduce_kernel", _lib.K_BN_BWD_REDUCE), ("bn_bwd_elemt_kernel", _lib.K_BN_BWD_ELEMT),
+                      ("stem_conv_kernel", _lib.K_STEM_CONV)):
         tot, n, nbytes = _lib.prof_read_bytes(kid)
         if n == 0:
             continue
         ach = nbytes / (tot * 1e-3) / 1e9
+        traffic, tsrc = _traffic(name) if name == "stem_conv_kernel" else (None, None)
         roof[name] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                      "traffic": None, "kernel": name, "avg_launch_us": tot / n * 1e3,
+                      "traffic": traffic, "traffic_source": tsrc, "kernel": name, "avg_launch_us": tot / n * 1e3,
                       "launches_per_step": n / 2, "algorithmic_bytes_per_step": nbytes / 2,
                       "ms_per_step": tot / 2, "peak_source": peak_src,
                       "timing": "CUDA events on the launching stream around each launch, full-model pass"}

@@ -10,8 +10,8 @@ import bench  # noqa: E402
 
 steps = int(sys.argv[sys.argv.index("--steps") + 1]) if "--steps" in sys.argv else 2
 dev = "cuda:0"
-model = bench._build_model(dev, "bf16")
-d, im = bench._batch(128, seed=21)
+model = bench._build_model("rnn210", dev, "bf16")
+d, im = bench._batch("rnn210", 128, seed=21)
 batch = (tuple(t.to(dev) for t in d), im.to(dev))
 params = [p for p in model.parameters() if p.requires_grad]
 for i in range(steps):

@@ -203,7 +203,7 @@ def launch_count():
 
 
 (K_ATTN_FWD, K_ATTN_BWD, K_TILEGRAD, K_BN_STATS, K_BN_APPLY, K_BN_BWD_REDUCE, K_BN_BWD_ELEMT, K_DECODE_PERSIST_FWD,
- K_DECODE_PERSIST_BWD) = range(9)
+ K_DECODE_PERSIST_BWD, K_STEM_CONV) = range(10)
 
 
 def prof_enable(on):

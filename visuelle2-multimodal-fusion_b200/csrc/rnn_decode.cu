@@ -507,12 +507,17 @@ struct TileGradArgs {
 // pairs of the item, so H is read once and dH / dV are written once.  The kernel is MUFU-bound, not HBM-bound
 // (B*L*E*T tanh evaluations): in tensor-core mode the single-instruction tanh.approx (the forward's choice there)
 // halves the MUFU work; the exact mode keeps the two-instruction form.
+constexpr int TG_CHUNK = 32;   // (step, row) pairs whose attention scalars are staged at once
 template <bool APPROX, int CPTG>
 __global__ void __launch_bounds__(256)
 tilegrad_kernel(TileGradArgs a) {
-  __shared__ float al_sh[2][TG_J], de_sh[2][TG_J];
+  // alpha / de of the CTA's 13 positions for a whole chunk of (step, row) pairs are staged up front, so the loop over
+  // the pairs has no barrier and the compiler can keep the next pairs' s / dC loads in flight under the tanh work
+  // (one barrier + two dependent global loads per pair left the MUFU pipe 25 % busy)
+  __shared__ float al_sh[TG_CHUNK][TG_J], de_sh[TG_CHUNK][TG_J];
   const int b = blockIdx.x, j0 = blockIdx.y * TG_J, E = a.E, L = a.L;
   const int nj = min(TG_J, L - j0);
+  const int iters = a.T * a.W;
   for (int x0 = 0; x0 < E; x0 += 256 * CPTG) {
     float h[CPTG][TG_J], accH[CPTG][TG_J], accV[CPTG][TG_J], wx[CPTG];
     bool act[CPTG];
@@ -528,33 +533,37 @@ tilegrad_kernel(TileGradArgs a) {
         accV[i][jj] = 0.f;
       }
     }
-    const int iters = a.T * a.W;
-    __syncthreads();                       // the previous x0 pass is done with the staging buffers
-    for (int it = 0; it < iters; it++) {
-      const int t = it / a.W, wi = it - t * a.W;
-      const long long tn = (long long)t * a.N + b * a.W + wi;
-      const int buf = it & 1;              // double-buffered scalars: one barrier per (step, row)
-      if (threadIdx.x < TG_J) {
-        const int jj = threadIdx.x;
-        al_sh[buf][jj] = jj < nj ? a.alpha[tn * L + j0 + jj] : 0.f;
-        de_sh[buf][jj] = jj < nj ? a.DE[tn * L + j0 + jj] : 0.f;
-      }
-      float s[CPTG], dc[CPTG];
-#pragma unroll
-      for (int i = 0; i < CPTG; i++) {
-        const int x = x0 + threadIdx.x + 256 * i;
-        s[i] = act[i] ? a.S_all[tn * a.ldS + a.mod * E + x] : 0.f;
-        dc[i] = act[i] ? a.DC_all[(tn * 2 + a.mod) * E + x] : 0.f;
+    for (int c0 = 0; c0 < iters; c0 += TG_CHUNK) {
+      const int cn = min(TG_CHUNK, iters - c0);
+      __syncthreads();                     // the previous chunk / x0 pass is done with the staging buffers
+      for (int k = threadIdx.x; k < cn * TG_J; k += 256) {
+        const int ii = k / TG_J, jj = k - ii * TG_J;
+        const int it = c0 + ii, t = it / a.W, wi = it - t * a.W;
+        const long long tn = (long long)t * a.N + b * a.W + wi;
+        al_sh[ii][jj] = jj < nj ? a.alpha[tn * L + j0 + jj] : 0.f;
+        de_sh[ii][jj] = jj < nj ? a.DE[tn * L + j0 + jj] : 0.f;
       }
       __syncthreads();
+#pragma unroll 2
+      for (int ii = 0; ii < cn; ii++) {
+        const int it = c0 + ii, t = it / a.W, wi = it - t * a.W;
+        const long long tn = (long long)t * a.N + b * a.W + wi;
+        float s[CPTG], dc[CPTG];
 #pragma unroll
-      for (int i = 0; i < CPTG; i++)
-#pragma unroll
-        for (int jj = 0; jj < TG_J; jj++) {
-          const float q = tanh_fast<APPROX>(h[i][jj] + s[i]);
-          accH[i][jj] = fmaf(de_sh[buf][jj], fmaf(-q, q, 1.f), accH[i][jj]);
-          accV[i][jj] = fmaf(al_sh[buf][jj], dc[i], accV[i][jj]);
+        for (int i = 0; i < CPTG; i++) {
+          const int x = x0 + threadIdx.x + 256 * i;
+          s[i] = act[i] ? __ldg(a.S_all + tn * a.ldS + a.mod * E + x) : 0.f;
+          dc[i] = act[i] ? __ldg(a.DC_all + (tn * 2 + a.mod) * E + x) : 0.f;
         }
+#pragma unroll
+        for (int i = 0; i < CPTG; i++)
+#pragma unroll
+          for (int jj = 0; jj < TG_J; jj++) {
+            const float q = tanh_fast<APPROX>(h[i][jj] + s[i]);
+            accH[i][jj] = fmaf(de_sh[ii][jj], fmaf(-q, q, 1.f), accH[i][jj]);
+            accV[i][jj] = fmaf(al_sh[ii][jj], dc[i], accV[i][jj]);
+          }
+      }
     }
 #pragma unroll
     for (int i = 0; i < CPTG; i++) {
