@@ -62,6 +62,32 @@ def _peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def _tensor_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["bf16_tflops_sustained"]), "measured (MEASURED_PEAKS.json bf16_tflops_sustained: kernels timed inside a step)"
+    return 1384.8, "fallback (B200_PROFILING.md)"
+
+
+def _gemm_tc_entry(nsteps):
+    """The tcgen05 GEMM launches (csrc/gemm_tc.cu) recorded since the last read: FLOPs summed by the library
+    (2 M N K per problem) over the summed launch durations, against the measured dense bf16 throughput."""
+    from visuelle2_multimodal_fusion_b200 import _lib
+    tot, n, flops = _lib.prof_read_bytes(_lib.K_GEMM_TC)
+    if n == 0:
+        return None
+    peak, src = _tensor_peak()
+    ach = flops / (tot * 1e-3) / 1e12
+    return {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+            "kernel": "gemm_tc_kernel", "launches_per_step": n / nsteps, "avg_launch_us": tot / n * 1e3,
+            "gflop_per_step": flops / nsteps / 1e9, "ms_per_step": tot / nsteps, "peak_source": src,
+            "note": "bf16 operands on the backbone features, tf32 on fp32 data (half the bf16 rate); M = 128 .. 12800 rows: "
+                    "launch- and tail-bound, not tensor-pipe bound (SURVEY 8d expects exactly that)",
+            "timing": "CUDA events on the launching stream around each launch, eager head-only pass"}
+
+
 def _build_model(name, device, precision):
     import visuelle2_multimodal_fusion_b200.synth as synth
     from visuelle2_multimodal_fusion_b200.models import CrossAttnRNN21, CrossAttnRNN210, CrossAttnRNNDemand
@@ -543,6 +569,9 @@ def _roofline_passes(r, args, nsteps):
                       "traffic": traffic, "traffic_source": tsrc, "kernel": name, "avg_launch_us": avg_ms * 1e3,
                       "launches_per_step": n / nprof, "algorithmic_bytes_per_launch": bytes_per_launch,
                       "peak_source": peak_src, "timing": timing}
+    g = _gemm_tc_entry(nprof)
+    if g is not None:
+        roof["gemm_tc_kernel"] = g
     for kname in ("decode_persist_fwd_kernel", "decode_persist_bwd_kernel"):
         if kname in roof and team:
             rr = roof[kname]
@@ -557,7 +586,7 @@ def _roofline_passes(r, args, nsteps):
     if "decode_persist_fwd_kernel" in roof and phases:
         rr = roof["decode_persist_fwd_kernel"]
         rr["phases_us_per_step"] = {k: {"work": round(w, 2), "barrier_wait": round(b, 2)} for k, (w, b) in phases.items()}
-        rr["decoder"] = "row-team tcgen05 kernel (csrc/decode_team.cu)" if len(phases) == 5 else "column-split kernel (csrc/decode_persist.cu)"
+        rr["decoder"] = "row-team tcgen05 kernel (csrc/decode_team.cu)" if team else "column-split kernel (csrc/decode_persist.cu)"
         if "P2 attention sweep" in phases:
             w, b = phases["P2 attention sweep"]
             pa = (tile_bytes + small) / ((w + b) * 1e-6) / 1e9
@@ -603,6 +632,7 @@ def _bn_passes(r, roof):
                       "timing": "CUDA events on the launching stream around each launch, full-model pass"}
     for kid in (_lib.K_ATTN_FWD, _lib.K_ATTN_BWD, _lib.K_TILEGRAD, _lib.K_DECODE_PERSIST_FWD, _lib.K_DECODE_PERSIST_BWD):
         _lib.prof_read(kid)          # drop the head spans of this pass
+    _lib.prof_read_bytes(_lib.K_GEMM_TC)
 
 
 def _forecast_pass(env, name, B, steps, cpu):
@@ -748,6 +778,14 @@ def run_product(args):
             ro.to_eager()
             ro.head_setup()
             hm = ro.head_ms(k_other)
+            _lib.prof_enable(True)                      # two eager head-only steps: the tcgen05 GEMMs of this head
+            for i in range(2):
+                ro.step_head(i)
+            torch.cuda.synchronize()
+            _lib.prof_enable(False)
+            head_gemm = _gemm_tc_entry(2)
+            for kid in range(_lib.K_GEMM_TC):
+                _lib.prof_read(kid)
             ro.head_restore()
             torch.cuda.set_stream(default_stream)
             tot = B * world * k_other
@@ -757,7 +795,8 @@ def run_product(args):
                                    "h2d_bytes_per_step": ro.h2d, "d2h_bytes_per_step": 4},
                            "head_only": {"ms_per_step": hm, "value": B * world / (hm * 1e-3), "unit": "samples/s",
                                          "eager_median_ms": ro.head_eager_ms,
-                                         "note": "feature maps in, gradient w.r.t. them out; CUDA-graph replay"},
+                                         "note": "feature maps in, gradient w.r.t. them out; CUDA-graph replay",
+                                         "gemm_tc": head_gemm},
                            "gpu_launches_per_step": lp,
                            "cpu_baseline": _cpu_sample(name, 16, threads, n_it=1) if want_cpu else None}
             ro.close()

@@ -31,7 +31,7 @@ long long v2f_launch_count(void);
 /* Kernel ids for the optional event timing below. */
 enum { V2F_K_ATTN_FWD = 0, V2F_K_ATTN_BWD = 1, V2F_K_TILEGRAD = 2, V2F_K_BN_STATS = 3, V2F_K_BN_APPLY = 4,
        V2F_K_BN_BWD_REDUCE = 5, V2F_K_BN_BWD_ELEMT = 6, V2F_K_DECODE_PERSIST_FWD = 7,
-       V2F_K_DECODE_PERSIST_BWD = 8, V2F_K_STEM_CONV = 9, V2F_K_COUNT = 10 };
+       V2F_K_DECODE_PERSIST_BWD = 8, V2F_K_STEM_CONV = 9, V2F_K_GEMM_TC = 10, V2F_K_COUNT = 11 };
 /* Per-kernel CUDA-event timing on the launching stream (bench.py roofline leg).  Off by default.
  * v2f_prof_read sums the spans recorded for one kernel id since the previous read.            */
 int v2f_prof_enable(int on);
@@ -341,6 +341,9 @@ int v2f_meanpool_bwd(int B, int L, int C, const float* dout, int layout, int kin
  * stored (bf16 [R,C]).  dx = gamma*rstd*(dz - mean(dz) - xhat*mean(dz*xhat)) (training) or
  * gamma*rstd*dz (eval); dgamma = sum dz*xhat, dbeta = sum dz.                                   */
 int v2f_bn2d_blocks(long long R, int C);
+/* A/B switch (default on): the kernels of one call (statistics -> finalize -> apply; reduce -> finalize -> elemt) are
+ * chained by programmatic dependent launch, so each successor's launch overlaps its predecessor's tail. */
+int v2f_bn2d_pdl_enable(int on);
 int v2f_bn2d_act_fwd(long long R, int C, const void* x, const void* res, const float* gamma,
                      const float* beta, float* run_mean, float* run_var, int training, float momentum,
                      float eps, int relu, void* y, float* save_mean, float* save_rstd,

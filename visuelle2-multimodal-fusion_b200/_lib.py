@@ -142,6 +142,8 @@ def _declare(lib):
                                               c_float, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]
     lib.v2f_bn2d_relu_maxpool_fwd_parts.argtypes = [c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_float,
                                                     c_float, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp]
+    lib.v2f_bn2d_pdl_enable.argtypes = [c_int]
+    lib.v2f_bn2d_pdl_enable.restype = c_int
     lib.v2f_stem_conv_blocks.argtypes = [c_int, c_int, c_int, c_int, c_int]
     lib.v2f_stem_conv_fwd.argtypes = [c_int, c_int, c_int, c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_vp]
     for name in ("v2f_bn2d_blocks", "v2f_bn2d_act_fwd", "v2f_bn2d_act_bwd", "v2f_bn2d_relu_maxpool_fwd",
@@ -203,7 +205,7 @@ def launch_count():
 
 
 (K_ATTN_FWD, K_ATTN_BWD, K_TILEGRAD, K_BN_STATS, K_BN_APPLY, K_BN_BWD_REDUCE, K_BN_BWD_ELEMT, K_DECODE_PERSIST_FWD,
- K_DECODE_PERSIST_BWD, K_STEM_CONV) = range(10)
+ K_DECODE_PERSIST_BWD, K_STEM_CONV, K_GEMM_TC) = range(11)
 
 
 def prof_enable(on):

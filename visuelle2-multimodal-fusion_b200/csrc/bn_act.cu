@@ -23,6 +23,32 @@ namespace v2f {
 
 constexpr int BN_THREADS = 256;
 
+// Programmatic dependent launch inside the stats -> finalize -> apply (and reduce -> finalize -> elemt) chains: a
+// kernel of the chain tells the scheduler at its start that its successor may be made resident (launch_dependents),
+// and the successor blocks at pdl_wait() until the predecessor grid has completed and its writes are visible.  The
+// launch latency and ramp-up of ~370 small launches per step then overlap the predecessor's tail.  Both instructions
+// are no-ops for a kernel launched without the attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+static bool g_bn_pdl = true;
+
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_chain(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, bool dependent,
+                                Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (dependent && g_bn_pdl) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 struct __align__(16) bf16x8 { __nv_bfloat162 a, b, c, d; };
 
 __device__ __forceinline__ void unpack8(const uint4& u, float* f) {
@@ -68,6 +94,7 @@ __host__ __device__ inline Geo make_geo(int C) {
 __global__ void __launch_bounds__(BN_THREADS)
 bn_stats_kernel(long long R, int C, const uint4* __restrict__ x, float* __restrict__ part) {
   extern __shared__ float sm[];   // [RB][2][CVB*8]
+  pdl_launch_dependents();        // the finalize kernel may become resident while this sweep runs
   const Geo g = make_geo(C);
   const int vcol = threadIdx.x % g.CVB, roff = threadIdx.x / g.CVB;
   for (int v0 = 0; v0 < g.CV; v0 += g.CVB) {
@@ -182,6 +209,8 @@ __global__ void bn_fwd_finalize_kernel(long long R, int C, int nblk, const float
                                        float* __restrict__ save_rstd) {
   const int c = blockIdx.x * FIN_X + threadIdx.x;
   double S = 0.0, Q = 0.0;
+  pdl_launch_dependents();
+  pdl_wait();                     // the statistics sweep (or the stem convolution) has completed
   if (training) merge_partials(C, c, nblk, part, S, Q);
   if (c >= C || threadIdx.y != 0) return;
   float mean, var;
@@ -216,6 +245,7 @@ bn_apply_kernel(long long R, int C, const uint4* __restrict__ x, const uint4* __
                 const float* __restrict__ scale, const float* __restrict__ shift, uint4* __restrict__ y) {
   const Geo g = make_geo(C);
   const int vcol = threadIdx.x % g.CVB, roff = threadIdx.x / g.CVB;
+  pdl_wait();                     // scale / shift come from the finalize kernel
   if (roff >= g.RB) return;
   for (int v0 = 0; v0 < g.CV; v0 += g.CVB) {
     const int v = v0 + vcol;
@@ -265,6 +295,7 @@ bn_bwd_reduce_kernel(long long R, int C, const uint4* __restrict__ dy, const uin
   extern __shared__ float sm[];
   const Geo g = make_geo(C);
   const int vcol = threadIdx.x % g.CVB, roff = threadIdx.x / g.CVB;
+  pdl_launch_dependents();
   for (int v0 = 0; v0 < g.CV; v0 += g.CVB) {
     const int v = v0 + vcol;
     float s[8], q[8], mu[8], rs[8];
@@ -336,6 +367,8 @@ __global__ void bn_bwd_finalize_kernel(long long R, int C, int nblk, const float
                                        float* __restrict__ coef) {
   const int c = blockIdx.x * FIN_X + threadIdx.x;
   double S, Q;
+  pdl_launch_dependents();
+  pdl_wait();
   merge_partials(C, c, nblk, part, S, Q);
   if (c >= C || threadIdx.y != 0) return;
   dbeta[c] = (float)S;
@@ -355,6 +388,7 @@ bn_bwd_elemt_kernel(long long R, int C, const uint4* __restrict__ dy, const uint
                     const uint4* __restrict__ y, const float* __restrict__ coef, uint4* __restrict__ dx) {
   const Geo g = make_geo(C);
   const int vcol = threadIdx.x % g.CVB, roff = threadIdx.x / g.CVB;
+  pdl_wait();                     // coefficients (and dz) come from the finalize / reduce kernels
   if (roff >= g.RB) return;
   constexpr int UN = (RELU && !HAVE_DZ) ? 2 : 3;      // 16-byte loads in flight per thread: 6
   for (int v0 = 0; v0 < g.CV; v0 += g.CVB) {
@@ -415,6 +449,7 @@ bn_relu_maxpool_kernel(int N, int H, int W, int C, int OH, int OW, const uint4* 
   const int CV = C / 8;
   const long long total = (long long)N * OH * OW * CV;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  pdl_wait();
   if (i >= total) return;
   const int v = (int)(i % CV);
   long long p = i / CV;
@@ -483,6 +518,12 @@ static inline int sweep_blocks(long long R, int C) {
 
 using namespace v2f;
 
+// A/B switch (default 1): 0 launches the chains without programmatic dependent launch.
+extern "C" int v2f_bn2d_pdl_enable(int on) {
+  g_bn_pdl = on != 0;
+  return V2F_OK;
+}
+
 extern "C" int v2f_bn2d_blocks(long long R, int C) {
   if (R <= 0 || C <= 0 || (C & 7)) return 0;
   return sweep_blocks(R, C);
@@ -508,17 +549,18 @@ extern "C" int v2f_bn2d_act_fwd(long long R, int C, const void* x, const void* r
     prof_end(V2F_K_BN_STATS, s);
     V2F_CHECK_LAUNCH();
   }
-  bn_fwd_finalize_kernel<<<(C + FIN_X - 1) / FIN_X, dim3(FIN_X, FIN_Y), 0, s>>>(R, C, nblk, part, gamma, beta, run_mean, run_var, training,
-                                                         momentum, eps, scale_shift, scale_shift + C, save_mean,
-                                                         save_rstd);
+  launch_chain(bn_fwd_finalize_kernel, dim3((C + FIN_X - 1) / FIN_X), dim3(FIN_X, FIN_Y), 0, s, training != 0, R, C, nblk,
+               part, gamma, beta, run_mean, run_var, training, momentum, eps, scale_shift, scale_shift + C, save_mean,
+               save_rstd);
   V2F_CHECK_LAUNCH();
   prof_begin(V2F_K_BN_APPLY, s);
   prof_bytes(V2F_K_BN_APPLY, tb * (res ? 3 : 2));
   const uint4 *xp = (const uint4*)x, *rp = (const uint4*)res;
   uint4* yp = (uint4*)y;
   const float *sc = scale_shift, *sh = scale_shift + C;
-#define BN_APPLY(RES_, RELU_) \
-  bn_apply_kernel<RES_, RELU_><<<wave_blocks(bn_apply_kernel<RES_, RELU_>, 0, R, C), BN_THREADS, 0, s>>>(R, C, xp, rp, sc, sh, yp)
+#define BN_APPLY(RES_, RELU_)                                                                                          \
+  launch_chain(bn_apply_kernel<RES_, RELU_>, dim3(wave_blocks(bn_apply_kernel<RES_, RELU_>, 0, R, C)), dim3(BN_THREADS), 0, s, \
+               true, R, C, xp, rp, sc, sh, yp)
   if (res && relu) BN_APPLY(true, true);
   else if (res) BN_APPLY(true, false);
   else if (relu) BN_APPLY(false, true);
@@ -564,12 +606,14 @@ extern "C" int v2f_bn2d_act_bwd(long long R, int C, const void* dy, const void* 
 #undef BN_RED
   prof_end(V2F_K_BN_BWD_REDUCE, s);
   V2F_CHECK_LAUNCH();
-  bn_bwd_finalize_kernel<<<(C + FIN_X - 1) / FIN_X, dim3(FIN_X, FIN_Y), 0, s>>>(R, C, nred, part, gamma, save_mean, save_rstd, training, dgamma, dbeta, coef);
+  launch_chain(bn_bwd_finalize_kernel, dim3((C + FIN_X - 1) / FIN_X), dim3(FIN_X, FIN_Y), 0, s, true, R, C, nred, part, gamma,
+               save_mean, save_rstd, training, dgamma, dbeta, coef);
   V2F_CHECK_LAUNCH();
   prof_begin(V2F_K_BN_BWD_ELEMT, s);
   prof_bytes(V2F_K_BN_BWD_ELEMT, tb * (3 + ((relu && !dz) ? 1 : 0)));
-#define BN_ELEMT(RELU_, HAVE_, SRC_) \
-  bn_bwd_elemt_kernel<RELU_, HAVE_><<<wave_blocks(bn_bwd_elemt_kernel<RELU_, HAVE_>, 0, R, C), BN_THREADS, 0, s>>>(R, C, SRC_, xp, yp, coef, dxp)
+#define BN_ELEMT(RELU_, HAVE_, SRC_)                                                                                  \
+  launch_chain(bn_bwd_elemt_kernel<RELU_, HAVE_>, dim3(wave_blocks(bn_bwd_elemt_kernel<RELU_, HAVE_>, 0, R, C)),        \
+               dim3(BN_THREADS), 0, s, true, R, C, SRC_, xp, yp, coef, dxp)
   if (have_dz && !relu) BN_ELEMT(false, false, (const uint4*)dz);
   else if (relu && dz) BN_ELEMT(true, true, (const uint4*)dz);
   else if (relu) BN_ELEMT(true, false, dyp);
@@ -596,14 +640,16 @@ static int stem_bn_pool(int N, int H, int W, int C, const void* x, const float* 
     bn_stats_kernel<<<nblk, BN_THREADS, smem, s>>>(R, C, (const uint4*)x, part);
     V2F_CHECK_LAUNCH();
   }
-  bn_fwd_finalize_kernel<<<(C + FIN_X - 1) / FIN_X, dim3(FIN_X, FIN_Y), 0, s>>>(R, C, nblk, part, gamma, beta, run_mean, run_var,
-                                                                   training, momentum, eps, scale_shift,
-                                                                   scale_shift + C, save_mean, save_rstd);
+  // after the stem convolution's epilogue statistics (part_blocks > 0) the finalize kernel follows a kernel that does
+  // not signal: a plain launch there
+  launch_chain(bn_fwd_finalize_kernel, dim3((C + FIN_X - 1) / FIN_X), dim3(FIN_X, FIN_Y), 0, s,
+               training != 0 && part_blocks <= 0, R, C, nblk, part, gamma, beta, run_mean, run_var, training, momentum, eps,
+               scale_shift, scale_shift + C, save_mean, save_rstd);
   V2F_CHECK_LAUNCH();
   const int OH = (H - 1) / 2 + 1, OW = (W - 1) / 2 + 1;
   const long long total = (long long)N * OH * OW * (C / 8);
-  bn_relu_maxpool_kernel<<<(unsigned)((total + BN_THREADS - 1) / BN_THREADS), BN_THREADS, 0, s>>>(
-      N, H, W, C, OH, OW, (const uint4*)x, scale_shift, scale_shift + C, (uint4*)y);
+  launch_chain(bn_relu_maxpool_kernel, dim3((unsigned)((total + BN_THREADS - 1) / BN_THREADS)), dim3(BN_THREADS), 0, s, true,
+               N, H, W, C, OH, OW, (const uint4*)x, (const float*)scale_shift, (const float*)(scale_shift + C), (uint4*)y);
   V2F_CHECK_LAUNCH();
   return V2F_OK;
 }

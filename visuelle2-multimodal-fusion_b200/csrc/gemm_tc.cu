@@ -337,20 +337,25 @@ extern "C" int v2f_gemm_tc_batched(int kind, int M, int N, int K, const void* A,
   V2F_TRY(tc_make_map(&mB, kind, B, N, K, ldb, batch, sB, bn));
   cudaStream_t s = (cudaStream_t)stream;
   const int gz = batch * splits;
+  int rc = V2F_OK;
 #define DISPATCH(KIND_)                                      \
   switch (bn) {                                              \
-    case 128: return launch_tc<KIND_, 128>(mA, mB, a, gz, s); \
-    case 64: return launch_tc<KIND_, 64>(mA, mB, a, gz, s);   \
-    case 32: return launch_tc<KIND_, 32>(mA, mB, a, gz, s);   \
-    default: return launch_tc<KIND_, 16>(mA, mB, a, gz, s);   \
+    case 128: rc = launch_tc<KIND_, 128>(mA, mB, a, gz, s); break; \
+    case 64: rc = launch_tc<KIND_, 64>(mA, mB, a, gz, s); break;   \
+    case 32: rc = launch_tc<KIND_, 32>(mA, mB, a, gz, s); break;   \
+    default: rc = launch_tc<KIND_, 16>(mA, mB, a, gz, s); break;   \
   }
+  // roofline leg of bench.py: CUDA events around the launch, 2 M N K flops per problem in the byte counter
+  prof_begin(V2F_K_GEMM_TC, s);
+  prof_bytes(V2F_K_GEMM_TC, 2LL * M * N * K * batch);
   if (kind == 0) {
     DISPATCH(0)
   } else {
     DISPATCH(1)
   }
 #undef DISPATCH
-  return V2F_OK;
+  prof_end(V2F_K_GEMM_TC, s);
+  return rc;
 }
 
 extern "C" int v2f_gemm_tc(int kind, int M, int N, int K, const void* A, long long lda, const void* B,

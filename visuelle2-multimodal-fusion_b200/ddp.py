@@ -112,24 +112,36 @@ class GradReducer:
             h = dist.all_reduce(flat, op=op, group=self.group, async_op=True)
             self.work.append((h, flat, ps))
 
-    def finish(self):
-        """Join: launch buckets that never filled (unused parameters), wait, write the mean back."""
+    def finish(self, copy_back=False):
+        """Join: launch buckets that never filled (unused parameters), wait, hand the mean to ``p.grad``.
+        ``copy_back``: write the mean into the existing ``p.grad`` storage instead of re-pointing ``p.grad`` at the
+        reduced bucket -- needed when that storage is static and owned by someone else (gradients left behind by a
+        CUDA-graph replay: the next replay writes there again)."""
         if self.world > 1:
             for i in range(len(self.buckets)):
                 if not self.launched[i]:
                     self._launch(i)
             import contextlib
+            main = torch.cuda.current_stream() if self.cuda else None
             with (torch.cuda.stream(self.stream) if self.cuda else contextlib.nullcontext()):
                 for h, flat, ps in self.work:
                     h.wait()                      # side stream waits for the collective
                     if not self.avg_in_collective:
                         flat.div_(self.world)
+                    # the averaged gradients are used where they are: p.grad is re-pointed at its slice of the
+                    # reduced bucket (no copy back; inside a captured graph the bucket is static storage of the graph)
                     views, off = [], 0
                     for p in ps:
                         n = p.numel()
-                        views.append(flat[off:off + n].view_as(p.grad))
+                        views.append(flat[off:off + n].view_as(p))
                         off += n
-                    torch._foreach_copy_([p.grad for p in ps], views)      # one multi-tensor launch per bucket
+                    if copy_back:
+                        torch._foreach_copy_([p.grad for p in ps], views)      # one multi-tensor launch per bucket
+                        continue
+                    if self.cuda and not torch.cuda.is_current_stream_capturing():
+                        flat.record_stream(main)          # allocated on the side stream, consumed on the caller's
+                    for p, v in zip(ps, views):
+                        p.grad = v
             if self.cuda:
                 torch.cuda.current_stream().wait_stream(self.stream)
         self._reset()
@@ -140,7 +152,7 @@ class GradReducer:
             for i in range(len(self.buckets)):
                 if not self.launched[i]:
                     self._launch(i)
-        self.finish()
+        self.finish(copy_back=True)
 
     def remove(self):
         for h in self.hooks:

@@ -51,6 +51,8 @@ def _stem_fusable(conv, bn, pool, x):
 
 
 STEM_CONV_TC = os.environ.get("V2F_STEM_CONV", "1") != "0"      # A/B switch: 0 keeps conv1 on the library convolution
+if os.environ.get("V2F_BN_PDL", "1") == "0":                    # A/B switch: BatchNorm chains without programmatic dependent launch
+    _lib.lib().v2f_bn2d_pdl_enable(0)
 _stem_pack_cache = WeakTensorKeyDictionary()                       # conv1.weight -> (version, data_ptr, packed bf16 [64,192])
 
 
