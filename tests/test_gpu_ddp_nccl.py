@@ -55,6 +55,11 @@ def _worker(rank, world, port, q):
                     step(mine)
                 torch.cuda.synchronize()
                 sharded = {k: p.grad.detach().clone() for k, p in m.named_parameters() if p.grad is not None}
+                if mode == "graph":
+                    # a captured graph holds the communicator's kernels: it has to die before the process group does
+                    # (destroy_process_group with the graph alive never returned)
+                    step.close()
+                    del step
                 red.remove()
                 for p in m.parameters():
                     p.grad = None
@@ -154,7 +159,7 @@ def _worker_gtm(rank, world, port, q):
         dist.destroy_process_group()
 
 
-def _collect(q, procs, timeout=600):
+def _collect(q, procs, timeout=240):
     """One result per worker; the first worker error fails the test at once (its peer is killed, not waited for)."""
     out = []
     try:

@@ -3,7 +3,7 @@
 O=gpurun_out/${1:-ab}; VAR=${2:-V2F_BN_PDL}; mkdir -p $O
 timeout 900 python -m pytest tests/test_gpu_trunk.py tests/test_gpu_rnn.py -q -x > $O/pytest.log 2>&1
 echo "pytest rc=$?" > $O/rc.txt; tail -3 $O/pytest.log
-for v in 1 0 1 0; do
+for v in 1 0; do
   env $VAR=$v timeout 600 python bench.py --only-headline --no-cpu-baseline --steps 20 --warmup 5 > $O/bench_$v.json 2> $O/bench_$v.err
   echo "bench $VAR=$v rc=$?" >> $O/rc.txt
   python - <<P

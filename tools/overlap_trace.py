@@ -66,15 +66,9 @@ def main():
         prof.export_chrome_trace(path)
         ev = [e for e in json.load(open(path))["traceEvents"] if e.get("cat") == "kernel"]
         ev.sort(key=lambda e: e["ts"])
-        # split into replays: gaps > 1 ms between consecutive kernels
-        groups, cur = [], [ev[0]]
-        for e in ev[1:]:
-            if e["ts"] - (cur[-1]["ts"] + cur[-1]["dur"]) > 1000:
-                groups.append(cur)
-                cur = []
-            cur.append(e)
-        groups.append(cur)
-        groups = [g for g in groups if len(g) > 500]
+        # split into replays: every replay launches the same kernel sequence
+        per = len(ev) // steps
+        groups = [ev[i * per:(i + 1) * per] for i in range(steps)] if per * steps == len(ev) else [ev]
         print(f"# NCCL all-reduce vs backward overlap inside the graph-replayed step ({world} GPUs, rank 0, torch.profiler/CUPTI)\n")
         print("| replay | kernels | step span ms | NCCL kernels | NCCL busy ms | of it under compute kernels | tail after last compute kernel ms |")
         print("|---:|---:|---:|---:|---:|---:|---:|")
@@ -95,6 +89,8 @@ def main():
                 print(f"* `{e['name'][:60]}` {(e['ts'] - t0) / 1e3:.3f} -> {(e['ts'] + e['dur'] - t0) / 1e3:.3f}")
         last = max(g, key=lambda e: e["ts"] + e["dur"])
         print(f"\nlast kernel of the replay: `{last['name'][:70]}` ends at {(last['ts'] + last['dur'] - t0) / 1e3:.3f} ms")
+    r.close()                        # the graph holds NCCL kernels: it must die before the process group
+    torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -142,6 +142,16 @@ class GraphedTrainStep:
         self.graph.replay()
         return self.static_loss
 
+    def close(self):
+        """Drop the captured graph (and its memory pool).  With a reducer the graph contains the communicator's NCCL
+        kernels: close every graphed step BEFORE ``torch.distributed.destroy_process_group()`` -- destroying the
+        communicator while a graph that captured its kernels is alive does not return."""
+        torch.cuda.synchronize(self.device)
+        self.graph = None
+        self.static_loss = None
+        for p in self.params:
+            p.grad = None
+
     def release(self):
         """Kept for callers of the first version: the module is never left in graph mode any more (the device word
         is installed only around warm-up and capture), so there is nothing to undo."""

@@ -278,33 +278,64 @@ CAST_GROUP_ELEMS = int(os.environ.get("V2F_CAST_GROUP_ELEMS", str(6 << 20)))   #
 _frozen_cache = WeakTensorKeyDictionary()
 
 
+class _LazyCasts(dict):
+    """{conv: bf16 weight} whose trainable entries are produced group by group at FIRST USE.  The autograd engine runs
+    ready nodes in reverse order of creation: a cast node created before the whole forward has the lowest priority of
+    the graph and its backward -- the fp32 weight gradients -- would only run after the last trunk kernel, so every
+    gradient bucket of the trunk would be all-reduced in a tail behind the backward (1.3 ms at 2 GPUs).  Created right
+    before the group's first convolution, the node's backward runs as soon as the group's earliest layer has produced
+    its weight gradient, and ddp.GradReducer's buckets overlap the rest of the backward."""
+
+    def __init__(self, groups):
+        super().__init__()
+        self.group_of = {c: g for g in groups for c in g}
+
+    def __missing__(self, conv):
+        grp = self.group_of.get(conv)
+        if grp is None:
+            raise KeyError(conv)
+        cast = _CastWeights.apply(*[c.weight for c in grp])
+        for c, w in zip(grp, cast):
+            self[c] = w
+        return self[conv]
+
+    def get(self, conv, default=None):
+        try:
+            return self[conv]
+        except KeyError:
+            return default
+
+    def __contains__(self, conv):
+        return dict.__contains__(self, conv) or conv in self.group_of
+
+
 def _bf16_weights(convs):
-    """{conv: bf16 weight} for the convolutions of one trunk forward."""
-    out = {}
+    """{conv: bf16 weight} for the convolutions of one trunk forward (``convs`` in forward order)."""
     # trainable weights are re-cast on EVERY forward, with or without autograd: optim.Adafactor updates them from a
     # CUDA kernel through raw pointers, which does not bump Tensor._version, so a cached copy keyed on the version went
-    # stale after the first no_grad pass (validation / forecast used the weights of that first pass for ever).  Only
+    # stale after the first no_grad pass (validation / forward used the weights of that first pass for ever).  Only
     # frozen weights (requires_grad=False: layer1/layer2 and the stem in the reference) are cached.
     train = [c for c in convs if c.weight.requires_grad]
+    out = {}
     if train:
         if torch.is_grad_enabled():
-            # one multi-tensor cast per group of consecutive layers (~CAST_GROUP_ELEMS weights): a group's fp32
-            # gradients appear as soon as ITS earliest layer's weight gradient exists, not at the very end of the
-            # backward, so ddp.GradReducer's buckets can be all-reduced while the rest of the trunk still runs
-            cast, grp, n = [], [], 0
+            # one multi-tensor cast per group of consecutive layers (~CAST_GROUP_ELEMS weights), issued lazily (see
+            # _LazyCasts): a group's fp32 gradients appear as soon as ITS earliest layer's weight gradient exists
+            groups, grp, n = [], [], 0
             for c in train:
                 grp.append(c)
                 n += c.weight.numel()
                 if n >= CAST_GROUP_ELEMS:
-                    cast.extend(_CastWeights.apply(*[g.weight for g in grp]))
+                    groups.append(grp)
                     grp, n = [], 0
             if grp:
-                cast.extend(_CastWeights.apply(*[g.weight for g in grp]))
+                groups.append(grp)
+            out = _LazyCasts(groups)
         else:
             cast = [torch.empty_like(c.weight, dtype=torch.bfloat16) for c in train]
             torch._foreach_copy_(cast, [c.weight.detach() for c in train])
-        for c, w in zip(train, cast):
-            out[c] = w
+            for c, w in zip(train, cast):
+                out[c] = w
     stale = []
     for c in convs:
         if c in out:
