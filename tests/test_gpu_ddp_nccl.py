@@ -11,6 +11,24 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+def _report_and_die(q, rank, text):
+    """Hand the traceback to the parent, FLUSH the queue's feeder thread (os._exit right after put() loses the message
+    and the parent waits for its whole timeout), then exit without waiting for the peer, which may be blocked in a
+    collective."""
+    q.put((rank, {"error": text}))
+    q.close()
+    q.join_thread()
+    os._exit(1)
+
+
+def _trace(rank, msg):
+    """Progress marks of a worker (V2F_NCCL_TEST_TRACE=<dir>): where a rank is when a collective does not return."""
+    d = os.environ.get("V2F_NCCL_TEST_TRACE")
+    if d:
+        with open(os.path.join(d, f"nccl_test_rank{rank}.log"), "a") as f:
+            f.write(msg + "\n")
+
+
 def _worker(rank, world, port, q):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -38,6 +56,7 @@ def _worker(rank, world, port, q):
         for mode in ("hooks", "graph"):
             for precision in ("fp32", "bf16"):
                 m.precision = precision
+                _trace(rank, f"{mode} {precision}: reducer")
                 red = GradReducer(m, hooks=True)                 # broadcasts rank 0's parameters
                 mine = shard_batch(full, rank, world)
                 for p in m.parameters():
@@ -50,10 +69,13 @@ def _worker(rank, world, port, q):
                     del loss
                 else:
                     torch.manual_seed(54)
+                    _trace(rank, f"{mode} {precision}: capture")
                     step = GraphedTrainStep(m, mine, reducer=red)
                     torch.manual_seed(55)
+                    _trace(rank, f"{mode} {precision}: replay")
                     step(mine)
                 torch.cuda.synchronize()
+                _trace(rank, f"{mode} {precision}: sharded step done")
                 sharded = {k: p.grad.detach().clone() for k, p in m.named_parameters() if p.grad is not None}
                 if mode == "graph":
                     # a captured graph holds the communicator's kernels: it has to die before the process group does
@@ -81,11 +103,11 @@ def _worker(rank, world, port, q):
                     floor = 1e-6 if k.endswith("attn_linear.bias") else 1e-7 * (s + 1e-3)
                     worst = max(worst, (d - floor) / max(s, 1e-30))
                 results[(mode, precision)] = worst
+                _trace(rank, f"{mode} {precision}: compared, worst {worst:.3e}")
         q.put((rank, results))
     except Exception:
         import traceback
-        q.put((rank, {"error": traceback.format_exc()}))
-        os._exit(1)                                 # the peer may be blocked in a collective: do not wait for it
+        _report_and_die(q, rank, traceback.format_exc())
     finally:
         dist.destroy_process_group()
 
@@ -153,18 +175,22 @@ def _worker_gtm(rank, world, port, q):
         q.put((rank, results))
     except Exception:
         import traceback
-        q.put((rank, {"error": traceback.format_exc()}))
-        os._exit(1)
+        _report_and_die(q, rank, traceback.format_exc())
     finally:
         dist.destroy_process_group()
 
 
-def _collect(q, procs, timeout=240):
+def _collect(q, procs, timeout=150):
     """One result per worker; the first worker error fails the test at once (its peer is killed, not waited for)."""
+    import queue
     out = []
     try:
         for _ in procs:
-            rank, res = q.get(timeout=timeout)
+            try:
+                rank, res = q.get(timeout=timeout)
+            except queue.Empty:
+                raise AssertionError(f"no result from the workers within {timeout} s (V2F_NCCL_TEST_TRACE=<dir> shows "
+                                     "where each rank is)") from None
             assert "error" not in res, f"rank {rank}:\n{res['error']}"
             out.append((rank, res))
         for p in procs:

@@ -104,6 +104,11 @@ class GraphedTrainStep:
         self.has_tf = hasattr(model, "draw_tf_mask")
         self._tf = _TfWord(dev) if self.has_tf else None      # owned here, not by the module
         self.params = [p for p in model.parameters() if p.requires_grad]
+        # autograd graphs of earlier eager steps that are only reachable through reference cycles (custom Function
+        # contexts) keep their AccumulateGrad nodes -- bound to the stream of that eager step -- alive until the cyclic
+        # collector runs; a capture that meets one of them fails with "legacy stream depends on a capturing stream"
+        import gc
+        gc.collect()
         side = self.side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side), _tf_installed(model, self._tf):
