@@ -245,3 +245,91 @@ def test_adafactor_structs_match_header(cname, mirror):
         exe = os.path.join(d, "s")
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
         assert int(subprocess.check_output([exe]).decode()) == ctypes.sizeof(cls)
+
+
+def test_lazy_weight_casts_run_their_backward_with_their_own_layers():
+    """trunk._LazyCasts: the multi-tensor cast of a group of trainable convolution weights is created at the group's
+    FIRST USE, so the autograd engine (which runs ready nodes in reverse order of creation) produces the group's fp32
+    weight gradients right after the group's earliest layer -- not after the whole backward, where every gradient
+    bucket of the trunk would be all-reduced in a tail (ddp.GradReducer)."""
+    import torch
+    import torch.nn as nn
+    import torch.nn.functional as F
+    from visuelle2_multimodal_fusion_b200 import trunk
+    torch.manual_seed(1)
+    convs = [nn.Conv2d(3, 4, 3, padding=1, bias=False) for _ in range(1)] + \
+            [nn.Conv2d(4, 4, 3, padding=1, bias=False) for _ in range(5)]
+    old = trunk.CAST_GROUP_ELEMS
+    trunk.CAST_GROUP_ELEMS = 2 * convs[1].weight.numel()          # groups of two layers
+    try:
+        events = []
+        for i, c in enumerate(convs):
+            c.weight.register_post_accumulate_grad_hook(lambda p, i=i: events.append(("wgrad", i)))
+        w16 = trunk._bf16_weights(convs)
+        assert isinstance(w16, trunk._LazyCasts) and len(w16) == 0          # nothing cast yet
+        x = torch.randn(2, 3, 6, 6).to(torch.bfloat16).requires_grad_(True)
+        y = x
+        for i, c in enumerate(convs):
+            y = F.conv2d(y, w16.get(c), None, c.stride, c.padding)
+            y.register_hook(lambda g, i=i: events.append(("act", i)))        # fires when layer i+1's backward is done
+        y.float().square().sum().backward()
+    finally:
+        trunk.CAST_GROUP_ELEMS = old
+    pos = {e: k for k, e in enumerate(events)}
+    groups = {id(g): [convs.index(c) for c in g] for g in w16.group_of.values()}.values()
+    assert len(groups) >= 3
+    for g in groups:
+        m = min(g)
+        if m == 0:
+            continue
+        # ("act", i) fires when layer i's backward is about to start: every weight gradient of the group is out after
+        # its earliest layer m has run and BEFORE layer m-1's backward starts
+        assert all(pos[("act", m)] < pos[("wgrad", j)] < pos[("act", m - 1)] for j in g), (g, events)
+    ref = [c.weight.grad.clone() for c in convs]
+    for c in convs:
+        c.weight.grad = None
+    y = x
+    for c in convs:
+        y = F.conv2d(y, c.weight.to(torch.bfloat16), None, c.stride, c.padding)
+    y.float().square().sum().backward()
+    for c, g in zip(convs, ref):
+        assert torch.equal(g, c.weight.grad)
+
+
+def test_stem_weight_packing_is_the_k_layout_of_the_header():
+    """trunk._stem_packed_weight: wpk[o, kh*24 + kw*3 + c] = w[o,c,kh,kw], zero elsewhere (include/v2f.h,
+    v2f_stem_conv_fwd) -- and a GEMM over patches gathered the way csrc/stem_conv.cu gathers them (whole rows staged
+    with the zero padding baked in at offset 9, 24-value windows starting at 6*ow) IS the 7x7 / stride 2 / pad 3
+    convolution."""
+    import torch
+    import torch.nn as nn
+    from visuelle2_multimodal_fusion_b200 import trunk
+    torch.manual_seed(2)
+    conv = nn.Conv2d(3, 64, 7, 2, 3, bias=False)
+    pk = trunk._stem_packed_weight(conv)
+    assert pk.shape == (64, 192) and pk.dtype == torch.bfloat16
+    w = conv.weight.detach().to(torch.bfloat16)
+    for o, c, kh, kw in [(0, 0, 0, 0), (5, 2, 3, 6), (63, 1, 6, 2)]:
+        assert pk[o, kh * 24 + kw * 3 + c] == w[o, c, kh, kw]
+    mask = torch.ones(192, dtype=torch.bool)
+    for kh in range(7):
+        mask[kh * 24:kh * 24 + 21] = False
+    assert bool((pk[:, mask] == 0).all())
+    N, H, W = 1, 15, 17
+    x = torch.randn(N, 3, H, W).to(torch.bfloat16)
+    OH, OW = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    rowlen = max(6 * (OW - 1) + 24, 9 + 3 * W)
+    rows = torch.zeros(N * H + 1, rowlen, dtype=torch.float64)
+    rows[:N * H, 9:9 + 3 * W] = x.double().permute(0, 2, 3, 1).reshape(N * H, 3 * W)
+    out = torch.zeros(N, 64, OH, OW, dtype=torch.float64)
+    for oh in range(OH):
+        for ow in range(OW):
+            a = torch.zeros(192, dtype=torch.float64)
+            for kc in range(21):
+                kh, c = divmod(kc, 3)
+                ih = 2 * oh - 3 + kh
+                src = rows[-1] if (ih < 0 or ih >= H) else rows[ih]
+                a[kc * 8:kc * 8 + 8] = src[6 * ow + 8 * c:6 * ow + 8 * c + 8]
+            out[0, :, oh, ow] = pk.double() @ a
+    ref = torch.nn.functional.conv2d(x.double(), w.double(), None, 2, 3)
+    assert float((out - ref).abs().max()) < 1e-9

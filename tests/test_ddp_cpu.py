@@ -46,6 +46,21 @@ def _worker(rank, world, port, out):
         red.finish()
     if rank == 0:
         torch.save({k: (p.grad.clone() if p.grad is not None else None) for k, p in m.named_parameters()}, out)
+    # finish() hands the mean over by re-pointing p.grad at its slice of the reduced bucket; reduce_now() -- gradients
+    # left in static storage by a CUDA-graph replay -- must write INTO that storage instead
+    red.remove()
+    red2 = GradReducer(m, bucket_bytes=64, hooks=False)
+    m.zero_grad(set_to_none=True)
+    (xs, ys), _ = shard_batch(((x, y), x), rank, world)
+    ((m(xs) - ys) ** 2).mean().backward()
+    static = {k: p.grad for k, p in m.named_parameters() if p.grad is not None}
+    ptrs = {k: g.data_ptr() for k, g in static.items()}
+    red2.reduce_now()
+    for k, p in m.named_parameters():
+        if p.grad is not None:
+            assert p.grad is static[k] and p.grad.data_ptr() == ptrs[k], k
+    if rank == 0:
+        torch.save({k: (p.grad.clone() if p.grad is not None else None) for k, p in m.named_parameters()}, out + ".now")
     dist.destroy_process_group()
 
 
@@ -58,8 +73,10 @@ def test_bucketed_allreduce_matches_global_batch(tmp_path):
     x = torch.randn(8, 6)
     y = torch.randn(8, 3)
     ((m(x) - y) ** 2).mean().backward()
+    now = torch.load(out + ".now")
     for k, p in m.named_parameters():
         if p.grad is None:
-            assert got[k] is None, k
+            assert got[k] is None and now[k] is None, k
         else:
             assert torch.allclose(got[k], p.grad, atol=1e-6), k
+            assert torch.allclose(now[k], p.grad, atol=1e-6), k
