@@ -36,7 +36,6 @@ namespace v2f {
 constexpr int SC_THREADS = 256;
 constexpr int SC_COUT = 64;
 constexpr int SC_RUN = 24;                     // 7 kernel columns x 3 channels = 21 values, padded to 24
-constexpr int SC_CHUNKS = 21;                  // 16-byte chunks (8 bf16) of real K per pixel: 7 rows x 3
 constexpr int SC_KSTEPS = 11;                  // 176 / 16
 constexpr int SC_KPAD = 192;                   // 3 swizzle atoms of 64
 constexpr int SC_A_ATOM = 128 * 128;           // bytes: 128 pixels x 64 bf16
@@ -112,16 +111,35 @@ __device__ __forceinline__ void sc_pix_adv(const ScArgs& a, ScPix& px) {
   }
 }
 
+// the three 16-byte chunks of kernel row kh of one pixel: staged row (or the zero row) -> swizzled A tile
+__device__ __forceinline__ void sc_gather_row(const __nv_bfloat16* colbase, int rowlen, int H, int ih0, int gbase,
+                                              uint8_t* dbase, uint32_t r7s, int kh) {
+  const int ih = ih0 + kh;
+  const int slot = (ih < 0 || ih >= H) ? SC_NSLOT : ((gbase + kh) & (SC_NSLOT - 1));
+  const uint32_t* s32 = reinterpret_cast<const uint32_t*>(colbase + slot * rowlen);
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    const int kc = kh * 3 + c;
+    uint4 v;
+    v.x = s32[4 * c + 0];
+    v.y = s32[4 * c + 1];
+    v.z = s32[4 * c + 2];
+    v.w = s32[4 * c + 3];
+    *reinterpret_cast<uint4*>(dbase + (kc >> 3) * SC_A_ATOM + (((uint32_t)(kc & 7) << 4) ^ r7s)) = v;
+  }
+}
+
 template <bool IN_BF16, bool NCHW>
 __global__ void __launch_bounds__(SC_THREADS, 2) stem_conv_kernel(const ScArgs a) {
   extern __shared__ uint8_t sc_smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(sc_smem_raw) + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment by OFFSET from the shared array (pointer arithmetic keeps the shared state space: rounding the
+  // pointer through an integer made every access below a generic LD / ST instead of LDS / STS)
+  uint8_t* smem = sc_smem_raw + ((1024u - (smem_u32(sc_smem_raw) & 1023u)) & 1023u);
   uint8_t* sA = smem;
   uint8_t* sB = smem + SC_A_BYTES;
   __nv_bfloat16* rows = reinterpret_cast<__nv_bfloat16*>(smem + SC_A_BYTES + SC_B_BYTES);   // [SC_NSLOT + 1][rowlen]
   const int rowlen = a.rowlen;
-  uint8_t* tail = reinterpret_cast<uint8_t*>(rows + (SC_NSLOT + 1) * rowlen);      // slot SC_NSLOT stays zero
-  tail = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tail) + 15) & ~(uintptr_t)15);
+  uint8_t* tail = reinterpret_cast<uint8_t*>(rows + (SC_NSLOT + 1) * rowlen);      // slot SC_NSLOT stays zero; rowlen % 8 == 0: 16-byte aligned
   uint64_t* bar = reinterpret_cast<uint64_t*>(tail);
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tail + 8);
   float* red = reinterpret_cast<float*>(tail + 16);                                       // [2][4][64]
@@ -223,29 +241,22 @@ __global__ void __launch_bounds__(SC_THREADS, 2) stem_conv_kernel(const ScArgs a
     }
     __syncthreads();
 
-    // ---- gather the A tile: thread = (pixel r, half of the 21 chunks)
+    // ---- gather the A tile: thread = (pixel r, kernel rows 0..3 | 4..6); chunk indices are compile-time constants in
+    // each half, so a chunk costs 4 shared loads at immediate offsets, one XOR for the swizzle and one 16-byte store
     {
-      const int r = tid & 127, hf = tid >> 7;
+      const int r = tid & 127;
       if (t * 128 + r < P) {
-        const int kc0 = hf ? 11 : 0, kc1 = hf ? SC_CHUNKS : 11;
         const int gbase = pxr.n * a.H + 2 * pxr.oh - 3;
         const int ih0 = 2 * pxr.oh - 3;
         const __nv_bfloat16* colbase = rows + 6 * pxr.ow;
-        int kh = hf ? 3 : 0, c = hf ? 2 : 0;               // chunk 11 = (kh 3, c 2)
-        for (int kc = kc0; kc < kc1; kc++) {
-          const int ih = ih0 + kh;
-          const int slot = (ih < 0 || ih >= a.H) ? SC_NSLOT : ((gbase + kh) & (SC_NSLOT - 1));
-          const uint32_t* s32 = reinterpret_cast<const uint32_t*>(colbase + slot * rowlen + 8 * c);
-          uint4 v;
-          v.x = s32[0];
-          v.y = s32[1];
-          v.z = s32[2];
-          v.w = s32[3];
-          *reinterpret_cast<uint4*>(sA + (kc >> 3) * SC_A_ATOM + sc_swz(r, kc & 7)) = v;
-          if (++c == 3) {
-            c = 0;
-            ++kh;
-          }
+        uint8_t* dbase = sA + (r >> 3) * 1024 + (r & 7) * 128;
+        const uint32_t r7s = (uint32_t)(r & 7) << 4;
+        if (tid < 128) {
+#pragma unroll
+          for (int kh = 0; kh < 4; kh++) sc_gather_row(colbase, rowlen, a.H, ih0, gbase, dbase, r7s, kh);
+        } else {
+#pragma unroll
+          for (int kh = 4; kh < 7; kh++) sc_gather_row(colbase, rowlen, a.H, ih0, gbase, dbase, r7s, kh);
         }
       }
     }
@@ -327,6 +338,8 @@ __global__ void __launch_bounds__(SC_THREADS, 2) stem_conv_kernel(const ScArgs a
 #pragma unroll
         for (int i = 0; i < 32; i++) g[i] = f[i] * f[i];
         // transposing butterfly: after the step with offset o a lane keeps the half of its values selected by its bit o
+        // (measured against a transposition through the free A buffer -- 8 STS.128 + 32 LDS + a CTA barrier per
+        // thread and tile: 71 us per launch instead of 50)
 #pragma unroll
         for (int o = 16; o >= 1; o >>= 1) {
           const bool up = (lane & o) != 0;
