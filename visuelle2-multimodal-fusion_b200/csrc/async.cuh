@@ -8,6 +8,12 @@ namespace v2f {
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
+// Round a pointer into the dynamic shared-memory array up to `align` bytes BY OFFSET: pointer arithmetic on the
+// __shared__ symbol keeps the shared state space, so the accesses compile to LDS / STS.  (Rounding through uintptr_t
+// yields a generic pointer and every access becomes a generic LD / ST.)
+__device__ __forceinline__ uint8_t* smem_align(uint8_t* p, uint32_t align) {
+  return p + ((align - (smem_u32(p) & (align - 1))) & (align - 1));
+}
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }

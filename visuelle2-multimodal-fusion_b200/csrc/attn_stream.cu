@@ -55,7 +55,7 @@ attn_stream_fwd_kernel(StreamArgs sa) {
   constexpr int STG = stream_stages(E);
   constexpr int TILE = ST_CH * E;                       // floats per operand per stage
   extern __shared__ uint8_t raw[];
-  float* ring = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(raw) + 127) & ~uintptr_t(127));
+  float* ring = reinterpret_cast<float*>(smem_align(raw, 128));
   uint64_t* full = reinterpret_cast<uint64_t*>(ring + (size_t)STG * 2 * TILE);
   uint64_t* empty = full + STG;
   float* e_sh = reinterpret_cast<float*>(empty + STG);  // [2][ST_CH]
@@ -243,7 +243,7 @@ attn_stream_bwd_kernel(StreamBwdArgs sa) {
   constexpr int STG = stream_stages(E);
   constexpr int TILE = ST_CH * E;
   extern __shared__ uint8_t raw[];
-  float* ring = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(raw) + 127) & ~uintptr_t(127));
+  float* ring = reinterpret_cast<float*>(smem_align(raw, 128));
   uint64_t* full = reinterpret_cast<uint64_t*>(ring + (size_t)STG * 2 * TILE);
   uint64_t* empty = full + STG;
   float* e_sh = reinterpret_cast<float*>(empty + STG);  // [2][ST_CH]

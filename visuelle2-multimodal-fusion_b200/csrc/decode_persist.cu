@@ -295,11 +295,11 @@ decode_persist_fwd_kernel(const __grid_constant__ DpArgs a) {
   const int G = gridDim.x, c = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-  float* W1 = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(raw) + 127) & ~uintptr_t(127));
+  float* W1 = reinterpret_cast<float*>(smem_align(raw, 128));
   float* W3 = W1 + DP_NT1 * 8 * PH;
   float* W5 = W3 + DP_NT3 * 8 * PE;
   float* ring = W5 + DP_NT5 * 8 * PE;                       // 2 groups x DP_SLOTS x SLOT floats; product scratch
-  ring = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ring) + 127) & ~uintptr_t(127));
+  ring = reinterpret_cast<float*>(smem_align(reinterpret_cast<uint8_t*>(ring), 128));
   constexpr int SCRATCH = dp_stages(TC) * DP_MB * DP_XP + (TC ? 2 : 4) * DP_MB * DP_NT1 * 8;   // product staging + partials
   constexpr int AREA = 2 * DP_SLOTS * SLOT > SCRATCH ? 2 * DP_SLOTS * SLOT : SCRATCH;
   uint64_t* full = reinterpret_cast<uint64_t*>(ring + AREA);                 // [2][DP_SLOTS]

@@ -172,7 +172,7 @@ decode_team_fwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_co
   const int n_own = n0 + c;                       // the row this CTA owns in the row-local phases
   const bool own = n_own < N;
 
-  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sm = smem_align(raw, 1024);
   uint8_t* Wsm = sm;                                            // [8 chunks][80 rows][128 B], swizzled by TMA
   uint8_t* ring = sm + DT_WBYTES;                               // B ring / tile rings
   float* stage1 = reinterpret_cast<float*>(ring + DT_RING);     // [48][65]: S columns and GH of the team's rows
@@ -937,7 +937,7 @@ decode_team_bwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_co
   const int n_own = n0 + c;
   const bool own = n_own < N;
 
-  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sm = smem_align(raw, 1024);
   uint8_t* Wsm = sm;                                            // [80 chunks][8 rows][128 B]
   uint8_t* ring = sm + DT_WBYTES;                               // A ring (products) / tile ring (sweep)
   float* stage = reinterpret_cast<float*>(ring + DT_RING);      // [64][9] dh columns of the team's rows; 16 KB slack before it is read by MMA overrun

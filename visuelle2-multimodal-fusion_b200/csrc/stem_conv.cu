@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(SC_THREADS, 2) stem_conv_kernel(const ScArgs a
   extern __shared__ uint8_t sc_smem_raw[];
   // 1024-byte alignment by OFFSET from the shared array (pointer arithmetic keeps the shared state space: rounding the
   // pointer through an integer made every access below a generic LD / ST instead of LDS / STS)
-  uint8_t* smem = sc_smem_raw + ((1024u - (smem_u32(sc_smem_raw) & 1023u)) & 1023u);
+  uint8_t* smem = smem_align(sc_smem_raw, 1024);
   uint8_t* sA = smem;
   uint8_t* sB = smem + SC_A_BYTES;
   __nv_bfloat16* rows = reinterpret_cast<__nv_bfloat16*>(smem + SC_A_BYTES + SC_B_BYTES);   // [SC_NSLOT + 1][rowlen]
