@@ -1,5 +1,5 @@
 #!/bin/bash
-O=gpurun_out/r02stem3; mkdir -p $O
+O=gpurun_out/${1:-stem}; mkdir -p $O
 timeout 600 python -m pytest tests/test_gpu_trunk.py -q -x -k "stem" > $O/pytest_stem.log 2>&1
 echo "stem pytest rc=$?" > $O/rc.txt
 tail -5 $O/pytest_stem.log
