@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     assert len(names) >= 12
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/v2f.h but not exported"
-    assert lib.v2f_version() == 3
+    assert lib.v2f_version() == 4
 
 
 def test_decode_params_struct_matches_header():

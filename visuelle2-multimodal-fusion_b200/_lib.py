@@ -10,7 +10,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libv2f_b200.so")
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 _lib = None
 

@@ -10,7 +10,7 @@
 #include "common.cuh"
 
 long long g_v2f_launches = 0;
-extern "C" int v2f_version(void) { return 3; }
+extern "C" int v2f_version(void) { return 4; }   // 4: v2f_decode_params gained team_ws / team_ws_floats
 extern "C" long long v2f_launch_count(void) { return g_v2f_launches; }
 
 namespace v2f {

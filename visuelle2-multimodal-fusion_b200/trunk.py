@@ -60,14 +60,18 @@ def _stem_packed_weight(conv):
     """conv1.weight [64,3,7,7] as the K-major operand of csrc/stem_conv.cu: wpk[o, kh*24 + kw*3 + c], zero-padded to
     [64,192] bf16.  Cached while the (frozen) weight is unchanged."""
     w = conv.weight
-    hit = _stem_pack_cache.get(w)
+    # like the bf16 weight copies: only a FROZEN weight is cached (optim.Adafactor updates trainable parameters through
+    # raw pointers without bumping Tensor._version, so a cached pack of a trainable conv1 would go stale unnoticed)
+    frozen = not w.requires_grad
+    hit = _stem_pack_cache.get(w) if frozen else None
     if hit is not None and hit[0] == w._version and hit[1] == w.data_ptr():
         return hit[2]
     with torch.no_grad():
         k = w.detach().to(torch.bfloat16).permute(0, 2, 3, 1).reshape(64, 7, 21)      # [o, kh, kw*3 + c]
         pk = torch.zeros(64, 192, device=w.device, dtype=torch.bfloat16)
         pk[:, :168].view(64, 7, 24)[:, :, :21] = k
-    _stem_pack_cache[w] = (w._version, w.data_ptr(), pk)
+    if frozen:
+        _stem_pack_cache[w] = (w._version, w.data_ptr(), pk)
     return pk
 
 
