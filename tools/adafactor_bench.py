@@ -16,7 +16,7 @@ def main():
     from transformers.optimization import Adafactor as Ref
     from visuelle2_multimodal_fusion_b200 import _lib
     from visuelle2_multimodal_fusion_b200.optim import Adafactor
-    model = bench._build_model("cuda:0", "bf16")
+    model = bench._build_model("rnn210", "cuda:0", "bf16")
     params = [p for p in model.parameters() if p.requires_grad]
     g = torch.Generator(device="cuda").manual_seed(0)
     print(f"{len(params)} trainable tensors, {sum(p.numel() for p in params) / 1e6:.1f} M scalars")

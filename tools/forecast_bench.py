@@ -13,10 +13,10 @@ sys.path.insert(0, ROOT)
 def main():
     import bench
     from visuelle2_multimodal_fusion_b200.graphs import GraphedForecast
-    model = bench._build_model("cuda:0", "bf16").eval()
+    model = bench._build_model("rnn210", "cuda:0", "bf16").eval()
     model.on_validation_epoch_start()
     for B in [int(a) for a in sys.argv[1:]] or [1, 16, 128]:
-        d, im = bench._batch(B, seed=3)
+        d, im = bench._batch("rnn210", B, seed=3)
         inputs = tuple(t.cuda() for t in d) + (im.cuda(),)
         fc = GraphedForecast(model, inputs)
         res = {}

@@ -4,10 +4,10 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import bench
 dev = "cuda:0"
-model = bench._build_model(dev, "bf16")
+model = bench._build_model("rnn210", dev, "bf16")
 res = []
 for s in (21, 22):
-    d, im = bench._batch(128, seed=s)
+    d, im = bench._batch("rnn210", 128, seed=s)
     res.append((tuple(t.to(dev) for t in d), im.to(dev)))
 params = [p for p in model.parameters() if p.requires_grad]
 mode = sys.argv[1] if len(sys.argv) > 1 else "lag1"

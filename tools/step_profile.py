@@ -7,8 +7,8 @@ import bench
 
 rows = int(sys.argv[sys.argv.index("--rows") + 1]) if "--rows" in sys.argv else 45
 dev = "cuda:0"
-model = bench._build_model(dev, "bf16")
-d, im = bench._batch(128, seed=21)
+model = bench._build_model("rnn210", dev, "bf16")
+d, im = bench._batch("rnn210", 128, seed=21)
 batch = (tuple(t.to(dev) for t in d), im.to(dev))
 params = [p for p in model.parameters() if p.requires_grad]
 

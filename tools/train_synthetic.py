@@ -24,11 +24,11 @@ def main():
     from visuelle2_multimodal_fusion_b200.data import DevicePrefetcher
     from visuelle2_multimodal_fusion_b200.graphs import GraphedTrainStep
     dev = "cuda:0"
-    model = bench._build_model(dev, "bf16")
+    model = bench._build_model("rnn210", dev, "bf16")
     model.train()
     model.on_train_epoch_start()
     opt = model.configure_optimizers()[0]
-    host = [bench._batch(args.batch, seed=100 + i, pin=True) for i in range(4)]
+    host = [bench._batch("rnn210", args.batch, seed=100 + i, pin=True) for i in range(4)]
     example = (tuple(t.to(dev) for t in host[0][0]), host[0][1].to(dev))
     step = GraphedTrainStep(model, example)
 
