@@ -825,10 +825,14 @@ def run_product(args):
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if args.precision == "bf16" else "fp32", "data": "synthetic",
             "config": _config("rnn210", B, world),
-            "execution": {"precision": {"backbone": "bf16 channels_last: torchvision modules, cuDNN convolutions; BatchNorm + residual add + "
-                                                    "ReLU (+ stem max-pool) as fused HBM sweeps of libv2f_b200.so (csrc/bn_act.cu)"
+            "execution": {"precision": {"backbone": "bf16 channels_last: torchvision modules, cuDNN convolutions except the stem (conv1 as a "
+                                                    "tcgen05 implicit GEMM reading the fp32 NCHW images in place, BatchNorm statistics from its "
+                                                    "epilogue: csrc/stem_conv.cu); BatchNorm + residual add + ReLU (+ stem max-pool) as fused HBM "
+                                                    "sweeps of libv2f_b200.so (csrc/bn_act.cu)"
                                         if args.precision == "bf16" else "fp32 torchvision/cuDNN, untouched",
-                                        "head": ("tcgen05 GEMMs: bf16 on backbone features, tf32 elsewhere; fp32 state, softmax and gates"
+                                        "head": ("decode loop and its BPTT as one persistent cooperative launch each with the products on "
+                                                 "tcgen05 and bf16 attention tiles (csrc/decode_team.cu); tcgen05 GEMMs: bf16 on backbone "
+                                                 "features, tf32 elsewhere; fp32 state, softmax and gates"
                                                  if args.precision == "bf16" else "fp32 CUDA-core kernels") + " (libv2f_b200.so)"},
                           "step": ("whole step (fwd + loss + bwd" + (" + bucketed NCCL gradient all-reduce on a side stream"
                                                                       if (world > 1 and graph_nccl) else "") +
