@@ -504,9 +504,10 @@ struct TileGradArgs {
 };
 
 // Thread = up to CPTG columns (x, x + 256, ...): the 13 tile values of each stay in registers for all T*W (step, row)
-// pairs of the item, so H is read once and dH / dV are written once.  The kernel is MUFU-bound, not HBM-bound
-// (B*L*E*T tanh evaluations): in tensor-core mode the single-instruction tanh.approx (the forward's choice there)
-// halves the MUFU work; the exact mode keeps the two-instruction form.
+// pairs of the item, so H is read once and dH / dV are written once.  Its floor is the MUFU pipe, not HBM: B*L*E*T tanh
+// evaluations at 16 per clock and SM (tools/probes/mufu_probe.cu: tanh.approx = ex2.approx = 31.2 G/s/SM) = 21.6 us for
+// the two launches of a step (measured: 68 us); in tensor-core mode the single-instruction tanh.approx (the forward's choice there) halves
+// the MUFU work; the exact mode keeps the two-instruction form.
 constexpr int TG_CHUNK = 32;   // (step, row) pairs whose attention scalars are staged at once
 template <bool APPROX, int CPTG>
 __global__ void __launch_bounds__(256)
@@ -544,6 +545,7 @@ tilegrad_kernel(TileGradArgs a) {
         de_sh[ii][jj] = jj < nj ? a.DE[tn * L + j0 + jj] : 0.f;
       }
       __syncthreads();
+      // (loading pair ii + 1 into a second register set before computing pair ii was measured SLOWER: 41.9 vs 34.2 us)
 #pragma unroll 2
       for (int ii = 0; ii < cn; ii++) {
         const int it = c0 + ii, t = it / a.W, wi = it - t * a.W;
